@@ -1,0 +1,132 @@
+"""CPU: host-side mirror of the reference interface -- Runtime registry, wrapper windowing/stitching
+(models/tts/waveglow.py:61-164), weight files, utterance sharding."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle.waveglow_oracle import get_steps, wrapper_infer
+from text_to_speech_b200 import sharding
+from text_to_speech_b200.runtime import Runtime, build_runtime, _runtimes
+from text_to_speech_b200.waveglow import WaveGlow, _get_steps
+from text_to_speech_b200.weights import (WaveGlowHParams, generate_weights, load_weights, save_weights,
+                                         weight_names, weights_digest)
+
+
+def test_unknown_runtime_raises_like_the_reference():
+    # utils/keras/runtimes/__init__.py:24-27
+    with pytest.raises(ValueError, match="Unsupported runtime"):
+        build_runtime("nope", "x.npz")
+    assert "b200" in _runtimes and issubclass(_runtimes["b200"], Runtime)
+
+
+def test_runtime_engine_cache_contract():
+    # runtime.py:20-29: engines cached per path, `reload` forces a new load, `engine=` bypasses both
+    loads = []
+
+    class Dummy(Runtime):
+        _engines = {}
+
+        def __call__(self, x):
+            return self.engine
+
+        @staticmethod
+        def load_engine(path, **kw):
+            loads.append(path)
+            return object()
+
+    a, b = Dummy("p"), Dummy("p")
+    assert a.engine is b.engine and loads == ["p"]
+    c = Dummy("p", reload=True)
+    assert c.engine is not a.engine and loads == ["p", "p"]
+    d = Dummy("q", engine="E")
+    assert d.engine == "E" and loads == ["p", "p"]
+    assert repr(a) == "<Dummy path=p>"
+
+
+@pytest.mark.parametrize("length,win,hop", [(100, 50, 40), (1000, 256, 192), (257, 256, 192), (300, 300, 100)])
+def test_get_steps_matches_reference_formula(length, win, hop):
+    a, b = _get_steps(length, win, hop), get_steps(length, win, hop)
+    assert list(a) == list(b)
+    assert a[0] == 0 and (len(a) == 1 or a[-1] == length - win)
+
+
+class _FakeRuntime:
+    """Deterministic stand-in vocoder: sample s of frame t = mel[t, 0] * 1000 + position in window."""
+    def __call__(self, mel, **kw):
+        mel = np.asarray(mel)
+        B, T, _ = mel.shape
+        base = np.repeat(mel[:, :, 0], 256, axis=1) * 1000.0
+        return base + np.arange(T * 256)[None] * 1e-3
+
+
+def _wrapper_with_fake():
+    w = WaveGlow.__new__(WaveGlow)
+    w.runtime, w.pad_mel_value, w.model = "b200", -11.0, _FakeRuntime()
+    return w
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(win_len=128), dict(win_len=64, hop_len=-16), dict(win_len=128, batch=True),
+                                dict(win_len=0.5), dict(win_len=512),
+                                dict(win_len=512, force_pad=True), dict(win_len=100, hop_len=0.5, max_win_len=80)])
+def test_wrapper_windowing_matches_reference_restatement(kw):
+    rng = np.random.default_rng(0)
+    mel = rng.normal(size=(1, 200, 80)).astype(np.float32)
+    got = _wrapper_with_fake()(mel, **kw)
+    want = wrapper_infer(_FakeRuntime(), mel, **kw)
+    assert got.shape == want.shape and np.array_equal(got, want)
+
+
+def test_wrapper_accepts_2d_and_batches():
+    rng = np.random.default_rng(1)
+    w = _wrapper_with_fake()
+    mel2 = rng.normal(size=(50, 80)).astype(np.float32)
+    assert w(mel2).shape == (1, 50 * 256)
+    melb = rng.normal(size=(3, 300, 80)).astype(np.float32)
+    assert w(melb, win_len=128).shape == (3, 300 * 256)      # batch > 1: direct inference (waveglow.py:108-112)
+
+
+def test_weight_file_roundtrip(tmp_path):
+    hp = WaveGlowHParams(n_flows=4, n_early_every=2, n_layers=2, n_channels=16)
+    w = generate_weights(hp, 3, bias_std=0.1)
+    p = tmp_path / "w.npz"
+    save_weights(p, hp, w)
+    hp2, w2 = load_weights(p)
+    assert hp2 == hp and weights_digest(w2) == weights_digest(w)
+    assert [n for n, _ in weight_names(hp)] == sorted(w, key=[n for n, _ in weight_names(hp)].index)
+
+
+def test_flow_schedule_matches_reference_topology():
+    # waveglow_arch.py:202-223 with NVIDIA hparams: flows 0-3 (4/8), 4-7 (3/6), 8-11 (2/4)
+    fc = WaveGlowHParams().flow_channels()
+    assert fc[:4] == [(4, 8)] * 4 and fc[4:8] == [(3, 6)] * 4 and fc[8:] == [(2, 4)] * 4
+    assert WaveGlowHParams().n_remaining_channels == 4
+
+
+def test_lpt_sharding_covers_everything_once_and_balances():
+    rng = np.random.default_rng(5)
+    lengths = rng.integers(172, 1724, size=1024)
+    for ws in (1, 2, 4, 8):
+        shards = sharding.assign_utterances(lengths, ws)
+        flat = sorted(i for s in shards for i in s)
+        assert flat == list(range(1024))
+        loads = [int(lengths[s].sum()) for s in shards]
+        assert max(loads) - min(loads) <= lengths.max()
+    batches = sharding.make_batches(shards[0], lengths, max_frames=16 * 860)
+    assert sorted(i for b in batches for i in b.indices) == sorted(shards[0])
+    assert all(len(b.indices) * b.T <= 16 * 860 or len(b.indices) == 1 for b in batches)
+    assert all(b.T == max(lengths[i] for i in b.indices) for b in batches)
+    assert sharding.padding_waste(batches, lengths) < 0.12
+
+
+def test_global_batch_plan_is_balanced_and_tight():
+    rng = np.random.default_rng(5)
+    lengths = rng.integers(172, 1724, size=1024)
+    for ws in (1, 2, 4, 8):
+        plan = sharding.plan_batches(lengths, ws, max_frames=16 * 860)
+        flat = sorted(i for r in plan for b in r for i in b.indices)
+        assert flat == list(range(1024))
+        loads = [sum(b.T * len(b.indices) for b in r) for r in plan]
+        assert (max(loads) - min(loads)) / max(loads) < 0.03
+        assert sharding.padding_waste([b for r in plan for b in r], lengths) < 0.02
+        assert plan == sharding.plan_batches(lengths, ws, max_frames=16 * 860)   # deterministic

@@ -1,0 +1,725 @@
+// libwg_b200.so -- host side of the C ABI declared in include/wg_b200.h.
+// Weight repacking (Keras layouts -> kernel layouts), workspace carving, launch sequence of
+// WaveGlow.infer (architectures/waveglow_arch.py:244-306) and the C entry points.
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/wg_b200.h"
+#include "common.cuh"
+#include "simt_kernels.cuh"
+#include "tc_kernels.cuh"
+
+namespace {
+
+using namespace wg;
+
+constexpr int HOP = 256;         // upsample stride (waveglow_arch.py:197)
+constexpr int UPSAMPLE_K = 1024; // upsample kernel size
+
+std::mutex g_err_mu;
+std::string g_create_err;
+
+#define CK WG_CK
+
+struct FlowW {
+  int n_half = 0, n_rem = 0;
+  float* Wstart = nullptr;  // [n_half, C]
+  float* bstart = nullptr;  // [C]
+  float* Wend8 = nullptr;   // [C, 8] zero padded   (fp32 mode)
+  float* bend8 = nullptr;   // [8]
+  float bse8[8] = {0};      // bf16 mode: bend + sum_i bskip_i @ Wend (host copy, passed inline)
+  float winv[64];
+};
+
+struct LayerW {
+  // fp32 mode
+  float* Wcat = nullptr;  // [3C+S, 2C] gate-interleaved columns
+  float* bcat = nullptr;  // [2C]
+  float* Wrs = nullptr;   // [C, rs_cols]
+  float* brs = nullptr;   // [rs_cols]
+  int rs_cols = 0;
+  // bf16 mode (fp32 side arrays; the bf16 matrices live in the stacked arrays below)
+  float* b1 = nullptr;    // [2C] chunk-packed order
+  float* b2 = nullptr;    // [C]
+  float* Wse = nullptr;   // [C, 8] = Wskip @ Wend (fp32)
+};
+
+}  // namespace
+
+struct wg_engine {
+  wg_config cfg{};
+  int device = 0;
+  int C = 0, S = 0, R = 0;  // channels, spect channels (n_mel*n_group), time-groups per frame
+  std::vector<FlowW> flows;
+  std::vector<LayerW> layers;  // [flow * n_layers + i]
+  float* Wup = nullptr;        // fp32: [4*n_mel, R*S]
+  float* bup = nullptr;        // [R*S]
+  // bf16 mode stacked operand matrices (K-major)
+  __nv_bfloat16* Wup16 = nullptr;  // [R*S, Kup_pad]
+  __nv_bfloat16* W1 = nullptr;     // [n_flows*n_layers*2C, 3C+S]
+  __nv_bfloat16* W2 = nullptr;     // [n_flows*n_layers*C, C]
+  int Kup = 0;
+  std::vector<void*> allocs;
+  std::string err;
+  int launches = 0;
+  int sm_count = 148;
+  // wg_infer_host staging
+  cudaStream_t stream = nullptr;
+  float *pin_mel = nullptr, *pin_z = nullptr, *pin_out = nullptr;
+  float *dev_mel = nullptr, *dev_z = nullptr, *dev_out = nullptr;
+  void* dev_ws = nullptr;
+  size_t cap_mel = 0, cap_z = 0, cap_out = 0, cap_ws = 0;
+};
+
+namespace {
+
+template <typename T>
+T* upload(wg_engine* e, const std::vector<T>& v) {
+  T* d = nullptr;
+  CK(cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(T)));
+  e->allocs.push_back(d);
+  CK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return d;
+}
+
+struct TensorView {
+  const float* data;
+  std::vector<int64_t> shape;
+};
+
+const TensorView& need(const std::map<std::string, TensorView>& m, const std::string& name,
+                       std::initializer_list<int64_t> shape) {
+  auto it = m.find(name);
+  if (it == m.end()) fail(WG_ERR_WEIGHTS, "missing weight tensor '%s'", name.c_str());
+  std::vector<int64_t> want(shape);
+  if (it->second.shape != want) {
+    std::string got, exp;
+    for (auto d : it->second.shape) got += std::to_string(d) + ",";
+    for (auto d : want) exp += std::to_string(d) + ",";
+    fail(WG_ERR_WEIGHTS, "weight '%s': shape [%s] != expected [%s]", name.c_str(), got.c_str(), exp.c_str());
+  }
+  return it->second;
+}
+
+// c x c inverse in fp32 (Gauss-Jordan, partial pivoting) -- invertible_conv.py:41-47 uses K.inv on
+// the float32 kernel once at weight load.
+void invert_f32(const float* W, int c, float* inv) {
+  float a[8][16];
+  for (int i = 0; i < c; ++i)
+    for (int j = 0; j < c; ++j) {
+      a[i][j] = W[i * c + j];
+      a[i][c + j] = (i == j) ? 1.f : 0.f;
+    }
+  for (int col = 0; col < c; ++col) {
+    int piv = col;
+    for (int r = col + 1; r < c; ++r)
+      if (std::fabs(a[r][col]) > std::fabs(a[piv][col])) piv = r;
+    if (std::fabs(a[piv][col]) < 1e-12f) fail(WG_ERR_WEIGHTS, "invertible 1x1 kernel is singular");
+    if (piv != col)
+      for (int j = 0; j < 2 * c; ++j) std::swap(a[piv][j], a[col][j]);
+    const float d = 1.f / a[col][col];
+    for (int j = 0; j < 2 * c; ++j) a[col][j] *= d;
+    for (int r = 0; r < c; ++r) {
+      if (r == col) continue;
+      const float f = a[r][col];
+      if (f != 0.f)
+        for (int j = 0; j < 2 * c; ++j) a[r][j] -= f * a[col][j];
+    }
+  }
+  for (int i = 0; i < c; ++i)
+    for (int j = 0; j < c; ++j) inv[i * c + j] = a[i][c + j];
+}
+
+inline __nv_bfloat16 f2bf(float x) { return __float2bfloat16_rn(x); }
+
+struct Ws {  // workspace carving for one (B, T)
+  size_t spect = 0, h32 = 0, acts = 0, skip = 0, acc8 = 0, audio0 = 0, audio1 = 0;
+  size_t spect16 = 0, h16a = 0, h16b = 0, aup16 = 0;
+  size_t total = 0;
+};
+
+Ws carve(const wg_engine* e, int B, int T) {
+  Ws w;
+  const size_t M = (size_t)B * T * e->R;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 1024);
+    return o;
+  };
+  w.h32 = take(M * e->C * 4);
+  w.acc8 = take(M * 8 * 4);
+  w.audio0 = take(M * 8 * 4);
+  w.audio1 = take(M * 8 * 4);
+  if (e->cfg.mode == WG_MODE_FP32) {
+    w.spect = take(M * e->S * 4);
+    w.acts = take(M * e->C * 4);
+    w.skip = take(M * e->C * 4);
+  } else {
+    w.spect16 = take(M * e->S * 2);
+    w.h16a = take(M * e->C * 2);
+    w.h16b = take(M * e->C * 2);
+    w.aup16 = take((size_t)B * T * e->Kup * 2);
+  }
+  w.total = off;
+  return w;
+}
+
+void check_shape(const wg_engine* e, int B, int T) {
+  if (B <= 0 || T <= 0) fail(WG_ERR_INVALID, "B and T must be positive (got B=%d, T=%d)", B, T);
+  const double M = (double)B * T * e->R;
+  if (M * std::max(e->S, e->C) > 2.0e9) fail(WG_ERR_INVALID, "B*T too large (B=%d, T=%d)", B, T);
+}
+
+template <int EPI>
+void launch_gemm(wg_engine* e, const GemmArgs& a, cudaStream_t st) {
+  dim3 grid((a.N + SG_BN - 1) / SG_BN, (a.M + SG_BM - 1) / SG_BM);
+  gemm_f32_kernel<EPI><<<grid, SG_THREADS, 0, st>>>(a);
+  CK(cudaGetLastError());
+  e->launches++;
+}
+
+void launch_boundary(wg_engine* e, const BoundaryArgs& a, cudaStream_t st) {
+  flow_boundary_kernel<<<(a.M + FB_ROWS - 1) / FB_ROWS, FB_THREADS, 0, st>>>(a);
+  CK(cudaGetLastError());
+  e->launches++;
+}
+
+// The launch sequence of WaveGlow.infer. stop_flow/stop_layer >= -1 make it a debug prefix run.
+void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int deterministic, int B,
+               int T, float* out, void* workspace, size_t ws_bytes, cudaStream_t st, int stop_flow,
+               int stop_layer, float* h_out, float* acc_out) {
+  check_shape(e, B, T);
+  if (!mel || (!out && stop_flow < 0)) fail(WG_ERR_INVALID, "mel/out must not be NULL");
+  if (!deterministic && !z) fail(WG_ERR_INVALID, "z must be given unless deterministic");
+  const Ws w = carve(e, B, T);
+  if (!workspace || ws_bytes < w.total)
+    fail(WG_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.total, ws_bytes);
+  if ((uintptr_t)workspace % 1024 != 0) fail(WG_ERR_WORKSPACE, "workspace must be 1024-byte aligned");
+  CK(cudaSetDevice(e->device));
+  e->launches = 0;
+
+  char* base = static_cast<char*>(workspace);
+  const wg_config& c = e->cfg;
+  const int C = e->C, S = e->S, R = e->R, L = T * R, M = B * L;
+  const bool bf16 = c.mode == WG_MODE_BF16;
+  float* h32 = reinterpret_cast<float*>(base + w.h32);
+  float* acc8 = reinterpret_cast<float*>(base + w.acc8);
+  float* audio[2] = {reinterpret_cast<float*>(base + w.audio0), reinterpret_cast<float*>(base + w.audio1)};
+  float* spect = reinterpret_cast<float*>(base + w.spect);
+  float* acts = reinterpret_cast<float*>(base + w.acts);
+  float* skip = reinterpret_cast<float*>(base + w.skip);
+  __nv_bfloat16* spect16 = reinterpret_cast<__nv_bfloat16*>(base + w.spect16);
+  __nv_bfloat16* h16[2] = {reinterpret_cast<__nv_bfloat16*>(base + w.h16a),
+                           reinterpret_cast<__nv_bfloat16*>(base + w.h16b)};
+  __nv_bfloat16* aup16 = reinterpret_cast<__nv_bfloat16*>(base + w.aup16);
+  const float* zz = deterministic ? nullptr : z;
+
+  TcPlan plan;
+  // ---- (1) upsample + trim + regroup: spect[B*L, S]  (waveglow_arch.py:245-253) ---------------
+  if (!bf16) {
+    GemmArgs g{};
+    g.nseg = UPSAMPLE_K / HOP;
+    for (int j = 0; j < g.nseg; ++j) g.seg[j] = ASeg{mel, c.n_mel_channels, c.n_mel_channels, -j};
+    g.W = e->Wup; g.bias = e->bup;
+    g.M = B * T; g.N = R * S; g.L = T;
+    g.out0 = spect; g.ld0 = R * S;
+    launch_gemm<EPI_STORE>(e, g, st);
+  } else {
+    tc_prepare(plan, e->sm_count, B, T, L, C, S, e->Kup, c.n_mel_channels, c.n_flows * c.n_layers,
+               e->Wup16, R * S, e->W1, e->W2, aup16, spect16, h16[0], h16[1]);
+    e->launches += tc_upsample(plan, mel, e->bup, st);
+  }
+
+  // ---- noise -> audio, start conv of the first flow (waveglow_arch.py:264-275, :108) ----------
+  const int F = c.n_flows;
+  int cur = 0, z_off = 0, hcur = 0;
+  {
+    BoundaryArgs a{};
+    a.first = 1; a.z = zz; a.n_group = c.n_group; a.z_off = 0; a.n_inject = e->flows[F - 1].n_rem;
+    a.sigma = sigma; a.audio_out = audio[cur]; a.M = M; a.C = C;
+    a.Wstart = e->flows[F - 1].Wstart; a.bstart = e->flows[F - 1].bstart;
+    a.n_half_next = e->flows[F - 1].n_half; a.h32 = h32; a.h16 = bf16 ? h16[hcur] : nullptr;
+    if (bf16) { a.acc8_rearm = acc8; std::memcpy(a.acc8_init, e->flows[F - 1].bse8, sizeof a.acc8_init); }
+    launch_boundary(e, a, st);
+    z_off = a.n_inject;
+  }
+
+  auto dump = [&](void) {
+    if (h_out) CK(cudaMemcpyAsync(h_out, h32, (size_t)M * C * 4, cudaMemcpyDeviceToDevice, st));
+    if (acc_out) CK(cudaMemcpyAsync(acc_out, acc8, (size_t)M * 8 * 4, cudaMemcpyDeviceToDevice, st));
+  };
+
+  for (int k = F - 1; k >= 0; --k) {
+    const FlowW& fw = e->flows[k];
+    if (k == stop_flow && stop_layer == -1) { dump(); return; }
+    for (int i = 0; i < c.n_layers; ++i) {
+      const LayerW& lw = e->layers[k * c.n_layers + i];
+      const int d = 1 << i;
+      const bool last = i == c.n_layers - 1;
+      if (!bf16) {
+        // in-conv (dilated k=3) + cond 1x1 as one K = 3C+S contraction, gate fused (:113-127, :19-24)
+        GemmArgs g{};
+        g.nseg = 4;
+        g.seg[0] = ASeg{h32, C, C, -d};
+        g.seg[1] = ASeg{h32, C, C, 0};
+        g.seg[2] = ASeg{h32, C, C, d};
+        g.seg[3] = ASeg{spect, S, S, 0};
+        g.W = lw.Wcat; g.bias = lw.bcat; g.M = M; g.N = 2 * C; g.L = L;
+        g.out0 = acts; g.ld0 = C;
+        launch_gemm<EPI_GATE>(e, g, st);
+        // res/skip 1x1 + residual add + skip accumulation (:129-139)
+        GemmArgs r{};
+        r.nseg = 1;
+        r.seg[0] = ASeg{acts, C, C, 0};
+        r.W = lw.Wrs; r.bias = lw.brs; r.M = M; r.N = lw.rs_cols; r.L = L;
+        r.out0 = h32; r.ld0 = C; r.out1 = skip; r.ld1 = C;
+        r.res_cols = last ? 0 : C; r.skip_init = (i == 0);
+        launch_gemm<EPI_RES_SKIP>(e, r, st);
+      } else {
+        e->launches += tc_wn_layer(plan, k * c.n_layers + i, d, last, i == 0, hcur, h32, acc8, lw.b1,
+                                   lw.b2, lw.Wse, nullptr, st);
+        if (!last) hcur ^= 1;
+      }
+      if (k == stop_flow && i == stop_layer) {
+        if (!bf16 && acc_out) {
+          end_conv_kernel<<<(M * 32 + 255) / 256, 256, 0, st>>>(skip, fw.Wend8, fw.bend8, acc8, M, C);
+          CK(cudaGetLastError());
+        }
+        dump();
+        return;
+      }
+    }
+    if (!bf16) {
+      end_conv_kernel<<<(int)(((size_t)M * 32 + 255) / 256), 256, 0, st>>>(skip, fw.Wend8, fw.bend8, acc8, M, C);
+      CK(cudaGetLastError());
+      e->launches++;
+    }
+    // coupling inverse + W^-1 + early re-injection + next start conv (:278-304)
+    BoundaryArgs a{};
+    a.first = 0; a.acc8 = acc8; a.audio_in = audio[cur]; a.z = zz; a.n_group = c.n_group;
+    a.sigma = sigma; a.c_in = 2 * fw.n_half; a.M = M; a.C = C;
+    std::memcpy(a.winv, fw.winv, sizeof a.winv);
+    const bool early = (k % c.n_early_every == 0) && k > 0;
+    a.n_inject = early ? c.n_early_size : 0;
+    a.z_off = z_off;
+    if (early) z_off += c.n_early_size;
+    if (k > 0) {
+      a.audio_out = audio[cur ^ 1];
+      a.Wstart = e->flows[k - 1].Wstart; a.bstart = e->flows[k - 1].bstart;
+      a.n_half_next = e->flows[k - 1].n_half; a.h32 = h32;
+      hcur = 0;
+      a.h16 = bf16 ? h16[hcur] : nullptr;
+      if (bf16) { a.acc8_rearm = acc8; std::memcpy(a.acc8_init, e->flows[k - 1].bse8, sizeof a.acc8_init); }
+    } else {
+      a.audio_out = out;  // [B*L, 8] == [B, 8L]  (waveglow_arch.py:306)
+      a.Wstart = nullptr;
+    }
+    launch_boundary(e, a, st);
+    cur ^= 1;
+  }
+}
+
+void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, int n_tensors, int device) {
+  const wg_config& c = *cfg;
+  e->cfg = c;
+  e->device = device;
+  if (c.mode != WG_MODE_FP32 && c.mode != WG_MODE_BF16) fail(WG_ERR_INVALID, "unknown mode %d", c.mode);
+  if (c.kernel_size != 3) fail(WG_ERR_UNSUPPORTED, "kernel_size must be 3 (got %d)", c.kernel_size);
+  if (c.n_group < 2 || c.n_group > 8 || c.n_group % 2 || HOP % c.n_group)
+    fail(WG_ERR_UNSUPPORTED, "n_group must be an even divisor of 256 that is <= 8 (got %d)", c.n_group);
+  if (c.n_mel_channels <= 0 || c.n_mel_channels % 16)
+    fail(WG_ERR_UNSUPPORTED, "n_mel_channels must be a positive multiple of 16 (got %d)", c.n_mel_channels);
+  if (c.n_channels <= 0 || c.n_channels % 16)
+    fail(WG_ERR_UNSUPPORTED, "n_channels must be a positive multiple of 16 (got %d)", c.n_channels);
+  if (c.n_flows <= 0 || c.n_layers <= 0 || c.n_layers > 12 || c.n_early_every <= 0 || c.n_early_size < 0 ||
+      c.n_early_size % 2)
+    fail(WG_ERR_INVALID, "bad flow/layer hparams");
+  if (c.mode == WG_MODE_BF16 && c.n_channels != 256)
+    fail(WG_ERR_UNSUPPORTED, "WG_MODE_BF16 currently requires n_channels == 256 (got %d); use WG_MODE_FP32",
+         c.n_channels);
+  if (c.mode == WG_MODE_BF16 && (c.n_mel_channels * c.n_group) % 64)
+    fail(WG_ERR_UNSUPPORTED, "WG_MODE_BF16 requires n_mel_channels*n_group %% 64 == 0");
+
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    fail(WG_ERR_CUDA, "no CUDA device available (%s); this engine has no CPU fallback",
+         ce != cudaSuccess ? cudaGetErrorString(ce) : "device count 0");
+  if (device < 0 || device >= ndev) fail(WG_ERR_INVALID, "device %d out of range [0,%d)", device, ndev);
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop{};
+  CK(cudaGetDeviceProperties(&prop, device));
+  e->sm_count = prop.multiProcessorCount;
+  if (c.mode == WG_MODE_BF16 && prop.major != 10)
+    fail(WG_ERR_UNSUPPORTED, "WG_MODE_BF16 needs an sm_100 GPU (tcgen05/TMEM); device is sm_%d%d", prop.major,
+         prop.minor);
+
+  const int C = c.n_channels, NL = c.n_layers, F = c.n_flows;
+  e->C = C;
+  e->S = c.n_mel_channels * c.n_group;
+  e->R = HOP / c.n_group;
+  const int S = e->S, R = e->R, NM = c.n_mel_channels, G = c.n_group;
+
+  std::map<std::string, TensorView> tm;
+  for (int i = 0; i < n_tensors; ++i) {
+    const wg_tensor& t = tensors[i];
+    if (!t.name || !t.data || t.ndim < 1 || t.ndim > 4) fail(WG_ERR_WEIGHTS, "bad tensor entry %d", i);
+    TensorView v{t.data, std::vector<int64_t>(t.shape, t.shape + t.ndim)};
+    tm[t.name] = v;
+  }
+
+  // flow schedule (waveglow_arch.py:202-223)
+  e->flows.resize(F);
+  {
+    int n_half = G / 2, n_rem = G;
+    for (int k = 0; k < F; ++k) {
+      if (k % c.n_early_every == 0 && k > 0) {
+        n_half -= c.n_early_size / 2;
+        n_rem -= c.n_early_size;
+      }
+      if (n_half <= 0) fail(WG_ERR_INVALID, "flow schedule exhausts the channels at flow %d", k);
+      e->flows[k].n_half = n_half;
+      e->flows[k].n_rem = n_rem;
+    }
+  }
+
+  // ---- upsample: polyphase packing -----------------------------------------------------------
+  // spect[b, R t + r, m*G + g] = bias[m] + sum_{j,i} mel[b, t-j, i] * Wup[256 j + G r + g, m, i]
+  {
+    const TensorView& uk = need(tm, "upsample/kernel", {UPSAMPLE_K, NM, NM});
+    const TensorView& ub = need(tm, "upsample/bias", {NM});
+    const int J = UPSAMPLE_K / HOP, N = R * S;
+    std::vector<float> bp((size_t)N);
+    for (int r = 0; r < R; ++r)
+      for (int m = 0; m < NM; ++m)
+        for (int g = 0; g < G; ++g) bp[(size_t)r * S + m * G + g] = ub.data[m];
+    e->bup = upload(e, bp);
+    if (c.mode == WG_MODE_FP32) {
+      std::vector<float> wp((size_t)J * NM * N);
+      for (int j = 0; j < J; ++j)
+        for (int i = 0; i < NM; ++i)
+          for (int r = 0; r < R; ++r)
+            for (int m = 0; m < NM; ++m)
+              for (int g = 0; g < G; ++g)
+                wp[((size_t)(j * NM + i)) * N + (size_t)r * S + m * G + g] =
+                    uk.data[((size_t)(HOP * j + G * r + g) * NM + m) * NM + i];
+      e->Wup = upload(e, wp);
+    } else {
+      e->Kup = (int)align_up((size_t)J * NM, 64);
+      std::vector<__nv_bfloat16> wp((size_t)N * e->Kup, f2bf(0.f));
+      for (int j = 0; j < J; ++j)
+        for (int i = 0; i < NM; ++i)
+          for (int r = 0; r < R; ++r)
+            for (int m = 0; m < NM; ++m)
+              for (int g = 0; g < G; ++g)
+                wp[((size_t)r * S + m * G + g) * e->Kup + (j * NM + i)] =
+                    f2bf(uk.data[((size_t)(HOP * j + G * r + g) * NM + m) * NM + i]);
+      e->Wup16 = upload(e, wp);
+    }
+  }
+
+  // ---- flows / layers ------------------------------------------------------------------------
+  e->layers.resize((size_t)F * NL);
+  const int K1 = 3 * C + S;
+  std::vector<__nv_bfloat16> w1all, w2all;
+  if (c.mode == WG_MODE_BF16) {
+    w1all.assign((size_t)F * NL * 2 * C * K1, f2bf(0.f));
+    w2all.assign((size_t)F * NL * C * C, f2bf(0.f));
+  }
+  for (int k = 0; k < F; ++k) {
+    FlowW& fw = e->flows[k];
+    const std::string p = "block-" + std::to_string(k) + "/";
+    const int nh = fw.n_half, nr = fw.n_rem;
+    {
+      const TensorView& ik = need(tm, "invertible_conv-" + std::to_string(k) + "/conv/kernel", {1, nr, nr});
+      // W[o,i] = kernel[0,i,o]; reverse: out[b] = sum_a in[a] * inv(W)[b,a]  (invertible_conv.py:41-51)
+      float W[64], Winv[64];
+      for (int o = 0; o < nr; ++o)
+        for (int i = 0; i < nr; ++i) W[o * nr + i] = ik.data[i * nr + o];
+      invert_f32(W, nr, Winv);
+      std::memset(fw.winv, 0, sizeof fw.winv);
+      for (int a = 0; a < nr; ++a)
+        for (int b = 0; b < nr; ++b) fw.winv[a * nr + b] = Winv[b * nr + a];
+    }
+    const TensorView& sk = need(tm, p + "start_conv/kernel", {1, nh, C});
+    const TensorView& sb = need(tm, p + "start_conv/bias", {C});
+    fw.Wstart = upload(e, std::vector<float>(sk.data, sk.data + (size_t)nh * C));
+    fw.bstart = upload(e, std::vector<float>(sb.data, sb.data + C));
+    const TensorView& ek = need(tm, p + "end_conv/kernel", {1, C, 2 * nh});
+    const TensorView& eb = need(tm, p + "end_conv/bias", {2 * nh});
+    std::vector<float> wend8((size_t)C * 8, 0.f), bend8(8, 0.f);
+    for (int cc = 0; cc < C; ++cc)
+      for (int j = 0; j < 2 * nh; ++j) wend8[(size_t)cc * 8 + j] = ek.data[(size_t)cc * 2 * nh + j];
+    for (int j = 0; j < 2 * nh; ++j) bend8[j] = eb.data[j];
+    if (c.mode == WG_MODE_FP32) {
+      fw.Wend8 = upload(e, wend8);
+      fw.bend8 = upload(e, bend8);
+    }
+    std::vector<double> bse(8, 0.0);
+    for (int j = 0; j < 8; ++j) bse[j] = bend8[j];
+
+    for (int i = 0; i < NL; ++i) {
+      LayerW& lw = e->layers[(size_t)k * NL + i];
+      const std::string si = std::to_string(i);
+      const int rs = (i < NL - 1) ? 2 * C : C;
+      lw.rs_cols = rs;
+      const TensorView& inw = need(tm, p + "in_conv-" + si + "/kernel", {3, C, 2 * C});
+      const TensorView& inb = need(tm, p + "in_conv-" + si + "/bias", {2 * C});
+      const TensorView& cw = need(tm, p + "cond_layer-" + si + "/kernel", {1, S, 2 * C});
+      const TensorView& cb = need(tm, p + "cond_layer-" + si + "/bias", {2 * C});
+      const TensorView& rw = need(tm, p + "res_skip_conv-" + si + "/kernel", {1, C, rs});
+      const TensorView& rb = need(tm, p + "res_skip_conv-" + si + "/bias", {rs});
+      auto wsrc = [&](int kk, int col) -> float {  // row kk of the [3C+S, 2C] concatenated operand
+        return kk < 3 * C ? inw.data[((size_t)kk) * 2 * C + col]           // [3,C,2C] flat = [(j*C+ci), col]
+                          : cw.data[((size_t)(kk - 3 * C)) * 2 * C + col];
+      };
+      if (c.mode == WG_MODE_FP32) {
+        // packed column p: group of 8 = [tanh 4c..4c+3 | sigmoid 4c..4c+3]
+        std::vector<float> wcat((size_t)K1 * 2 * C), bcat((size_t)2 * C);
+        for (int pcol = 0; pcol < 2 * C; ++pcol) {
+          const int g4 = pcol >> 3, q = pcol & 7;
+          const int col = q < 4 ? 4 * g4 + q : C + 4 * g4 + (q - 4);
+          bcat[pcol] = inb.data[col] + cb.data[col];
+          for (int kk = 0; kk < K1; ++kk) wcat[(size_t)kk * 2 * C + pcol] = wsrc(kk, col);
+        }
+        lw.Wcat = upload(e, wcat);
+        lw.bcat = upload(e, bcat);
+        lw.Wrs = upload(e, std::vector<float>(rw.data, rw.data + (size_t)C * rs));
+        lw.brs = upload(e, std::vector<float>(rb.data, rb.data + rs));
+      } else {
+        // chunk packing: 256-column chunk q = [tanh 128q..128q+127 | sigmoid 128q..128q+127]
+        std::vector<float> b1((size_t)2 * C), b2((size_t)C, 0.f), wse((size_t)C * 8, 0.f);
+        __nv_bfloat16* w1 = w1all.data() + ((size_t)k * NL + i) * 2 * C * K1;
+        for (int pcol = 0; pcol < 2 * C; ++pcol) {
+          const int chunk = pcol >> 8, wi = pcol & 255;
+          const int col = wi < 128 ? 128 * chunk + wi : C + 128 * chunk + (wi - 128);
+          b1[pcol] = inb.data[col] + cb.data[col];
+          for (int kk = 0; kk < K1; ++kk) w1[(size_t)pcol * K1 + kk] = f2bf(wsrc(kk, col));
+        }
+        const int skip_off = (i < NL - 1) ? C : 0;
+        if (i < NL - 1) {
+          __nv_bfloat16* w2 = w2all.data() + ((size_t)k * NL + i) * C * C;
+          for (int n = 0; n < C; ++n) {
+            b2[n] = rb.data[n];
+            for (int kk = 0; kk < C; ++kk) w2[(size_t)n * C + kk] = f2bf(rw.data[(size_t)kk * rs + n]);
+          }
+        }
+        // skip o end fold: acc8 += acts @ (Wskip @ Wend);  bias folded into bse8
+        for (int kk = 0; kk < C; ++kk)
+          for (int j = 0; j < 2 * nh; ++j) {
+            double s = 0.0;
+            for (int n = 0; n < C; ++n)
+              s += (double)rw.data[(size_t)kk * rs + skip_off + n] * (double)wend8[(size_t)n * 8 + j];
+            wse[(size_t)kk * 8 + j] = (float)s;
+          }
+        for (int j = 0; j < 2 * nh; ++j) {
+          double s = 0.0;
+          for (int n = 0; n < C; ++n) s += (double)rb.data[skip_off + n] * (double)wend8[(size_t)n * 8 + j];
+          bse[j] += s;
+        }
+        lw.b1 = upload(e, b1);
+        lw.b2 = upload(e, b2);
+        lw.Wse = upload(e, wse);
+      }
+    }
+    if (c.mode == WG_MODE_BF16) {
+      for (int j = 0; j < 8; ++j) fw.bse8[j] = (float)bse[j];
+    }
+  }
+  if (c.mode == WG_MODE_BF16) {
+    e->W1 = upload(e, w1all);
+    e->W2 = upload(e, w2all);
+    tc_init();
+  }
+  CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+}
+
+void destroy_engine(wg_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  for (void* p : e->allocs) cudaFree(p);
+  if (e->pin_mel) cudaFreeHost(e->pin_mel);
+  if (e->pin_z) cudaFreeHost(e->pin_z);
+  if (e->pin_out) cudaFreeHost(e->pin_out);
+  if (e->dev_mel) cudaFree(e->dev_mel);
+  if (e->dev_z) cudaFree(e->dev_z);
+  if (e->dev_out) cudaFree(e->dev_out);
+  if (e->dev_ws) cudaFree(e->dev_ws);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+template <typename F>
+int guarded(wg_handle h, F&& f) {
+  try {
+    f();
+    return WG_OK;
+  } catch (const Fail& x) {
+    if (h) h->err = x.msg;
+    else {
+      std::lock_guard<std::mutex> g(g_err_mu);
+      g_create_err = x.msg;
+    }
+    return x.code;
+  } catch (const std::exception& x) {
+    if (h) h->err = x.what();
+    return WG_ERR_INVALID;
+  }
+}
+
+// grows a pinned-host / device buffer pair together (tensorrt_runtime.py:143-177 re-allocates its
+// per-shape buffers the same way when the input shapes change)
+void ensure_pair(float*& pin, float*& dev, size_t& cap, size_t bytes) {
+  if (cap >= bytes && pin && dev) return;
+  if (pin) cudaFreeHost(pin);
+  if (dev) cudaFree(dev);
+  pin = nullptr; dev = nullptr; cap = 0;
+  CK(cudaMallocHost(reinterpret_cast<void**>(&pin), bytes));
+  CK(cudaMalloc(reinterpret_cast<void**>(&dev), bytes));
+  cap = bytes;
+}
+
+}  // namespace
+
+extern "C" {
+
+int wg_abi_version(void) { return WG_ABI_VERSION; }
+
+int wg_create(const wg_config* cfg, const wg_tensor* tensors, int32_t n_tensors, int32_t device, wg_handle* out) {
+  if (out) *out = nullptr;
+  if (!cfg || !tensors || !out || n_tensors <= 0) {
+    std::lock_guard<std::mutex> g(g_err_mu);
+    g_create_err = "wg_create: NULL argument";
+    return WG_ERR_INVALID;
+  }
+  wg_engine* e = new wg_engine();
+  int rc = guarded(nullptr, [&] { build_engine(e, cfg, tensors, n_tensors, device); });
+  if (rc != WG_OK) {
+    destroy_engine(e);
+    return rc;
+  }
+  *out = e;
+  return WG_OK;
+}
+
+void wg_destroy(wg_handle h) { destroy_engine(h); }
+
+const char* wg_last_error(wg_handle h) {
+  if (h) return h->err.c_str();
+  std::lock_guard<std::mutex> g(g_err_mu);
+  static thread_local std::string copy;
+  copy = g_create_err;
+  return copy.c_str();
+}
+
+int wg_workspace_bytes(wg_handle h, int32_t B, int32_t T, size_t* bytes) {
+  if (!h || !bytes) return WG_ERR_INVALID;
+  return guarded(h, [&] {
+    check_shape(h, B, T);
+    *bytes = carve(h, B, T).total;
+  });
+}
+
+int wg_infer(wg_handle h, const float* mel, const float* z, float sigma, int32_t deterministic, int32_t B,
+             int32_t T, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h) return WG_ERR_INVALID;
+  return guarded(h, [&] {
+    run_infer(h, mel, z, sigma, deterministic, B, T, out, workspace, workspace_bytes,
+              static_cast<cudaStream_t>(stream), -2, -2, nullptr, nullptr);
+  });
+}
+
+int wg_infer_host(wg_handle h, const float* mel_host, const float* z_host, float sigma, int32_t deterministic,
+                  int32_t B, int32_t T, float* out_host) {
+  if (!h) return WG_ERR_INVALID;
+  return guarded(h, [&] {
+    check_shape(h, B, T);
+    if (!mel_host || !out_host) fail(WG_ERR_INVALID, "mel_host/out_host must not be NULL");
+    if (!deterministic && !z_host) fail(WG_ERR_INVALID, "z_host must be given unless deterministic");
+    CK(cudaSetDevice(h->device));
+    const size_t L = (size_t)T * h->R;
+    const size_t mel_b = (size_t)B * T * h->cfg.n_mel_channels * 4, z_b = (size_t)B * L * h->cfg.n_group * 4,
+                 out_b = (size_t)B * L * h->cfg.n_group * 4, ws_b = carve(h, B, T).total;
+    ensure_pair(h->pin_mel, h->dev_mel, h->cap_mel, mel_b);
+    ensure_pair(h->pin_out, h->dev_out, h->cap_out, out_b);
+    if (!deterministic) ensure_pair(h->pin_z, h->dev_z, h->cap_z, z_b);
+    if (h->cap_ws < ws_b) {
+      if (h->dev_ws) cudaFree(h->dev_ws);
+      h->dev_ws = nullptr; h->cap_ws = 0;
+      CK(cudaMalloc(&h->dev_ws, ws_b));
+      h->cap_ws = ws_b;
+    }
+    std::memcpy(h->pin_mel, mel_host, mel_b);
+    CK(cudaMemcpyAsync(h->dev_mel, h->pin_mel, mel_b, cudaMemcpyHostToDevice, h->stream));
+    if (!deterministic) {
+      std::memcpy(h->pin_z, z_host, z_b);
+      CK(cudaMemcpyAsync(h->dev_z, h->pin_z, z_b, cudaMemcpyHostToDevice, h->stream));
+    }
+    run_infer(h, h->dev_mel, deterministic ? nullptr : h->dev_z, sigma, deterministic, B, T, h->dev_out, h->dev_ws,
+              h->cap_ws, h->stream, -2, -2, nullptr, nullptr);
+    CK(cudaMemcpyAsync(h->pin_out, h->dev_out, out_b, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    std::memcpy(out_host, h->pin_out, out_b);
+  });
+}
+
+int wg_last_launch_count(wg_handle h) { return h ? h->launches : 0; }
+
+int wg_debug_infer_prefix(wg_handle h, const float* mel, const float* z, float sigma, int32_t deterministic,
+                          int32_t B, int32_t T, void* workspace, size_t workspace_bytes, void* stream,
+                          int32_t stop_flow, int32_t stop_layer, float* h_out, float* acc_out) {
+  if (!h) return WG_ERR_INVALID;
+  return guarded(h, [&] {
+    if (stop_flow < 0 || stop_flow >= h->cfg.n_flows || stop_layer < -1 || stop_layer >= h->cfg.n_layers)
+      fail(WG_ERR_INVALID, "bad stop point (%d, %d)", stop_flow, stop_layer);
+    run_infer(h, mel, z, sigma, deterministic, B, T, nullptr, workspace, workspace_bytes,
+              static_cast<cudaStream_t>(stream), stop_flow, stop_layer, h_out, acc_out);
+  });
+}
+
+int wg_debug_get_spect(wg_handle h, int32_t B, int32_t T, const void* workspace, float* spect_out, void* stream) {
+  if (!h) return WG_ERR_INVALID;
+  return guarded(h, [&] {
+    check_shape(h, B, T);
+    if (!workspace || !spect_out) fail(WG_ERR_INVALID, "NULL argument");
+    const Ws w = carve(h, B, T);
+    const size_t n = (size_t)B * T * h->R * h->S;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (h->cfg.mode == WG_MODE_FP32) {
+      CK(cudaMemcpyAsync(spect_out, static_cast<const char*>(workspace) + w.spect, n * 4, cudaMemcpyDeviceToDevice, st));
+    } else {
+      tc_bf16_to_f32(reinterpret_cast<const __nv_bfloat16*>(static_cast<const char*>(workspace) + w.spect16),
+                     spect_out, n, st);
+      CK(cudaGetLastError());
+    }
+  });
+}
+
+int wg_debug_gemm_bf16(const void* A, const void* W, const float* bias, float* D, int32_t M, int32_t N, int32_t K,
+                       void* stream) {
+  std::string msg;
+  try {
+    tc_init();
+    tc_debug_gemm(static_cast<const __nv_bfloat16*>(A), static_cast<const __nv_bfloat16*>(W), bias, D, M, N, K,
+                  static_cast<cudaStream_t>(stream));
+    return WG_OK;
+  } catch (const Fail& x) {
+    std::lock_guard<std::mutex> g(g_err_mu);
+    g_create_err = x.msg;
+    return x.code;
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,723 @@
+// tcgen05 / TMEM / TMA kernels of the WaveGlow engine (WG_MODE_BF16), sm_100a only.
+//
+//   tc_gemm_kernel      D[M,N] = A[M,K] @ W[N,K]^T + bias -- the polyphase ConvTranspose upsample
+//                       (waveglow_arch.py:196-198, :245-253) and the stand-alone GEMM self-test.
+//   tc_wn_layer_kernel  one fused WN layer (waveglow_arch.py:105-141 loop body):
+//                         GEMM1  [128 x (3C+S)] @ [(3C+S) x 2C]  dilated k=3 conv (3 row-shifted A tiles,
+//                                TMA zero fill = 'same' padding) + cond 1x1 as extra K
+//                         gate   tanh * sigmoid on the fp32 accumulator (TMEM -> registers)
+//                         fold   acc8 += acts @ (Wskip @ Wend)   (skip accumulation + end conv, fp32 FMA)
+//                         GEMM2  acts[128 x C] (smem, written by the gate epilogue) @ Wres[C x C]
+//                         res    h += GEMM2 + b   (fp32 master + bf16 shadow for the next layer's TMA)
+//
+// Operands are BF16, K-major, 128-byte swizzled in shared memory (TMA SWIZZLE_128B == UMMA
+// LayoutType::SWIZZLE_128B); accumulators are fp32 in TMEM; one elected thread issues tcgen05.mma.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace wg {
+
+// ================================================================================================
+// PTX wrappers
+// ================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done;
+}
+// Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU.
+__device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
+  printf("wg_b200: mbarrier timeout block %d thread %d bar 0x%x parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) mbar_timeout(bar, parity);
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// ---- tcgen05 ------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 in
+// [0,14), LBO>>4 in [16,30) (unused for swizzled K-major), SBO>>4 in [32,46) = 8 rows * 128 B,
+// version=1 in [46,48), layout_type=2 (SWIZZLE_128B) in [61,64). Tile bases are 1024-B aligned.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16: D=f32 (bit4), A=B=bf16 (bits 7,10),
+// both K-major, N>>3 in [17,23), M>>4 in [24,29).
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// ================================================================================================
+// Generic GEMM: D[M,N] = A[M,K] @ W[N,K]^T + bias[N].  Tile 128 x 256 x 64, 4-stage TMA ring.
+// warp 0: TMA producer, warp 1: TMEM alloc + MMA issuer, warps 2..5: epilogue.
+// ================================================================================================
+constexpr int TG_BM = 128, TG_BN = 256, TG_BK = 64, TG_STAGES = 4, TG_THREADS = 192;
+constexpr int TG_A_BYTES = TG_BM * TG_BK * 2, TG_B_BYTES = TG_BN * TG_BK * 2;
+constexpr int TG_STAGE_BYTES = TG_A_BYTES + TG_B_BYTES;
+constexpr int TG_SMEM = TG_STAGES * TG_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+template <typename OutT>
+__global__ void __launch_bounds__(TG_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+               const float* __restrict__ bias, OutT* __restrict__ D, int M, int N, int K) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TG_STAGES * TG_STAGE_BYTES);
+  // bars[0..S) full, [S..2S) empty, [2S] accumulator full; then the TMEM base address
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TG_STAGES + 1);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (TG_STAGES + s); };
+  const uint32_t acc_bar = bar_base + 8u * (2 * TG_STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * TG_BN, m0 = blockIdx.y * TG_BM;
+  const int num_kb = K / TG_BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_a);
+    prefetch_tmap(&map_w);
+    for (int s = 0; s < TG_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(acc_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % TG_STAGES;
+        const uint32_t ph = (kb / TG_STAGES) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        mbar_expect_tx(full_bar(s), TG_STAGE_BYTES);
+        const uint32_t a_dst = smem_base + s * TG_STAGE_BYTES;
+        tma_load_2d(a_dst, &map_a, full_bar(s), kb * TG_BK, m0);
+        tma_load_2d(a_dst + TG_A_BYTES, &map_w, full_bar(s), kb * TG_BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TG_BM, TG_BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % TG_STAGES;
+        const uint32_t ph = (kb / TG_STAGES) & 1;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_base + s * TG_STAGE_BYTES;
+        const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + TG_A_BYTES);
+#pragma unroll
+        for (int k = 0; k < TG_BK / 16; ++k)
+          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+        tc_commit(empty_bar(s));
+      }
+      tc_commit(acc_bar);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int m = m0 + row;
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+    for (int cb = 0; cb < TG_BN / 16; ++cb) {
+      uint32_t r[16];
+      tmem_ld16(taddr + cb * 16, r);
+      tmem_ld_wait();
+      if (m < M) {
+        const int n = n0 + cb * 16;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + (bias ? __ldg(bias + n + j) : 0.f);
+        if constexpr (sizeof(OutT) == 4) {
+          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(D) + (size_t)m * N + n);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        } else {
+          uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(D) + (size_t)m * N + n);
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+            o[q] = make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                              pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ================================================================================================
+// Fused WN layer (C = 256, S = 640).  One CTA per SM, persistent over 128-row tiles.
+//   warp 0      TMA producer        warp 1      TMEM alloc + MMA issuer       warps 2..9  epilogue
+// TMEM: two 256-column fp32 regions R0/R1.  Tile with parity p:
+//   GEMM1 chunk a (gate channels 0..127)   -> R[p]      K = 22 blocks of 64 (12 conv + 10 cond)
+//   GEMM1 chunk b (gate channels 128..255) -> R[p^1]    (issued while the epilogue drains chunk a)
+//   GEMM2 (res)                            -> R[p]      A = acts tile in shared memory
+// ================================================================================================
+constexpr int WL_C = 256, WL_S = 640, WL_BM = 128, WL_BK = 64;
+constexpr int WL_STAGES = 3;
+constexpr int WL_A_BYTES = WL_BM * WL_BK * 2;          // 16 KB
+constexpr int WL_B_BYTES = 256 * WL_BK * 2;            // 32 KB
+constexpr int WL_STAGE_BYTES = WL_A_BYTES + WL_B_BYTES;
+constexpr int WL_KB_CONV = 3 * WL_C / WL_BK;           // 12
+constexpr int WL_KB1 = WL_KB_CONV + WL_S / WL_BK;      // 22
+constexpr int WL_KB2 = WL_C / WL_BK;                   // 4
+constexpr int WL_K1 = 3 * WL_C + WL_S;                 // 1408
+constexpr int WL_ACTS_BYTES = WL_BM * WL_C * 2;        // 64 KB
+constexpr int WL_EPI_WARPS = 8, WL_EPI_THREADS = WL_EPI_WARPS * 32;
+constexpr int WL_THREADS = 64 + WL_EPI_THREADS;        // 320
+constexpr int WL_OFF_ACTS = WL_STAGES * WL_STAGE_BYTES;
+constexpr int WL_OFF_WSE = WL_OFF_ACTS + WL_ACTS_BYTES;
+constexpr int WL_OFF_B1 = WL_OFF_WSE + WL_C * 8 * 4;
+constexpr int WL_OFF_B2 = WL_OFF_B1 + 2 * WL_C * 4;
+constexpr int WL_OFF_O8 = WL_OFF_B2 + WL_C * 4;          // [128][8] fp32: partial fold sums of the hf=1 warps
+constexpr int WL_OFF_BARS = WL_OFF_O8 + WL_BM * 8 * 4;
+constexpr int WL_NBARS = 2 * WL_STAGES + 3 + 2 + 1 + 1;
+constexpr int WL_SMEM = WL_OFF_BARS + WL_NBARS * 8 + 16 + 1024;
+
+struct WnLayerParams {
+  int L, tiles_per_b, n_tiles;
+  int layer;      // row block in the stacked W1 / W2 matrices
+  int dilation;
+  const float* b1;   // [512] chunk-packed
+  const float* b2;   // [256]
+  const float* Wse;  // [256, 8]
+  float* h32;        // [B*L, 256] fp32 master residual stream (updated in place)
+  __nv_bfloat16* h16_out;  // [B*L, 256] bf16 shadow written for the next layer
+  float* acc8;       // [B*L, 8] folded skip/end accumulator (read-modify-write, one thread per row)
+};
+
+template <bool LAST>
+__global__ void __launch_bounds__(WL_THREADS, 1)
+tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_spect,
+                   const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2,
+                   const WnLayerParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t smem_base = smem_u32(smem);
+  float* s_wse = reinterpret_cast<float*>(smem + WL_OFF_WSE);
+  float* s_b1 = reinterpret_cast<float*>(smem + WL_OFF_B1);
+  float* s_b2 = reinterpret_cast<float*>(smem + WL_OFF_B2);
+  float* s_o8 = reinterpret_cast<float*>(smem + WL_OFF_O8);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WL_OFF_BARS);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + WL_NBARS);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (WL_STAGES + s); };
+  auto dfull_bar = [&](int i) { return bar_base + 8u * (2 * WL_STAGES + i); };        // 0: chunk a, 1: chunk b, 2: GEMM2
+  auto drained_bar = [&](int i) { return bar_base + 8u * (2 * WL_STAGES + 3 + i); };  // chunk a / b accumulators read out
+  const uint32_t acts_bar = bar_base + 8u * (2 * WL_STAGES + 5);                      // acts tile complete in smem
+  const uint32_t epi2_bar = bar_base + 8u * (2 * WL_STAGES + 6);                      // GEMM2 accumulator read out
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_h);
+    prefetch_tmap(&map_spect);
+    prefetch_tmap(&map_w1);
+    prefetch_tmap(&map_w2);
+    for (int s = 0; s < WL_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int i = 0; i < 3; ++i) mbar_init(dfull_bar(i), 1);
+    for (int i = 0; i < 2; ++i) mbar_init(drained_bar(i), WL_EPI_THREADS);
+    mbar_init(acts_bar, WL_EPI_THREADS);
+    mbar_init(epi2_bar, WL_EPI_THREADS);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < WL_C * 8; i += WL_THREADS) s_wse[i] = p.Wse[i];
+  for (int i = threadIdx.x; i < 2 * WL_C; i += WL_THREADS) s_b1[i] = p.b1[i];
+  if (!LAST)
+    for (int i = threadIdx.x; i < WL_C; i += WL_THREADS) s_b2[i] = p.b2[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================== TMA producer ======================================
+    if (lane == 0) {
+      uint32_t it = 0;  // running stage counter
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int b = tile / p.tiles_per_b, l0 = (tile - b * p.tiles_per_b) * WL_BM;
+        for (int q = 0; q < 2; ++q) {
+          for (int kb = 0; kb < WL_KB1; ++kb, ++it) {
+            const int s = it % WL_STAGES;
+            const uint32_t ph = (it / WL_STAGES) & 1;
+            mbar_wait(empty_bar(s), ph ^ 1);
+            mbar_expect_tx(full_bar(s), WL_STAGE_BYTES);
+            const uint32_t a_dst = smem_base + s * WL_STAGE_BYTES;
+            if (kb < WL_KB_CONV) {
+              const int tap = kb >> 2, cblk = kb & 3;
+              tma_load_3d(a_dst, &map_h, full_bar(s), cblk * WL_BK, l0 + (tap - 1) * p.dilation, b);
+            } else {
+              tma_load_3d(a_dst, &map_spect, full_bar(s), (kb - WL_KB_CONV) * WL_BK, l0, b);
+            }
+            tma_load_2d(a_dst + WL_A_BYTES, &map_w1, full_bar(s), kb * WL_BK, p.layer * 2 * WL_C + q * 256);
+          }
+        }
+        if (!LAST) {
+          for (int kb = 0; kb < WL_KB2; ++kb, ++it) {
+            const int s = it % WL_STAGES;
+            const uint32_t ph = (it / WL_STAGES) & 1;
+            mbar_wait(empty_bar(s), ph ^ 1);
+            mbar_expect_tx(full_bar(s), WL_B_BYTES);
+            tma_load_2d(smem_base + s * WL_STAGE_BYTES + WL_A_BYTES, &map_w2, full_bar(s), kb * WL_BK, p.layer * WL_C);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ====================================== MMA issuer =======================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 256);
+      uint32_t it = 0;
+      uint32_t n = 0;  // local tile counter
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++n) {
+        const uint32_t par = LAST ? 0u : (n & 1u);
+        const uint32_t prev_ph = (n - 1) & 1u;
+        for (int q = 0; q < 2; ++q) {
+          const uint32_t d_tmem = tmem_base + 256u * (q == 0 ? par : (par ^ 1u));
+          if (n > 0) {
+            if (LAST) {
+              mbar_wait(drained_bar(q), prev_ph);   // this region still holds tile n-1's chunk q
+              tc_fence_after();
+            } else if (q == 1) {
+              mbar_wait(epi2_bar, prev_ph);         // R[p^1] held GEMM2 of tile n-1
+              tc_fence_after();
+            }
+          }
+          for (int kb = 0; kb < WL_KB1; ++kb, ++it) {
+            const int s = it % WL_STAGES;
+            const uint32_t ph = (it / WL_STAGES) & 1;
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            const uint32_t a_addr = smem_base + s * WL_STAGE_BYTES;
+            const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + WL_A_BYTES);
+#pragma unroll
+            for (int k = 0; k < WL_BK / 16; ++k)
+              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+            tc_commit(empty_bar(s));
+          }
+          tc_commit(dfull_bar(q));
+        }
+        if (!LAST) {
+          mbar_wait(acts_bar, n & 1u);   // gate epilogue wrote all of acts and drained both D1 regions
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + 256u * par;
+          for (int kb = 0; kb < WL_KB2; ++kb, ++it) {
+            const int s = it % WL_STAGES;
+            const uint32_t ph = (it / WL_STAGES) & 1;
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            const uint64_t adesc = umma_desc_sw128(smem_base + WL_OFF_ACTS + kb * WL_A_BYTES);
+            const uint64_t bdesc = umma_desc_sw128(smem_base + s * WL_STAGE_BYTES + WL_A_BYTES);
+#pragma unroll
+            for (int k = 0; k < WL_BK / 16; ++k)
+              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+            tc_commit(empty_bar(s));
+          }
+          tc_commit(dfull_bar(2));
+        }
+      }
+    }
+  } else {
+    // ======================================= epilogue ========================================
+    const int we = warp - 2;
+    const int quarter = warp & 3;       // TMEM lane quarter this warp may access
+    const int hf = we >> 2;             // which half of the columns this warp handles
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    uint8_t* acts = smem + WL_OFF_ACTS;
+    float* scratch = reinterpret_cast<float*>(acts + we * 8192);   // epilogue-2 transposition tile [32][64]
+    uint32_t n = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++n) {
+      const int b = tile / p.tiles_per_b, l0 = (tile - b * p.tiles_per_b) * WL_BM;
+      const uint32_t par = LAST ? 0u : (n & 1u);
+      const uint32_t ph = n & 1u;
+      const bool valid = (l0 + row) < p.L;
+      const size_t m = static_cast<size_t>(b) * p.L + l0 + row;
+      float o8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o8[j] = 0.f;
+
+      // ---- gate epilogue: chunk q holds gate channels [128 q, 128 q + 128) ---------------------
+      for (int q = 0; q < 2; ++q) {
+        mbar_wait(dfull_bar(q), ph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + lane_addr + 256u * (q == 0 ? par : (par ^ 1u));
+        uint8_t* kblk = acts + (q * 2 + hf) * WL_A_BYTES + row * 128;   // K-block (64 channels) row
+#pragma unroll 1
+        for (int st = 0; st < 4; ++st) {
+          uint32_t t[16], g[16];
+          const int colT = hf * 64 + st * 16;
+          tmem_ld16(taddr + colT, t);
+          tmem_ld16(taddr + 128 + colT, g);
+          tmem_ld_wait();
+          const float* bT = s_b1 + q * 256 + colT;
+          const float* bG = bT + 128;
+          const float* wse = s_wse + (q * 128 + colT) * 8;
+          float a[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float xt = __uint_as_float(t[j]) + bT[j];
+            const float xg = __uint_as_float(g[j]) + bG[j];
+            a[j] = tanh_fast(xt) * fmaf(0.5f, tanh_fast(0.5f * xg), 0.5f);
+            const float4 w0 = *reinterpret_cast<const float4*>(wse + j * 8);
+            const float4 w1 = *reinterpret_cast<const float4*>(wse + j * 8 + 4);
+            o8[0] = fmaf(a[j], w0.x, o8[0]); o8[1] = fmaf(a[j], w0.y, o8[1]);
+            o8[2] = fmaf(a[j], w0.z, o8[2]); o8[3] = fmaf(a[j], w0.w, o8[3]);
+            o8[4] = fmaf(a[j], w1.x, o8[4]); o8[5] = fmaf(a[j], w1.y, o8[5]);
+            o8[6] = fmaf(a[j], w1.z, o8[6]); o8[7] = fmaf(a[j], w1.w, o8[7]);
+          }
+          if (!LAST) {
+            // bf16 acts into the K-major SWIZZLE_128B A tile of GEMM2: 16-byte chunk c of row r at c ^ (r & 7)
+            const uint4 v0 = make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]), pack_bf16x2(a[6], a[7]));
+            const uint4 v1 = make_uint4(pack_bf16x2(a[8], a[9]), pack_bf16x2(a[10], a[11]), pack_bf16x2(a[12], a[13]), pack_bf16x2(a[14], a[15]));
+            *reinterpret_cast<uint4*>(kblk + (((st * 2) ^ (row & 7)) << 4)) = v0;
+            *reinterpret_cast<uint4*>(kblk + (((st * 2 + 1) ^ (row & 7)) << 4)) = v1;
+          }
+        }
+        tc_fence_before();
+        if (LAST) mbar_arrive(drained_bar(q));
+      }
+      if (!LAST) {
+        fence_proxy_async_smem();   // acts (generic-proxy writes) -> visible to the MMA (async proxy)
+        mbar_arrive(acts_bar);
+      }
+      // fold accumulator: the two column halves of a row are combined in a fixed order (bit-reproducible)
+      if (hf == 1) {
+        *reinterpret_cast<float4*>(s_o8 + row * 8) = make_float4(o8[0], o8[1], o8[2], o8[3]);
+        *reinterpret_cast<float4*>(s_o8 + row * 8 + 4) = make_float4(o8[4], o8[5], o8[6], o8[7]);
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(WL_EPI_THREADS) : "memory");
+      if (hf == 0 && valid) {
+        const float4 p0 = *reinterpret_cast<const float4*>(s_o8 + row * 8);
+        const float4 p1 = *reinterpret_cast<const float4*>(s_o8 + row * 8 + 4);
+        float4* o = reinterpret_cast<float4*>(p.acc8 + m * 8);
+        float4 a0 = o[0], a1 = o[1];
+        a0.x += o8[0] + p0.x; a0.y += o8[1] + p0.y; a0.z += o8[2] + p0.z; a0.w += o8[3] + p0.w;
+        a1.x += o8[4] + p1.x; a1.y += o8[5] + p1.y; a1.z += o8[6] + p1.z; a1.w += o8[7] + p1.w;
+        o[0] = a0; o[1] = a1;
+      }
+
+      // ---- residual epilogue: h += GEMM2 + b2 ----------------------------------------------------
+      if (!LAST) {
+        mbar_wait(dfull_bar(2), ph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + lane_addr + 256u * par;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+          const int colbase = hf * 128 + pass * 64;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint32_t r[16];
+            tmem_ld16(taddr + colbase + i * 16, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const int chunk = (i * 4 + c4) ^ (lane & 15);
+              *reinterpret_cast<uint4*>(scratch + lane * 64 + chunk * 4) = make_uint4(r[4 * c4], r[4 * c4 + 1], r[4 * c4 + 2], r[4 * c4 + 3]);
+            }
+          }
+          if (pass == 1) {
+            tc_fence_before();
+            mbar_arrive(epi2_bar);   // all TMEM reads of this tile are done
+          }
+          __syncwarp();
+          const int ck = lane & 15, rsub = lane >> 4;
+          const int col = colbase + ck * 4;
+          const float4 bb = *reinterpret_cast<const float4*>(s_b2 + col);
+#pragma unroll 4
+          for (int itr = 0; itr < 16; ++itr) {
+            const int rr = itr * 2 + rsub;
+            const int l = l0 + quarter * 32 + rr;
+            if (l < p.L) {
+              const float4 dv = *reinterpret_cast<const float4*>(scratch + rr * 64 + ((ck ^ (rr & 15)) << 2));
+              const size_t mm = static_cast<size_t>(b) * p.L + l;
+              float4* hp = reinterpret_cast<float4*>(p.h32 + mm * WL_C + col);
+              float4 h = *hp;
+              h.x += dv.x + bb.x; h.y += dv.y + bb.y; h.z += dv.z + bb.z; h.w += dv.w + bb.w;
+              *hp = h;
+              *reinterpret_cast<uint2*>(p.h16_out + mm * WL_C + col) = make_uint2(pack_bf16x2(h.x, h.y), pack_bf16x2(h.z, h.w));
+            }
+          }
+          __syncwarp();
+        }
+      }
+      // (a) the transposition scratch aliases the acts tile, (b) s_o8 is reused by the next tile:
+      // no epilogue warp may run ahead into the next tile before all are done with this one
+      asm volatile("bar.sync 1, %0;" ::"n"(WL_EPI_THREADS) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ================================================================================================
+// Small helper kernels
+// ================================================================================================
+// A operand of the polyphase upsample GEMM: aup[b*T + t, j*n_mel + i] = bf16(mel[b, t-j, i]), 0 for t < j.
+__global__ void upsample_im2col_kernel(const float* __restrict__ mel, __nv_bfloat16* __restrict__ aup, int B, int T,
+                                       int n_mel, int Kup) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(B) * T * Kup;
+  if (idx >= total) return;
+  const int kk = static_cast<int>(idx % Kup);
+  const size_t bt = idx / Kup;
+  const int t = static_cast<int>(bt % T);
+  const int j = kk / n_mel, i = kk - j * n_mel;
+  float v = 0.f;
+  if (j < 4 && t - j >= 0) v = mel[(bt - j) * n_mel + i];
+  aup[idx] = __float2bfloat16_rn(v);
+}
+
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, size_t n) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx < n) out[idx] = __bfloat162float(in[idx]);
+}
+
+// ================================================================================================
+// Host side: tensor maps + launches
+// ================================================================================================
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled& encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  return fn;
+}
+
+inline void tc_init() {
+  if (encode_fn()) return;
+  void* f = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  WG_CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres));
+  if (!f || qres != cudaDriverEntryPointSuccess) fail(WG_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  encode_fn() = reinterpret_cast<PFN_encodeTiled>(f);
+  WG_CK(cudaFuncSetAttribute(tc_gemm_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
+  WG_CK(cudaFuncSetAttribute(tc_gemm_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
+  WG_CK(cudaFuncSetAttribute(tc_wn_layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WL_SMEM));
+  WG_CK(cudaFuncSetAttribute(tc_wn_layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WL_SMEM));
+}
+
+// bf16 tensor map, innermost dim contiguous, SWIZZLE_128B, box inner = 64 elements (128 B).
+inline void make_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box) {
+  cuuint64_t gdim[3], gstr[2];
+  cuuint32_t bx[3], es[3] = {1, 1, 1};
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+  }
+  for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) fail(WG_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+}
+
+inline void make_map_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  const uint64_t dims[2] = {cols, rows}, str[1] = {cols * 2};
+  const uint32_t box[2] = {64, box_rows};
+  make_map(m, ptr, 2, dims, str, box);
+}
+
+inline void make_map_3d(CUtensorMap* m, const void* ptr, uint64_t batch, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  const uint64_t dims[3] = {cols, rows, batch}, str[2] = {cols * 2, rows * cols * 2};
+  const uint32_t box[3] = {64, box_rows, 1};
+  make_map(m, ptr, 3, dims, str, box);
+}
+
+struct TcPlan {
+  CUtensorMap m_aup, m_wup, m_w1, m_w2, m_h16[2], m_spect;
+  int sm_count = 0, B = 0, T = 0, L = 0, C = 0, S = 0, Kup = 0, n_mel = 0, NupN = 0;
+  int tiles_per_b = 0, n_tiles = 0;
+  __nv_bfloat16 *aup16 = nullptr, *spect16 = nullptr, *h16[2] = {nullptr, nullptr};
+};
+
+inline void tc_prepare(TcPlan& pl, int sm_count, int B, int T, int L, int C, int S, int Kup, int n_mel,
+                       int n_layers_total, const __nv_bfloat16* Wup16, int NupN, const __nv_bfloat16* W1,
+                       const __nv_bfloat16* W2, __nv_bfloat16* aup16, __nv_bfloat16* spect16, __nv_bfloat16* h16a,
+                       __nv_bfloat16* h16b) {
+  if (C != WL_C || S != WL_S) fail(WG_ERR_UNSUPPORTED, "tensor path is built for C=256, S=640 (got C=%d, S=%d)", C, S);
+  pl.sm_count = sm_count; pl.B = B; pl.T = T; pl.L = L; pl.C = C; pl.S = S; pl.Kup = Kup; pl.n_mel = n_mel; pl.NupN = NupN;
+  pl.tiles_per_b = (L + WL_BM - 1) / WL_BM;
+  pl.n_tiles = pl.tiles_per_b * B;
+  pl.aup16 = aup16; pl.spect16 = spect16; pl.h16[0] = h16a; pl.h16[1] = h16b;
+  make_map_2d(&pl.m_aup, aup16, (uint64_t)B * T, Kup, TG_BM);
+  make_map_2d(&pl.m_wup, Wup16, NupN, Kup, TG_BN);
+  make_map_2d(&pl.m_w1, W1, (uint64_t)n_layers_total * 2 * C, 3 * C + S, 256);
+  make_map_2d(&pl.m_w2, W2, (uint64_t)n_layers_total * C, C, 256);
+  make_map_3d(&pl.m_h16[0], h16a, B, L, C, WL_BM);
+  make_map_3d(&pl.m_h16[1], h16b, B, L, C, WL_BM);
+  make_map_3d(&pl.m_spect, spect16, B, L, S, WL_BM);
+}
+
+inline int tc_upsample(const TcPlan& pl, const float* mel, const float* bup, cudaStream_t st) {
+  const size_t total = (size_t)pl.B * pl.T * pl.Kup;
+  upsample_im2col_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(mel, pl.aup16, pl.B, pl.T, pl.n_mel, pl.Kup);
+  WG_CK(cudaGetLastError());
+  const int M = pl.B * pl.T;
+  dim3 grid(pl.NupN / TG_BN, (M + TG_BM - 1) / TG_BM);
+  tc_gemm_kernel<__nv_bfloat16><<<grid, TG_THREADS, TG_SMEM, st>>>(pl.m_aup, pl.m_wup, bup, pl.spect16, M, pl.NupN, pl.Kup);
+  WG_CK(cudaGetLastError());
+  return 2;
+}
+
+inline int tc_wn_layer(const TcPlan& pl, int layer, int dilation, bool last, bool /*first*/, int hcur, float* h32,
+                       float* acc8, const float* b1, const float* b2, const float* Wse, const float* /*bse8*/,
+                       cudaStream_t st) {
+  WnLayerParams p{};
+  p.L = pl.L; p.tiles_per_b = pl.tiles_per_b; p.n_tiles = pl.n_tiles; p.layer = layer; p.dilation = dilation;
+  p.b1 = b1; p.b2 = b2; p.Wse = Wse; p.h32 = h32; p.h16_out = pl.h16[hcur ^ 1]; p.acc8 = acc8;
+  const int grid = pl.n_tiles < pl.sm_count ? pl.n_tiles : pl.sm_count;
+  if (last)
+    tc_wn_layer_kernel<true><<<grid, WL_THREADS, WL_SMEM, st>>>(pl.m_h16[hcur], pl.m_spect, pl.m_w1, pl.m_w2, p);
+  else
+    tc_wn_layer_kernel<false><<<grid, WL_THREADS, WL_SMEM, st>>>(pl.m_h16[hcur], pl.m_spect, pl.m_w1, pl.m_w2, p);
+  WG_CK(cudaGetLastError());
+  return 1;
+}
+
+inline void tc_bf16_to_f32(const __nv_bfloat16* in, float* out, size_t n, cudaStream_t st) {
+  bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n);
+}
+
+inline void tc_debug_gemm(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, float* D, int M, int N,
+                          int K, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0 || N % TG_BN || K % TG_BK)
+    fail(WG_ERR_INVALID, "debug GEMM needs N %% 256 == 0 and K %% 64 == 0 (got M=%d N=%d K=%d)", M, N, K);
+  CUtensorMap ma, mw;
+  make_map_2d(&ma, A, M, K, TG_BM);
+  make_map_2d(&mw, W, N, K, TG_BN);
+  dim3 grid(N / TG_BN, (M + TG_BM - 1) / TG_BM);
+  tc_gemm_kernel<float><<<grid, TG_THREADS, TG_SMEM, st>>>(ma, mw, bias, D, M, N, K);
+  WG_CK(cudaGetLastError());
+}
+
+}  // namespace wg

@@ -1,0 +1,87 @@
+"""Utterance sharding across the GPUs of one box.
+
+The path has no cross-utterance dependency (each output sample depends only on its own mel, z and
+the weights), so whole utterances are partitioned: longest-processing-time-first over ranks, then
+length-bucketed batches inside a rank. No collective is involved; results stay with their rank
+(pinned host buffers) and are concatenated by utterance index by whoever needs them.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Sequence
+
+
+def assign_utterances(lengths: Sequence[int], world_size: int) -> List[List[int]]:
+    """Greedy LPT: sort by length (desc, index as tie-break), give each utterance to the least
+    loaded rank. Deterministic, so every rank computes the same partition without talking."""
+    if world_size <= 0:
+        raise ValueError("world_size must be positive")
+    order = sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i))
+    load = [0] * world_size
+    shards = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda k: (load[k], k))
+        shards[r].append(i)
+        load[r] += int(lengths[i])
+    return shards
+
+
+@dataclass
+class Batch:
+    indices: List[int]   # utterance ids (global)
+    T: int               # padded frame count of the batch (max length in it)
+
+
+def make_batches(indices: Sequence[int], lengths: Sequence[int], max_frames: int, max_batch: int = 64) -> List[Batch]:
+    """Length-bucketed batches: utterances sorted by length, cut so that B * T_max <= max_frames.
+    Padding frames cost FLOPs but are trimmed like models/tts/waveglow.py:82 trims to T*256."""
+    idx = sorted(indices, key=lambda i: (-int(lengths[i]), i))
+    batches, cur = [], []
+    for i in idx:
+        tmax = int(lengths[cur[0]]) if cur else int(lengths[i])
+        if cur and ((len(cur) + 1) * tmax > max_frames or len(cur) >= max_batch):
+            batches.append(Batch(cur, int(lengths[cur[0]])))
+            cur = []
+        cur.append(i)
+    if cur:
+        batches.append(Batch(cur, int(lengths[cur[0]])))
+    return batches
+
+
+def plan_batches(lengths: Sequence[int], world_size: int, max_frames: int, max_batch: int = 64) -> List[List[Batch]]:
+    """Global plan used by bench.py / the multi-GPU driver. ALL utterances are bucketed by length first
+    (so the spread inside a batch, hence the padding waste, does not grow with the number of ranks);
+    the number of batches is a multiple of world_size and the cuts are placed at equal shares of the
+    total frame count, so every rank gets the same number of near-equal batches; batches then go to
+    ranks longest-processing-time-first (cost = B * T_max frames). Deterministic: every rank computes
+    the same plan without communicating."""
+    n = len(lengths)
+    idx = sorted(range(n), key=lambda i: (-int(lengths[i]), i))
+    total = sum(int(l) for l in lengths)
+    nb = world_size * max(1, -(-total // (max_frames * world_size)))
+    nb = min(nb, n) if n >= world_size else nb
+    batches, cur, acc, k = [], [], 0, 1
+    for i in idx:
+        cur.append(i)
+        acc += int(lengths[i])
+        if (acc >= total * k / nb or len(cur) >= max_batch) and len(batches) < nb - 1:
+            batches.append(Batch(cur, int(lengths[cur[0]])))
+            cur = []
+            while acc >= total * k / nb:
+                k += 1
+    if cur:
+        batches.append(Batch(cur, int(lengths[cur[0]])))
+    order = sorted(range(len(batches)), key=lambda j: (-batches[j].T * len(batches[j].indices), j))
+    load = [0] * world_size
+    per_rank: List[List[Batch]] = [[] for _ in range(world_size)]
+    for j in order:
+        r = min(range(world_size), key=lambda q: (load[q], q))
+        per_rank[r].append(batches[j])
+        load[r] += batches[j].T * len(batches[j].indices)
+    return per_rank
+
+
+def padding_waste(batches: Sequence[Batch], lengths: Sequence[int]) -> float:
+    real = sum(int(lengths[i]) for b in batches for i in b.indices)
+    padded = sum(b.T * len(b.indices) for b in batches)
+    return 0.0 if padded == 0 else 1.0 - real / padded
