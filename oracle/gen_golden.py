@@ -49,7 +49,7 @@ def main(out_dir=os.path.join(ROOT, "tests", "golden")):
             hparams=np.frombuffer(hp.to_json().encode(), dtype=np.uint8),
             weight_seed=np.int64(wseed), weight_kwargs=np.frombuffer(repr(sorted(wkw.items())).encode(), dtype=np.uint8),
             weights_sha256=np.frombuffer(weights_digest(w).encode(), dtype=np.uint8),
-            input_seed=np.int64(iseed), mel=mel, z=z, sigma=np.float32(sigma),
+            input_seed=np.int64(iseed), mel=mel, z=z, sigma=np.float64(sigma),
             wave_reference_fp32=ref.astype(np.float32), wave_oracle_fp64=o64.astype(np.float64),
             wave_reference_deterministic=det.astype(np.float32),
             produced_by=np.frombuffer(("reference source over " + which_keras()).encode(), dtype=np.uint8),
