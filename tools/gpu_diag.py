@@ -1,0 +1,122 @@
+"""Staged GPU diagnostics (development aid, run under gpurun): each stage prints error statistics
+against the oracle so one remote call localises a bug. Usage: python tools/gpu_diag.py <stage>...
+stages: fp32 | gemm | bf16 | time"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle.waveglow_oracle import OracleWaveGlow                      # noqa: E402
+from text_to_speech_b200.engine import WaveGlowEngine, debug_gemm_bf16  # noqa: E402
+from text_to_speech_b200.weights import WaveGlowHParams, generate_weights, synthetic_inputs  # noqa: E402
+
+
+def stats(name, got, ref):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    err = np.abs(got - ref)
+    snr = 10 * np.log10((ref ** 2).mean() / max((err ** 2).mean(), 1e-300))
+    print(f"  {name:34s} max|ref| {np.abs(ref).max():9.4f}  max err {err.max():.3e}  rms err {np.sqrt((err**2).mean()):.3e}  "
+          f"SNR {snr:6.1f} dB  nan {int(np.isnan(got).sum())}", flush=True)
+    return err.max()
+
+
+def stage_fp32():
+    for C, B, T in ((64, 2, 5), (256, 1, 24)):
+        hp = WaveGlowHParams(n_channels=C)
+        w = generate_weights(hp, 1234, bias_std=0.05)
+        mel, z = synthetic_inputs(5, B, T, hp)
+        taps = {}
+        ref = OracleWaveGlow(hp, w).infer(mel, z, 0.6, taps=taps).numpy()
+        eng = WaveGlowEngine(hp, w, mode="fp32")
+        md, zd = torch.from_numpy(mel).cuda(), torch.from_numpy(z).cuda()
+        out = eng.infer_device(md, zd, sigma=0.6)
+        torch.cuda.synchronize()
+        print(f"fp32 C={C} B={B} T={T} launches={eng.last_launch_count}")
+        stats("spect", eng.debug_spect(B, T).cpu().numpy(), taps["spect"].reshape(-1, 640).numpy())
+        for (k, i) in [(11, -1), (11, 0), (11, 7), (10, 7), (0, 7)]:
+            h, acc = eng.debug_prefix(md, zd, 0.6, k, i)
+            torch.cuda.synchronize()
+            if i >= 0:
+                stats(f"h flow{k} layer{i}", h.cpu().numpy(), taps[f"flow{k}/layer{i}/audio"].reshape(-1, C).numpy())
+        stats("waveform", out.cpu().numpy(), ref)
+
+
+def stage_gemm():
+    for (M, N, K) in ((128, 256, 64), (128, 256, 128), (256, 512, 320), (1000, 1024, 1408)):
+        g = torch.Generator(device="cuda").manual_seed(1)
+        A = torch.randn(M, K, generator=g, device="cuda").to(torch.bfloat16)
+        W = torch.randn(N, K, generator=g, device="cuda").to(torch.bfloat16)
+        bias = torch.randn(N, generator=g, device="cuda")
+        D = debug_gemm_bf16(A, W, bias)
+        torch.cuda.synchronize()
+        ref = A.float() @ W.float().t() + bias
+        print(f"gemm {M}x{N}x{K}")
+        stats("D", D.cpu().numpy(), ref.cpu().numpy())
+        if M == 128 and K == 64:
+            e = (D - ref).abs().cpu().numpy()
+            print("   err by row block of 8:", np.round(e.reshape(16, 8, N).max(axis=(1, 2)), 3))
+            print("   err by col block of 32:", np.round(e.reshape(M, 8, 32).max(axis=(0, 2)), 3))
+
+
+def stage_bf16():
+    hp = WaveGlowHParams()
+    w = generate_weights(hp, 1234, bias_std=0.05)
+    B, T = 2, 7
+    mel, z = synthetic_inputs(5, B, T, hp)
+    taps = {}
+    o = OracleWaveGlow(hp, w)
+    ref = o.infer(mel, z, 0.6, taps=taps).numpy()
+    eng = WaveGlowEngine(hp, w, mode="bf16")
+    md, zd = torch.from_numpy(mel).cuda(), torch.from_numpy(z).cuda()
+    print("bf16: upsample + start conv")
+    h, acc = eng.debug_prefix(md, zd, 0.6, 11, -1)
+    torch.cuda.synchronize()
+    stats("spect", eng.debug_spect(B, T).cpu().numpy(), taps["spect"].reshape(-1, 640).numpy())
+    for (k, i) in [(11, 0), (11, 1), (11, 6), (11, 7), (10, 0), (10, 7), (0, 7)]:
+        h, acc = eng.debug_prefix(md, zd, 0.6, k, i)
+        torch.cuda.synchronize()
+        nh = hp.flow_channels()[k][0]
+        ref_acc = (o.w[f"block-{k}/end_conv/bias"] + taps[f"flow{k}/layer{i}/skip"] @ o.w[f"block-{k}/end_conv/kernel"][0])
+        stats(f"h flow{k} layer{i}", h.cpu().numpy(), taps[f"flow{k}/layer{i}/audio"].reshape(-1, 256).numpy())
+        stats(f"acc8 flow{k} layer{i}", acc.cpu().numpy()[:, :2 * nh], ref_acc.reshape(-1, 2 * nh).numpy())
+    out = eng.infer_device(md, zd, sigma=0.6)
+    torch.cuda.synchronize()
+    stats("waveform", out.cpu().numpy(), ref)
+    print("launches", eng.last_launch_count)
+
+
+def stage_time():
+    hp = WaveGlowHParams()
+    w = generate_weights(hp, 1234)
+    for mode, (B, T) in (("bf16", (16, 860)), ("fp32", (1, 200))):
+        eng = WaveGlowEngine(hp, w, mode=mode)
+        mel, z = synthetic_inputs(1, B, T, hp)
+        md, zd = torch.from_numpy(mel).cuda(), torch.from_numpy(z).cuda()
+        out = torch.empty(B, T * 256, device="cuda")
+        for _ in range(2):
+            eng.infer_device(md, zd, 0.6, out=out)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n = 3
+        for _ in range(n):
+            eng.infer_device(md, zd, 0.6, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        flop = 20308852.0 * B * T * 256
+        print(f"time {mode} B={B} T={T}: {ms:.2f} ms/infer, {B*T*256/ms*1e3/1e6:.2f} Msamples/s, {flop/ms/1e9:.1f} TFLOP/s algorithmic")
+        eng.close()
+
+
+if __name__ == "__main__":
+    for st in sys.argv[1:]:
+        t = time.time()
+        print(f"===== stage {st} =====", flush=True)
+        globals()["stage_" + st]()
+        print(f"===== stage {st} done in {time.time()-t:.1f}s =====", flush=True)
