@@ -105,6 +105,13 @@ int wg_last_launch_count(wg_handle h);
 
 /* ---- test / profiling hooks (used by tests/ and bench.py only) ------------------------------ */
 
+/* Per-kernel device timing: when enabled, wg_infer brackets every WN-layer launch (the dominant
+ * kernel: tc_wn_layer_kernel in BF16 mode, the in-conv+gate GEMM in FP32 mode) with CUDA events on
+ * the caller's stream. wg_profile_read synchronises those events and returns the summed duration
+ * (ms) and the number of launches recorded since the last read. */
+int wg_profile_enable(wg_handle h, int32_t enable);
+int wg_profile_read(wg_handle h, double* layer_ms_sum, int32_t* layer_launches);
+
 /* Runs wg_infer but stops after WN layer `stop_layer` of flow `stop_flow` (flows run 11..0) and
  * copies the residual stream h [B*L, C] (float32) and the pre-coupling accumulator [B*L, 8] to
  * the given DEVICE buffers (either may be NULL). stop_layer == -1: stop right after the start

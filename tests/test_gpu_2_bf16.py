@@ -74,7 +74,10 @@ def test_bf16_intermediates_against_oracle_taps(lib_built):
         eh = np.abs(h.cpu().numpy() - ref_h).max()
         ea = np.abs(acc.cpu().numpy()[:, :2 * nh] - ref_acc).max()
         print(f"flow {k} layer {i}: h err {eh:.3e} (|h| {np.abs(ref_h).max():.2f}), acc err {ea:.3e}")
-        assert eh <= 5e-2 * max(1.0, np.abs(ref_h).max()) and ea <= 3e-2, (k, i)
+        assert eh <= 5e-2 * max(1.0, np.abs(ref_h).max()), (k, i)
+        # the folded skip/end accumulator carries the bias terms of ALL layers from the start, so it is
+        # comparable with end(skip) only once the last layer has been added
+        assert i != hp.n_layers - 1 or ea <= 3e-2, (k, i)
 
 
 @pytest.mark.parametrize("B,T", [(1, 1), (1, 4), (2, 5), (3, 13), (1, 37)])

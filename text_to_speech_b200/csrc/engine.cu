@@ -80,6 +80,10 @@ struct wg_engine {
   float *dev_mel = nullptr, *dev_z = nullptr, *dev_out = nullptr;
   void* dev_ws = nullptr;
   size_t cap_mel = 0, cap_z = 0, cap_out = 0, cap_ws = 0;
+  // per-kernel profiling (wg_profile_enable / wg_profile_read)
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;   // pairs: [2i] start, [2i+1] stop
+  size_t ev_used = 0;
 };
 
 namespace {
@@ -256,6 +260,16 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
     z_off = a.n_inject;
   }
 
+  auto prof_mark = [&](void) {
+    if (!e->profiling) return;
+    if (e->ev_used == e->ev_pool.size()) {
+      cudaEvent_t ev;
+      CK(cudaEventCreate(&ev));
+      e->ev_pool.push_back(ev);
+    }
+    CK(cudaEventRecord(e->ev_pool[e->ev_used++], st));
+  };
+
   auto dump = [&](void) {
     if (h_out) CK(cudaMemcpyAsync(h_out, h32, (size_t)M * C * 4, cudaMemcpyDeviceToDevice, st));
     if (acc_out) CK(cudaMemcpyAsync(acc_out, acc8, (size_t)M * 8 * 4, cudaMemcpyDeviceToDevice, st));
@@ -278,7 +292,9 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
         g.seg[3] = ASeg{spect, S, S, 0};
         g.W = lw.Wcat; g.bias = lw.bcat; g.M = M; g.N = 2 * C; g.L = L;
         g.out0 = acts; g.ld0 = C;
+        prof_mark();
         launch_gemm<EPI_GATE>(e, g, st);
+        prof_mark();
         // res/skip 1x1 + residual add + skip accumulation (:129-139)
         GemmArgs r{};
         r.nseg = 1;
@@ -288,8 +304,10 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
         r.res_cols = last ? 0 : C; r.skip_init = (i == 0);
         launch_gemm<EPI_RES_SKIP>(e, r, st);
       } else {
+        prof_mark();
         e->launches += tc_wn_layer(plan, k * c.n_layers + i, d, last, i == 0, hcur, h32, acc8, lw.b1,
                                    lw.b2, lw.Wse, nullptr, st);
+        prof_mark();
         if (!last) hcur ^= 1;
       }
       if (k == stop_flow && i == stop_layer) {
@@ -558,6 +576,7 @@ void destroy_engine(wg_engine* e) {
   if (e->dev_out) cudaFree(e->dev_out);
   if (e->dev_ws) cudaFree(e->dev_ws);
   if (e->stream) cudaStreamDestroy(e->stream);
+  for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
   delete e;
 }
 
@@ -676,6 +695,29 @@ int wg_infer_host(wg_handle h, const float* mel_host, const float* z_host, float
 }
 
 int wg_last_launch_count(wg_handle h) { return h ? h->launches : 0; }
+
+int wg_profile_enable(wg_handle h, int32_t enable) {
+  if (!h) return WG_ERR_INVALID;
+  h->profiling = enable != 0;
+  h->ev_used = 0;
+  return WG_OK;
+}
+
+int wg_profile_read(wg_handle h, double* layer_ms_sum, int32_t* layer_launches) {
+  if (!h || !layer_ms_sum || !layer_launches) return WG_ERR_INVALID;
+  return guarded(h, [&] {
+    double sum = 0.0;
+    for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
+      CK(cudaEventSynchronize(h->ev_pool[i + 1]));
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, h->ev_pool[i], h->ev_pool[i + 1]));
+      sum += ms;
+    }
+    *layer_ms_sum = sum;
+    *layer_launches = (int32_t)(h->ev_used / 2);
+    h->ev_used = 0;
+  });
+}
 
 int wg_debug_infer_prefix(wg_handle h, const float* mel, const float* z, float sigma, int32_t deterministic,
                           int32_t B, int32_t T, void* workspace, size_t workspace_bytes, void* stream,

@@ -78,6 +78,15 @@ class WaveGlowEngine:
     def last_launch_count(self):
         return self._lib.wg_last_launch_count(self._h)
 
+    def profile_enable(self, on=True):
+        self._check(self._lib.wg_profile_enable(self._h, int(bool(on))), "wg_profile_enable")
+
+    def profile_read(self):
+        """(sum of WN-layer kernel durations in ms, number of launches) since the last read."""
+        ms, n = ctypes.c_double(), ctypes.c_int32()
+        self._check(self._lib.wg_profile_read(self._h, ctypes.byref(ms), ctypes.byref(n)), "wg_profile_read")
+        return ms.value, n.value
+
     # -- device-resident call (inputs already in HBM) ------------------------------------------------
     def infer_device(self, mel, z=None, sigma=1.0, deterministic=False, out=None):
         """mel [B,T,n_mel] / z [B,32T,8] / out [B,256T]: float32 CUDA tensors on this engine's device.
