@@ -112,6 +112,13 @@ int wg_last_launch_count(wg_handle h);
 int wg_profile_enable(wg_handle h, int32_t enable);
 int wg_profile_read(wg_handle h, double* layer_ms_sum, int32_t* layer_launches);
 
+/* In-kernel cycle counters of the fused WN-layer kernel, summed over CTAs and launches since the last
+ * read (only when the engine was created with the environment variable WG_LAYER_TIMING=1, BF16 mode):
+ * [0] MMA-warp total, [1] MMA waiting for TMA data, [2] MMA waiting for the epilogue, [3..5] epilogue
+ * waiting for chunk a / chunk b / GEMM2 accumulators, [6] gate-epilogue work, [7] residual-epilogue work,
+ * [8] TMA producer waiting for free stages. */
+int wg_debug_read_timing(wg_handle h, uint64_t* out16);
+
 /* Runs wg_infer but stops after WN layer `stop_layer` of flow `stop_flow` (flows run 11..0) and
  * copies the residual stream h [B*L, C] (float32) and the pre-coupling accumulator [B*L, 8] to
  * the given DEVICE buffers (either may be NULL). stop_layer == -1: stop right after the start

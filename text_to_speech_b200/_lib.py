@@ -23,7 +23,7 @@ ABI_VERSION = 1
 
 # every symbol include/wg_b200.h declares (tests check the library exports all of them)
 EXPORTS = ["wg_abi_version", "wg_create", "wg_destroy", "wg_last_error", "wg_workspace_bytes", "wg_infer",
-           "wg_infer_host", "wg_last_launch_count", "wg_profile_enable", "wg_profile_read", "wg_debug_infer_prefix", "wg_debug_get_spect",
+           "wg_infer_host", "wg_last_launch_count", "wg_profile_enable", "wg_profile_read", "wg_debug_read_timing", "wg_debug_infer_prefix", "wg_debug_get_spect",
            "wg_debug_gemm_bf16"]
 
 
@@ -100,6 +100,8 @@ def load_library():
     lib.wg_profile_enable.argtypes = [vp, i32]
     lib.wg_profile_read.restype = c.c_int
     lib.wg_profile_read.argtypes = [vp, c.POINTER(c.c_double), c.POINTER(i32)]
+    lib.wg_debug_read_timing.restype = c.c_int
+    lib.wg_debug_read_timing.argtypes = [vp, c.POINTER(c.c_uint64)]
     lib.wg_debug_infer_prefix.restype = c.c_int
     lib.wg_debug_infer_prefix.argtypes = [vp, vp, vp, c.c_float, i32, i32, i32, vp, c.c_size_t, vp, i32, i32, vp, vp]
     lib.wg_debug_get_spect.restype = c.c_int

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -52,7 +53,7 @@ struct LayerW {
   // bf16 mode (fp32 side arrays; the bf16 matrices live in the stacked arrays below)
   float* b1 = nullptr;    // [2C] chunk-packed order
   float* b2 = nullptr;    // [C]
-  float* Wse = nullptr;   // [C, 8] = Wskip @ Wend (fp32)
+  std::vector<float> wse_h;  // [C, 8] = Wskip @ Wend (fp32), host copy: passed in the kernel parameter bank
 };
 
 }  // namespace
@@ -81,6 +82,8 @@ struct wg_engine {
   void* dev_ws = nullptr;
   size_t cap_mel = 0, cap_z = 0, cap_out = 0, cap_ws = 0;
   // per-kernel profiling (wg_profile_enable / wg_profile_read)
+  unsigned long long* timing = nullptr;   // WG_LAYER_TIMING=1: in-kernel cycle counters (debug)
+  int dbg_flags = 0;                      // WG_DEBUG_FLAGS (see WnLayerParams::flags)
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;   // pairs: [2i] start, [2i+1] stop
   size_t ev_used = 0;
@@ -149,7 +152,7 @@ inline __nv_bfloat16 f2bf(float x) { return __float2bfloat16_rn(x); }
 
 struct Ws {  // workspace carving for one (B, T)
   size_t spect = 0, h32 = 0, acts = 0, skip = 0, acc8 = 0, audio0 = 0, audio1 = 0;
-  size_t spect16 = 0, h16a = 0, h16b = 0, aup16 = 0;
+  size_t spect16 = 0, h16a = 0, h16b = 0, hlo = 0, aup16 = 0;
   size_t total = 0;
 };
 
@@ -162,7 +165,7 @@ Ws carve(const wg_engine* e, int B, int T) {
     off = align_up(off + bytes, 1024);
     return o;
   };
-  w.h32 = take(M * e->C * 4);
+  if (e->cfg.mode == WG_MODE_FP32) w.h32 = take(M * e->C * 4);
   w.acc8 = take(M * 8 * 4);
   w.audio0 = take(M * 8 * 4);
   w.audio1 = take(M * 8 * 4);
@@ -174,6 +177,7 @@ Ws carve(const wg_engine* e, int B, int T) {
     w.spect16 = take(M * e->S * 2);
     w.h16a = take(M * e->C * 2);
     w.h16b = take(M * e->C * 2);
+    w.hlo = take(M * e->C * 2);
     w.aup16 = take((size_t)B * T * e->Kup * 2);
   }
   w.total = off;
@@ -218,7 +222,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
   const wg_config& c = e->cfg;
   const int C = e->C, S = e->S, R = e->R, L = T * R, M = B * L;
   const bool bf16 = c.mode == WG_MODE_BF16;
-  float* h32 = reinterpret_cast<float*>(base + w.h32);
+  float* h32 = bf16 ? nullptr : reinterpret_cast<float*>(base + w.h32);
   float* acc8 = reinterpret_cast<float*>(base + w.acc8);
   float* audio[2] = {reinterpret_cast<float*>(base + w.audio0), reinterpret_cast<float*>(base + w.audio1)};
   float* spect = reinterpret_cast<float*>(base + w.spect);
@@ -227,6 +231,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
   __nv_bfloat16* spect16 = reinterpret_cast<__nv_bfloat16*>(base + w.spect16);
   __nv_bfloat16* h16[2] = {reinterpret_cast<__nv_bfloat16*>(base + w.h16a),
                            reinterpret_cast<__nv_bfloat16*>(base + w.h16b)};
+  __nv_bfloat16* hlo = reinterpret_cast<__nv_bfloat16*>(base + w.hlo);
   __nv_bfloat16* aup16 = reinterpret_cast<__nv_bfloat16*>(base + w.aup16);
   const float* zz = deterministic ? nullptr : z;
 
@@ -242,7 +247,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
     launch_gemm<EPI_STORE>(e, g, st);
   } else {
     tc_prepare(plan, e->sm_count, B, T, L, C, S, e->Kup, c.n_mel_channels, c.n_flows * c.n_layers,
-               e->Wup16, R * S, e->W1, e->W2, aup16, spect16, h16[0], h16[1]);
+               e->Wup16, R * S, e->W1, e->W2, aup16, spect16, h16[0], h16[1], hlo);
     e->launches += tc_upsample(plan, mel, e->bup, st);
   }
 
@@ -254,7 +259,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
     a.first = 1; a.z = zz; a.n_group = c.n_group; a.z_off = 0; a.n_inject = e->flows[F - 1].n_rem;
     a.sigma = sigma; a.audio_out = audio[cur]; a.M = M; a.C = C;
     a.Wstart = e->flows[F - 1].Wstart; a.bstart = e->flows[F - 1].bstart;
-    a.n_half_next = e->flows[F - 1].n_half; a.h32 = h32; a.h16 = bf16 ? h16[hcur] : nullptr;
+    a.n_half_next = e->flows[F - 1].n_half; a.h32 = h32; a.h16 = bf16 ? h16[hcur] : nullptr; a.hlo = bf16 ? hlo : nullptr;
     if (bf16) { a.acc8_rearm = acc8; std::memcpy(a.acc8_init, e->flows[F - 1].bse8, sizeof a.acc8_init); }
     launch_boundary(e, a, st);
     z_off = a.n_inject;
@@ -271,7 +276,12 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
   };
 
   auto dump = [&](void) {
-    if (h_out) CK(cudaMemcpyAsync(h_out, h32, (size_t)M * C * 4, cudaMemcpyDeviceToDevice, st));
+    if (h_out && !bf16) CK(cudaMemcpyAsync(h_out, h32, (size_t)M * C * 4, cudaMemcpyDeviceToDevice, st));
+    if (h_out && bf16) {
+      const size_t n = (size_t)M * C;
+      hilo_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h16[hcur], hlo, h_out, n);
+      CK(cudaGetLastError());
+    }
     if (acc_out) CK(cudaMemcpyAsync(acc_out, acc8, (size_t)M * 8 * 4, cudaMemcpyDeviceToDevice, st));
   };
 
@@ -305,8 +315,8 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
         launch_gemm<EPI_RES_SKIP>(e, r, st);
       } else {
         prof_mark();
-        e->launches += tc_wn_layer(plan, k * c.n_layers + i, d, last, i == 0, hcur, h32, acc8, lw.b1,
-                                   lw.b2, lw.Wse, nullptr, st);
+        e->launches += tc_wn_layer(plan, k * c.n_layers + i, d, last, hcur, acc8, lw.b1, lw.b2, lw.wse_h.data(),
+                                   e->timing, e->dbg_flags, st);
         prof_mark();
         if (!last) hcur ^= 1;
       }
@@ -338,7 +348,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
       a.Wstart = e->flows[k - 1].Wstart; a.bstart = e->flows[k - 1].bstart;
       a.n_half_next = e->flows[k - 1].n_half; a.h32 = h32;
       hcur = 0;
-      a.h16 = bf16 ? h16[hcur] : nullptr;
+      a.h16 = bf16 ? h16[hcur] : nullptr; a.hlo = bf16 ? hlo : nullptr;
       if (bf16) { a.acc8_rearm = acc8; std::memcpy(a.acc8_init, e->flows[k - 1].bse8, sizeof a.acc8_init); }
     } else {
       a.audio_out = out;  // [B*L, 8] == [B, 8L]  (waveglow_arch.py:306)
@@ -518,7 +528,9 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
         lw.brs = upload(e, std::vector<float>(rb.data, rb.data + rs));
       } else {
         // chunk packing: 256-column chunk q = [tanh 128q..128q+127 | sigmoid 128q..128q+127]
-        std::vector<float> b1((size_t)2 * C), b2((size_t)C, 0.f), wse((size_t)C * 8, 0.f);
+        std::vector<float> b1((size_t)2 * C), b2((size_t)C, 0.f);
+        lw.wse_h.assign((size_t)C * 8, 0.f);
+        std::vector<float>& wse = lw.wse_h;
         __nv_bfloat16* w1 = w1all.data() + ((size_t)k * NL + i) * 2 * C * K1;
         for (int pcol = 0; pcol < 2 * C; ++pcol) {
           const int chunk = pcol >> 8, wi = pcol & 255;
@@ -549,7 +561,6 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
         }
         lw.b1 = upload(e, b1);
         lw.b2 = upload(e, b2);
-        lw.Wse = upload(e, wse);
       }
     }
     if (c.mode == WG_MODE_BF16) {
@@ -560,6 +571,14 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
     e->W1 = upload(e, w1all);
     e->W2 = upload(e, w2all);
     tc_init();
+    if (const char* f = std::getenv("WG_DEBUG_FLAGS")) e->dbg_flags = std::atoi(f);
+    if (const char* t = std::getenv("WG_LAYER_TIMING")) {
+      if (t[0] == '1') {
+        CK(cudaMalloc(&e->timing, 16 * sizeof(unsigned long long)));
+        e->allocs.push_back(e->timing);
+        CK(cudaMemset(e->timing, 0, 16 * sizeof(unsigned long long)));
+      }
+    }
   }
   CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
 }
@@ -716,6 +735,16 @@ int wg_profile_read(wg_handle h, double* layer_ms_sum, int32_t* layer_launches) 
     *layer_ms_sum = sum;
     *layer_launches = (int32_t)(h->ev_used / 2);
     h->ev_used = 0;
+  });
+}
+
+int wg_debug_read_timing(wg_handle h, uint64_t* out16) {
+  if (!h || !out16) return WG_ERR_INVALID;
+  return guarded(h, [&] {
+    if (!h->timing) fail(WG_ERR_INVALID, "layer timing is off (set WG_LAYER_TIMING=1 before wg_create, BF16 mode)");
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out16, h->timing, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CK(cudaMemset(h->timing, 0, 16 * sizeof(unsigned long long)));
   });
 }
 

@@ -218,7 +218,8 @@ struct BoundaryArgs {
   int n_half_next;
   int C;
   float* h32;             // [M, C]
-  __nv_bfloat16* h16;     // [M, C] or null
+  __nv_bfloat16* h16;     // [M, C] or null: bf16(h)            (bf16 mode: residual stream = hi + lo)
+  __nv_bfloat16* hlo;     // [M, C] or null: bf16(h - bf16(h))
   int M;
   // bf16 mode: re-arm the folded skip/end accumulator for the next flow (acc8 = bias term) once
   // this flow's value has been consumed
@@ -290,13 +291,18 @@ flow_boundary_kernel(const __grid_constant__ BoundaryArgs a) {
       const float4 w = *reinterpret_cast<const float4*>(a.Wstart + (size_t)j * a.C + c4);
       v.x = fmaf(x, w.x, v.x); v.y = fmaf(x, w.y, v.y); v.z = fmaf(x, w.z, v.z); v.w = fmaf(x, w.w, v.w);
     }
-    *reinterpret_cast<float4*>(a.h32 + (size_t)m * a.C + c4) = v;
+    if (a.h32) *reinterpret_cast<float4*>(a.h32 + (size_t)m * a.C + c4) = v;
     if (a.h16) {
       __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
       uint2 u;
       u.x = *reinterpret_cast<uint32_t*>(&p0);
       u.y = *reinterpret_cast<uint32_t*>(&p1);
       *reinterpret_cast<uint2*>(a.h16 + (size_t)m * a.C + c4) = u;
+      const float2 f0 = __bfloat1622float2(p0), f1 = __bfloat1622float2(p1);
+      __nv_bfloat162 q0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y), q1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+      u.x = *reinterpret_cast<uint32_t*>(&q0);
+      u.y = *reinterpret_cast<uint32_t*>(&q1);
+      *reinterpret_cast<uint2*>(a.hlo + (size_t)m * a.C + c4) = u;
     }
   }
 }

@@ -18,6 +18,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstring>
+
 #include "common.cuh"
 
 namespace wg {
@@ -82,6 +84,18 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, 
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* m, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---- tcgen05 ------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
@@ -263,10 +277,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // ================================================================================================
 // Fused WN layer (C = 256, S = 640).  One CTA per SM, persistent over 128-row tiles.
 //   warp 0      TMA producer        warp 1      TMEM alloc + MMA issuer       warps 2..9  epilogue
+//
+// The residual stream h is kept as a bf16 pair (hi, lo) with hi = bf16(h), lo = bf16(h - hi): hi is the
+// MMA operand of the next layer's dilated conv, hi + lo carries ~16 mantissa bits. The residual add
+// itself runs on the tensor core:  D2 = acts @ Wres + hi @ I + lo @ I  (I = 64x64 identity B tile), so
+// the epilogue never reads h back from global memory.
+//
 // TMEM: two 256-column fp32 regions R0/R1.  Tile with parity p:
 //   GEMM1 chunk a (gate channels 0..127)   -> R[p]      K = 22 blocks of 64 (12 conv + 10 cond)
 //   GEMM1 chunk b (gate channels 128..255) -> R[p^1]    (issued while the epilogue drains chunk a)
-//   GEMM2 (res)                            -> R[p]      A = acts tile in shared memory
+//   GEMM2 + residual                       -> R[p]      the half that depends only on chunk a's acts
+//                                                       is issued before chunk b's epilogue finishes
 // ================================================================================================
 constexpr int WL_C = 256, WL_S = 640, WL_BM = 128, WL_BK = 64;
 constexpr int WL_STAGES = 3;
@@ -281,13 +302,14 @@ constexpr int WL_ACTS_BYTES = WL_BM * WL_C * 2;        // 64 KB
 constexpr int WL_EPI_WARPS = 8, WL_EPI_THREADS = WL_EPI_WARPS * 32;
 constexpr int WL_THREADS = 64 + WL_EPI_THREADS;        // 320
 constexpr int WL_OFF_ACTS = WL_STAGES * WL_STAGE_BYTES;
-constexpr int WL_OFF_WSE = WL_OFF_ACTS + WL_ACTS_BYTES;
-constexpr int WL_OFF_B1 = WL_OFF_WSE + WL_C * 8 * 4;
+constexpr int WL_OFF_I64 = WL_OFF_ACTS + WL_ACTS_BYTES;   // 64x64 bf16 identity, K-major SWIZZLE_128B (8 KB)
+constexpr int WL_OFF_B1 = WL_OFF_I64 + 64 * 128;
 constexpr int WL_OFF_B2 = WL_OFF_B1 + 2 * WL_C * 4;
-constexpr int WL_OFF_O8 = WL_OFF_B2 + WL_C * 4;          // [128][8] fp32: partial fold sums of the hf=1 warps
+constexpr int WL_OFF_O8 = WL_OFF_B2 + WL_C * 4;           // [128][8] fp32: partial fold sums of the hf=1 warps
 constexpr int WL_OFF_BARS = WL_OFF_O8 + WL_BM * 8 * 4;
-constexpr int WL_NBARS = 2 * WL_STAGES + 3 + 2 + 1 + 1;
-constexpr int WL_SMEM = WL_OFF_BARS + WL_NBARS * 8 + 16 + 1024;
+constexpr int WL_NBARS = 2 * WL_STAGES + 3 + 2 + 3;
+constexpr int WL_SMEM = WL_OFF_BARS + WL_NBARS * 8 + 16;
+static_assert(WL_SMEM <= 232448, "shared memory budget");
 
 struct WnLayerParams {
   int L, tiles_per_b, n_tiles;
@@ -295,38 +317,104 @@ struct WnLayerParams {
   int dilation;
   const float* b1;   // [512] chunk-packed
   const float* b2;   // [256]
-  const float* Wse;  // [256, 8]
-  float* h32;        // [B*L, 256] fp32 master residual stream (updated in place)
-  __nv_bfloat16* h16_out;  // [B*L, 256] bf16 shadow written for the next layer
+  __nv_bfloat16* hi_out;   // [B*L, 256] bf16(h) written for the next layer
+  __nv_bfloat16* lo;       // [B*L, 256] bf16(h - hi), updated in place (rows are tile-private)
   float* acc8;       // [B*L, 8] folded skip/end accumulator (read-modify-write, one thread per row)
+  unsigned long long* timing;   // optional [16] cycle counters (debug), may be null
+  int flags;   // debug/tuning: 1 = skip every other W1 tile load (wrong results; L2-bandwidth probe),
+               //               2 = skip every other activation tile load (same), 8 = L2-prefetch the next tile
 };
+
+struct WnLayerConst {   // kernel-parameter (constant bank) copy: every read is warp-uniform
+  float wse[WL_C * 8];  // Wskip @ Wend, [256][8]
+};
+
+// Residual epilogue for 16 columns of one row: v = accumulator + bias; pass 0 stages hi = bf16(v), pass 1
+// stages lo = bf16(v - hi) into the SWIZZLE_128B staging tile.
+__device__ __forceinline__ void resid_step(const uint32_t (&r)[16], const float* bb, uint8_t* stg, int gi, int row,
+                                           int pass) {
+  uint32_t w[8];
+#pragma unroll
+  for (int j2 = 0; j2 < 8; ++j2) {
+    const float2 b2v = *reinterpret_cast<const float2*>(bb + 2 * j2);
+    const float v0 = __uint_as_float(r[2 * j2]) + b2v.x;
+    const float v1 = __uint_as_float(r[2 * j2 + 1]) + b2v.y;
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+    const float2 hf2 = __bfloat1622float2(h2);
+    const uint32_t hi_bits = *reinterpret_cast<const uint32_t*>(&h2);
+    const uint32_t lo_bits = pack_bf16x2(v0 - hf2.x, v1 - hf2.y);
+    w[j2] = pass == 0 ? hi_bits : lo_bits;
+  }
+  uint8_t* dst = stg + (gi >> 2) * (128 * 64 * 2);
+  const int c0 = (gi & 3) * 2;
+  *reinterpret_cast<uint4*>(dst + ((c0 ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+  *reinterpret_cast<uint4*>(dst + (((c0 + 1) ^ (row & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+// Gate epilogue for 16 gate channels of one row: tanh * sigmoid on the fp32 accumulator (registers t/g),
+// fold into the skip/end accumulator (weights from the kernel-parameter bank, warp-uniform address), and
+// bf16 acts into the GEMM2 A tile (K-major SWIZZLE_128B: 16-byte chunk c of row r sits at c ^ (r & 7)).
+template <bool LAST>
+__device__ __forceinline__ void gate_step(const uint32_t (&t)[16], const uint32_t (&g)[16], const float* bT,
+                                          const float* wse, uint8_t* kblk, int st, int row, float (&o8)[8]) {
+  const float* bG = bT + 128;
+  float a[16];
+#pragma unroll
+  for (int j4 = 0; j4 < 4; ++j4) {
+    const float4 bt4 = *reinterpret_cast<const float4*>(bT + 4 * j4);
+    const float4 bg4 = *reinterpret_cast<const float4*>(bG + 4 * j4);
+    const float btv[4] = {bt4.x, bt4.y, bt4.z, bt4.w}, bgv[4] = {bg4.x, bg4.y, bg4.z, bg4.w};
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = 4 * j4 + jj;
+      const float xt = __uint_as_float(t[j]) + btv[jj];
+      const float xg = __uint_as_float(g[j]) + bgv[jj];
+      a[j] = tanh_fast(xt) * fmaf(0.5f, tanh_fast(0.5f * xg), 0.5f);
+      const float4 w0 = *reinterpret_cast<const float4*>(wse + j * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(wse + j * 8 + 4);
+      o8[0] = fmaf(a[j], w0.x, o8[0]); o8[1] = fmaf(a[j], w0.y, o8[1]);
+      o8[2] = fmaf(a[j], w0.z, o8[2]); o8[3] = fmaf(a[j], w0.w, o8[3]);
+      o8[4] = fmaf(a[j], w1.x, o8[4]); o8[5] = fmaf(a[j], w1.y, o8[5]);
+      o8[6] = fmaf(a[j], w1.z, o8[6]); o8[7] = fmaf(a[j], w1.w, o8[7]);
+    }
+  }
+  if (!LAST) {
+    const uint4 v0 = make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]), pack_bf16x2(a[6], a[7]));
+    const uint4 v1 = make_uint4(pack_bf16x2(a[8], a[9]), pack_bf16x2(a[10], a[11]), pack_bf16x2(a[12], a[13]), pack_bf16x2(a[14], a[15]));
+    *reinterpret_cast<uint4*>(kblk + (((st * 2) ^ (row & 7)) << 4)) = v0;
+    *reinterpret_cast<uint4*>(kblk + (((st * 2 + 1) ^ (row & 7)) << 4)) = v1;
+  }
+}
 
 template <bool LAST>
 __global__ void __launch_bounds__(WL_THREADS, 1)
-tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_spect,
-                   const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2,
-                   const WnLayerParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_ho,
+                   const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_spect, const __grid_constant__ CUtensorMap map_w1,
+                   const __grid_constant__ CUtensorMap map_w2, const WnLayerParams p,
+                   const __grid_constant__ WnLayerConst cw) {
+  extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
-  float* s_wse = reinterpret_cast<float*>(smem + WL_OFF_WSE);
   float* s_b1 = reinterpret_cast<float*>(smem + WL_OFF_B1);
   float* s_b2 = reinterpret_cast<float*>(smem + WL_OFF_B2);
   float* s_o8 = reinterpret_cast<float*>(smem + WL_OFF_O8);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WL_OFF_BARS);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + WL_NBARS);
-  const uint32_t bar_base = smem_u32(bars);
+  const uint32_t bar_base = smem_base + WL_OFF_BARS;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (WL_STAGES + s); };
   auto dfull_bar = [&](int i) { return bar_base + 8u * (2 * WL_STAGES + i); };        // 0: chunk a, 1: chunk b, 2: GEMM2
-  auto drained_bar = [&](int i) { return bar_base + 8u * (2 * WL_STAGES + 3 + i); };  // chunk a / b accumulators read out
-  const uint32_t acts_bar = bar_base + 8u * (2 * WL_STAGES + 5);                      // acts tile complete in smem
-  const uint32_t epi2_bar = bar_base + 8u * (2 * WL_STAGES + 6);                      // GEMM2 accumulator read out
+  auto drained_bar = [&](int i) { return bar_base + 8u * (2 * WL_STAGES + 3 + i); };  // LAST: chunk a / b accumulators read out
+  const uint32_t actsa_bar = bar_base + 8u * (2 * WL_STAGES + 5);                     // acts K-blocks 0,1 in smem, D1a read out
+  const uint32_t acts_bar = bar_base + 8u * (2 * WL_STAGES + 6);                      // acts K-blocks 2,3 in smem, D1b read out
+  const uint32_t epi2_bar = bar_base + 8u * (2 * WL_STAGES + 7);                      // GEMM2 accumulator read out
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((smem_base & 1023u) != 0u) __trap();   // SWIZZLE_128B tiles need 1024-byte aligned bases
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_h);
+    prefetch_tmap(&map_ho);
+    prefetch_tmap(&map_lo);
     prefetch_tmap(&map_spect);
     prefetch_tmap(&map_w1);
     prefetch_tmap(&map_w2);
@@ -336,6 +424,7 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
     }
     for (int i = 0; i < 3; ++i) mbar_init(dfull_bar(i), 1);
     for (int i = 0; i < 2; ++i) mbar_init(drained_bar(i), WL_EPI_THREADS);
+    mbar_init(actsa_bar, WL_EPI_THREADS);
     mbar_init(acts_bar, WL_EPI_THREADS);
     mbar_init(epi2_bar, WL_EPI_THREADS);
     fence_barrier_init();
@@ -344,100 +433,171 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
     tmem_alloc(smem_u32(tmem_slot), 512);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < WL_C * 8; i += WL_THREADS) s_wse[i] = p.Wse[i];
   for (int i = threadIdx.x; i < 2 * WL_C; i += WL_THREADS) s_b1[i] = p.b1[i];
-  if (!LAST)
+  if (!LAST) {
     for (int i = threadIdx.x; i < WL_C; i += WL_THREADS) s_b2[i] = p.b2[i];
+    // identity B tile: element (n, k) of a [64 x 64] K-major SWIZZLE_128B tile sits at byte
+    // n*128 + (((k>>3) ^ (n&7)) << 4) + (k&7)*2
+    uint32_t* i64w = reinterpret_cast<uint32_t*>(smem + WL_OFF_I64);
+    for (int i = threadIdx.x; i < 64 * 32; i += WL_THREADS) {
+      const int n = i >> 5, w = i & 31;                 // 32-bit word w of row n (physical position)
+      const int chunk_phys = w >> 2, chunk_log = chunk_phys ^ (n & 7);
+      const int k0 = chunk_log * 8 + (w & 3) * 2;       // logical k of the low half-word
+      uint32_t v = 0;
+      if (k0 == n) v = 0x00003F80u;                      // bf16 1.0 in the low half
+      if (k0 + 1 == n) v = 0x3F800000u;
+      i64w[i] = v;
+    }
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const bool timing = p.timing != nullptr;
 
   if (warp == 0) {
     // ===================================== TMA producer ======================================
     if (lane == 0) {
       uint32_t it = 0;  // running stage counter
+      long long t_wait = 0;
+      auto acquire = [&](uint32_t bytes) -> uint32_t {
+        const int s = it % WL_STAGES;
+        const uint32_t ph = (it / WL_STAGES) & 1;
+        long long t0 = 0;
+        if (timing) t0 = clock64();
+        mbar_wait(empty_bar(s), ph ^ 1);
+        if (timing) t_wait += clock64() - t0;
+        mbar_expect_tx(full_bar(s), bytes);
+        return static_cast<uint32_t>(s);
+      };
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const int b = tile / p.tiles_per_b, l0 = (tile - b * p.tiles_per_b) * WL_BM;
         for (int q = 0; q < 2; ++q) {
+          // during the second chunk, pull the NEXT tile's activation rows into L2, one box per stage
+          // (spread out so the prefetches never queue ahead of a demand load in the TMA unit)
+          const int nt = tile + static_cast<int>(gridDim.x);
+          const bool pf = q == 1 && nt < p.n_tiles && (p.flags & 8);   // measured slower on B200 (r01): off unless asked
+          const int nb = nt / p.tiles_per_b, nl0 = (nt - nb * p.tiles_per_b) * WL_BM;
           for (int kb = 0; kb < WL_KB1; ++kb, ++it) {
-            const int s = it % WL_STAGES;
-            const uint32_t ph = (it / WL_STAGES) & 1;
-            mbar_wait(empty_bar(s), ph ^ 1);
-            mbar_expect_tx(full_bar(s), WL_STAGE_BYTES);
+            const bool skip_b = (p.flags & 1) && (kb & 1), skip_a = (p.flags & 2) && (kb & 1);
+            const uint32_t s = acquire((skip_a ? 0 : WL_A_BYTES) + (skip_b ? 0 : WL_B_BYTES));
             const uint32_t a_dst = smem_base + s * WL_STAGE_BYTES;
             if (kb < WL_KB_CONV) {
               const int tap = kb >> 2, cblk = kb & 3;
-              tma_load_3d(a_dst, &map_h, full_bar(s), cblk * WL_BK, l0 + (tap - 1) * p.dilation, b);
+              if (!skip_a) tma_load_3d(a_dst, &map_h, full_bar(s), cblk * WL_BK, l0 + (tap - 1) * p.dilation, b);
+              if (pf) tma_prefetch_3d(&map_h, cblk * WL_BK, nl0 + (tap - 1) * p.dilation, nb);
             } else {
-              tma_load_3d(a_dst, &map_spect, full_bar(s), (kb - WL_KB_CONV) * WL_BK, l0, b);
+              if (!skip_a) tma_load_3d(a_dst, &map_spect, full_bar(s), (kb - WL_KB_CONV) * WL_BK, l0, b);
+              if (pf) tma_prefetch_3d(&map_spect, (kb - WL_KB_CONV) * WL_BK, nl0, nb);
             }
-            tma_load_2d(a_dst + WL_A_BYTES, &map_w1, full_bar(s), kb * WL_BK, p.layer * 2 * WL_C + q * 256);
+            if (!skip_b) tma_load_2d(a_dst + WL_A_BYTES, &map_w1, full_bar(s), kb * WL_BK, p.layer * 2 * WL_C + q * 256);
           }
         }
         if (!LAST) {
-          for (int kb = 0; kb < WL_KB2; ++kb, ++it) {
-            const int s = it % WL_STAGES;
-            const uint32_t ph = (it / WL_STAGES) & 1;
-            mbar_wait(empty_bar(s), ph ^ 1);
-            mbar_expect_tx(full_bar(s), WL_B_BYTES);
-            tma_load_2d(smem_base + s * WL_STAGE_BYTES + WL_A_BYTES, &map_w2, full_bar(s), kb * WL_BK, p.layer * WL_C);
+          // consumption order of the MMA warp: W2/hi blocks 0,1 | lo blocks 0..3 | W2/hi blocks 2,3
+          for (int step = 0; step < 6; ++step, ++it) {
+            if (step == 2 || step == 3) {
+              const uint32_t s = acquire(2 * WL_A_BYTES);
+              const uint32_t dst = smem_base + s * WL_STAGE_BYTES;
+              const int kb = (step - 2) * 2;
+              tma_load_3d(dst, &map_lo, full_bar(s), kb * WL_BK, l0, b);
+              tma_load_3d(dst + WL_A_BYTES, &map_lo, full_bar(s), (kb + 1) * WL_BK, l0, b);
+            } else {
+              const int kb = step < 2 ? step : step - 2;
+              const uint32_t s = acquire(WL_STAGE_BYTES);
+              const uint32_t dst = smem_base + s * WL_STAGE_BYTES;
+              tma_load_3d(dst, &map_h, full_bar(s), kb * WL_BK, l0, b);
+              tma_load_2d(dst + WL_A_BYTES, &map_w2, full_bar(s), kb * WL_BK, p.layer * WL_C);
+            }
           }
         }
       }
+      if (timing) atomicAdd(p.timing + 8, static_cast<unsigned long long>(t_wait));
     }
   } else if (warp == 1) {
     // ====================================== MMA issuer =======================================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, 256);
+      constexpr uint32_t idesc_id = umma_idesc_bf16(128, 64);
+      const uint64_t idesc64 = umma_desc_sw128(smem_base + WL_OFF_I64);
       uint32_t it = 0;
       uint32_t n = 0;  // local tile counter
+      long long t_full = 0, t_epi = 0, t_begin = 0;
+      if (timing) t_begin = clock64();
+      auto wait_full = [&]() -> uint32_t {
+        const int s = it % WL_STAGES;
+        const uint32_t ph = (it / WL_STAGES) & 1;
+        long long t0 = 0;
+        if (timing) t0 = clock64();
+        mbar_wait(full_bar(s), ph);
+        if (timing) t_full += clock64() - t0;
+        tc_fence_after();
+        return smem_base + s * WL_STAGE_BYTES;
+      };
+      auto wait_epi = [&](uint32_t bar, uint32_t ph) {
+        long long t0 = 0;
+        if (timing) t0 = clock64();
+        mbar_wait(bar, ph);
+        if (timing) t_epi += clock64() - t0;
+        tc_fence_after();
+      };
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++n) {
         const uint32_t par = LAST ? 0u : (n & 1u);
         const uint32_t prev_ph = (n - 1) & 1u;
         for (int q = 0; q < 2; ++q) {
           const uint32_t d_tmem = tmem_base + 256u * (q == 0 ? par : (par ^ 1u));
           if (n > 0) {
-            if (LAST) {
-              mbar_wait(drained_bar(q), prev_ph);   // this region still holds tile n-1's chunk q
-              tc_fence_after();
-            } else if (q == 1) {
-              mbar_wait(epi2_bar, prev_ph);         // R[p^1] held GEMM2 of tile n-1
-              tc_fence_after();
-            }
+            if (LAST) wait_epi(drained_bar(q), prev_ph);   // this region still holds tile n-1's chunk q
+            else if (q == 1) wait_epi(epi2_bar, prev_ph);  // R[p^1] held GEMM2 of tile n-1
           }
           for (int kb = 0; kb < WL_KB1; ++kb, ++it) {
-            const int s = it % WL_STAGES;
-            const uint32_t ph = (it / WL_STAGES) & 1;
-            mbar_wait(full_bar(s), ph);
-            tc_fence_after();
-            const uint32_t a_addr = smem_base + s * WL_STAGE_BYTES;
+            const uint32_t a_addr = wait_full();
             const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + WL_A_BYTES);
 #pragma unroll
             for (int k = 0; k < WL_BK / 16; ++k)
               umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
-            tc_commit(empty_bar(s));
+            tc_commit(empty_bar(it % WL_STAGES));
           }
           tc_commit(dfull_bar(q));
         }
         if (!LAST) {
-          mbar_wait(acts_bar, n & 1u);   // gate epilogue wrote all of acts and drained both D1 regions
-          tc_fence_after();
           const uint32_t d_tmem = tmem_base + 256u * par;
-          for (int kb = 0; kb < WL_KB2; ++kb, ++it) {
-            const int s = it % WL_STAGES;
-            const uint32_t ph = (it / WL_STAGES) & 1;
-            mbar_wait(full_bar(s), ph);
-            tc_fence_after();
-            const uint64_t adesc = umma_desc_sw128(smem_base + WL_OFF_ACTS + kb * WL_A_BYTES);
-            const uint64_t bdesc = umma_desc_sw128(smem_base + s * WL_STAGE_BYTES + WL_A_BYTES);
+          wait_epi(actsa_bar, n & 1u);   // acts blocks 0,1 written, D1a (this region) read out
+          for (int step = 0; step < 6; ++step, ++it) {
+            if (step == 4) wait_epi(acts_bar, n & 1u);   // acts blocks 2,3 written, D1b read out
+            const uint32_t st_addr = wait_full();
+            if (step == 2 || step == 3) {
+              // lo blocks 2j, 2j+1 -> identity add into columns [128 j', ...)
+              const int kb = (step - 2) * 2;
 #pragma unroll
-            for (int k = 0; k < WL_BK / 16; ++k)
-              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
-            tc_commit(empty_bar(s));
+              for (int h2 = 0; h2 < 2; ++h2) {
+                const uint64_t adesc = umma_desc_sw128(st_addr + h2 * WL_A_BYTES);
+#pragma unroll
+                for (int k = 0; k < WL_BK / 16; ++k)
+                  umma_bf16(d_tmem + 64u * (kb + h2), adesc + 2 * k, idesc64 + 2 * k, idesc_id, 1u);
+              }
+            } else {
+              const int kb = step < 2 ? step : step - 2;
+              const uint64_t adesc = umma_desc_sw128(smem_base + WL_OFF_ACTS + kb * WL_A_BYTES);
+              const uint64_t bdesc = umma_desc_sw128(st_addr + WL_A_BYTES);
+#pragma unroll
+              for (int k = 0; k < WL_BK / 16; ++k)
+                umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (step | k) ? 1u : 0u);
+              const uint64_t hdesc = umma_desc_sw128(st_addr);   // hi block kb (centre tap rows)
+#pragma unroll
+              for (int k = 0; k < WL_BK / 16; ++k)
+                umma_bf16(d_tmem + 64u * kb, hdesc + 2 * k, idesc64 + 2 * k, idesc_id, 1u);
+            }
+            tc_commit(empty_bar(it % WL_STAGES));
           }
           tc_commit(dfull_bar(2));
         }
+      }
+      if (timing) {
+        atomicAdd(p.timing + 0, static_cast<unsigned long long>(clock64() - t_begin));
+        atomicAdd(p.timing + 1, static_cast<unsigned long long>(t_full));
+        atomicAdd(p.timing + 2, static_cast<unsigned long long>(t_epi));
       }
     }
   } else {
@@ -448,7 +608,8 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     uint8_t* acts = smem + WL_OFF_ACTS;
-    float* scratch = reinterpret_cast<float*>(acts + we * 8192);   // epilogue-2 transposition tile [32][64]
+    const bool tmr = timing && we == 0 && lane == 0;
+    long long t_w0 = 0, t_w1 = 0, t_w2 = 0, t_e1 = 0, t_e2 = 0;
     uint32_t n = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++n) {
       const int b = tile / p.tiles_per_b, l0 = (tile - b * p.tiles_per_b) * WL_BM;
@@ -461,48 +622,44 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
       for (int j = 0; j < 8; ++j) o8[j] = 0.f;
 
       // ---- gate epilogue: chunk q holds gate channels [128 q, 128 q + 128) ---------------------
+      // (loops deliberately NOT fully unrolled: the kernel must stay inside the instruction cache)
+#pragma unroll 1
       for (int q = 0; q < 2; ++q) {
+        long long t0 = 0;
+        if (tmr) t0 = clock64();
         mbar_wait(dfull_bar(q), ph);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + lane_addr + 256u * (q == 0 ? par : (par ^ 1u));
+        long long t1 = 0;
+        if (tmr) { t1 = clock64(); (q == 0 ? t_w0 : t_w1) += t1 - t0; }
+        const uint32_t taddr = tmem_base + lane_addr + 256u * (q == 0 ? par : (par ^ 1u)) + hf * 64;
         uint8_t* kblk = acts + (q * 2 + hf) * WL_A_BYTES + row * 128;   // K-block (64 channels) row
+        const float* bT0 = s_b1 + q * 256 + hf * 64;
+        const float* wse0 = cw.wse + (q * 128 + hf * 64) * 8;
+        uint32_t t0r[16], g0r[16], t1r[16], g1r[16];
+        tmem_ld16(taddr, t0r);
+        tmem_ld16(taddr + 128, g0r);
 #pragma unroll 1
-        for (int st = 0; st < 4; ++st) {
-          uint32_t t[16], g[16];
-          const int colT = hf * 64 + st * 16;
-          tmem_ld16(taddr + colT, t);
-          tmem_ld16(taddr + 128 + colT, g);
+        for (int sp = 0; sp < 2; ++sp) {          // two steps of 16 channels per iteration (double-buffered)
+          const int st = 2 * sp;
           tmem_ld_wait();
-          const float* bT = s_b1 + q * 256 + colT;
-          const float* bG = bT + 128;
-          const float* wse = s_wse + (q * 128 + colT) * 8;
-          float a[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float xt = __uint_as_float(t[j]) + bT[j];
-            const float xg = __uint_as_float(g[j]) + bG[j];
-            a[j] = tanh_fast(xt) * fmaf(0.5f, tanh_fast(0.5f * xg), 0.5f);
-            const float4 w0 = *reinterpret_cast<const float4*>(wse + j * 8);
-            const float4 w1 = *reinterpret_cast<const float4*>(wse + j * 8 + 4);
-            o8[0] = fmaf(a[j], w0.x, o8[0]); o8[1] = fmaf(a[j], w0.y, o8[1]);
-            o8[2] = fmaf(a[j], w0.z, o8[2]); o8[3] = fmaf(a[j], w0.w, o8[3]);
-            o8[4] = fmaf(a[j], w1.x, o8[4]); o8[5] = fmaf(a[j], w1.y, o8[5]);
-            o8[6] = fmaf(a[j], w1.z, o8[6]); o8[7] = fmaf(a[j], w1.w, o8[7]);
+          tmem_ld16(taddr + (st + 1) * 16, t1r);
+          tmem_ld16(taddr + 128 + (st + 1) * 16, g1r);
+          gate_step<LAST>(t0r, g0r, bT0 + st * 16, wse0 + st * 128, kblk, st, row, o8);
+          tmem_ld_wait();
+          if (sp == 0) {
+            tmem_ld16(taddr + (st + 2) * 16, t0r);
+            tmem_ld16(taddr + 128 + (st + 2) * 16, g0r);
           }
-          if (!LAST) {
-            // bf16 acts into the K-major SWIZZLE_128B A tile of GEMM2: 16-byte chunk c of row r at c ^ (r & 7)
-            const uint4 v0 = make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]), pack_bf16x2(a[6], a[7]));
-            const uint4 v1 = make_uint4(pack_bf16x2(a[8], a[9]), pack_bf16x2(a[10], a[11]), pack_bf16x2(a[12], a[13]), pack_bf16x2(a[14], a[15]));
-            *reinterpret_cast<uint4*>(kblk + (((st * 2) ^ (row & 7)) << 4)) = v0;
-            *reinterpret_cast<uint4*>(kblk + (((st * 2 + 1) ^ (row & 7)) << 4)) = v1;
-          }
+          gate_step<LAST>(t1r, g1r, bT0 + (st + 1) * 16, wse0 + (st + 1) * 128, kblk, st + 1, row, o8);
         }
         tc_fence_before();
-        if (LAST) mbar_arrive(drained_bar(q));
-      }
-      if (!LAST) {
-        fence_proxy_async_smem();   // acts (generic-proxy writes) -> visible to the MMA (async proxy)
-        mbar_arrive(acts_bar);
+        if (LAST) {
+          mbar_arrive(drained_bar(q));
+        } else {
+          fence_proxy_async_smem();   // acts (generic-proxy writes) -> visible to the MMA (async proxy)
+          mbar_arrive(q == 0 ? actsa_bar : acts_bar);
+        }
+        if (tmr) t_e1 += clock64() - t1;
       }
       // fold accumulator: the two column halves of a row are combined in a fixed order (bit-reproducible)
       if (hf == 1) {
@@ -520,53 +677,65 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
         o[0] = a0; o[1] = a1;
       }
 
-      // ---- residual epilogue: h += GEMM2 + b2 ----------------------------------------------------
+      // ---- residual epilogue: h = GEMM2 + hi + lo (already in the accumulator) + b2 -> (hi, lo) ----
+      // Staged through the (now free) acts tile in the TMA SWIZZLE_128B layout and written with TMA
+      // stores (rows beyond L are clipped by the tensor map). Two passes over the accumulator: hi, then lo.
       if (!LAST) {
+        long long t0 = 0;
+        if (tmr) t0 = clock64();
         mbar_wait(dfull_bar(2), ph);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + lane_addr + 256u * par;
+        long long t1 = 0;
+        if (tmr) { t1 = clock64(); t_w2 += t1 - t0; }
+        const uint32_t taddr = tmem_base + lane_addr + 256u * par + hf * 128;
+        uint8_t* stg = acts + (hf * 2) * WL_A_BYTES + row * 128;      // this half's two 64-column blocks
+        const uint32_t stg_addr = smem_base + WL_OFF_ACTS + (hf * 2) * WL_A_BYTES;
+        const bool issuer = (we == hf * 4) && lane == 0;
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {
-          const int colbase = hf * 128 + pass * 64;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint32_t r[16];
-            tmem_ld16(taddr + colbase + i * 16, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-              const int chunk = (i * 4 + c4) ^ (lane & 15);
-              *reinterpret_cast<uint4*>(scratch + lane * 64 + chunk * 4) = make_uint4(r[4 * c4], r[4 * c4 + 1], r[4 * c4 + 2], r[4 * c4 + 3]);
-            }
-          }
           if (pass == 1) {
-            tc_fence_before();
-            mbar_arrive(epi2_bar);   // all TMEM reads of this tile are done
+            if (issuer) bulk_wait_read0();   // the hi store has finished reading the staging tile
+            if (hf == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
+            else asm volatile("bar.sync 4, 128;" ::: "memory");
           }
-          __syncwarp();
-          const int ck = lane & 15, rsub = lane >> 4;
-          const int col = colbase + ck * 4;
-          const float4 bb = *reinterpret_cast<const float4*>(s_b2 + col);
-#pragma unroll 4
-          for (int itr = 0; itr < 16; ++itr) {
-            const int rr = itr * 2 + rsub;
-            const int l = l0 + quarter * 32 + rr;
-            if (l < p.L) {
-              const float4 dv = *reinterpret_cast<const float4*>(scratch + rr * 64 + ((ck ^ (rr & 15)) << 2));
-              const size_t mm = static_cast<size_t>(b) * p.L + l;
-              float4* hp = reinterpret_cast<float4*>(p.h32 + mm * WL_C + col);
-              float4 h = *hp;
-              h.x += dv.x + bb.x; h.y += dv.y + bb.y; h.z += dv.z + bb.z; h.w += dv.w + bb.w;
-              *hp = h;
-              *reinterpret_cast<uint2*>(p.h16_out + mm * WL_C + col) = make_uint2(pack_bf16x2(h.x, h.y), pack_bf16x2(h.z, h.w));
+          uint32_t r0[16], r1[16];
+          tmem_ld16(taddr, r0);
+#pragma unroll 1
+          for (int gp = 0; gp < 4; ++gp) {          // two groups of 16 columns per iteration
+            tmem_ld_wait();
+            tmem_ld16(taddr + (2 * gp + 1) * 16, r1);
+            resid_step(r0, s_b2 + hf * 128 + (2 * gp) * 16, stg, 2 * gp, row, pass);
+            tmem_ld_wait();
+            if (gp < 3) tmem_ld16(taddr + (2 * gp + 2) * 16, r0);
+            else if (pass == 1) {
+              tc_fence_before();
+              mbar_arrive(epi2_bar);   // all TMEM reads of this tile are done
             }
+            resid_step(r1, s_b2 + hf * 128 + (2 * gp + 1) * 16, stg, 2 * gp + 1, row, pass);
           }
-          __syncwarp();
+          fence_proxy_async_smem();
+          if (hf == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
+          else asm volatile("bar.sync 4, 128;" ::: "memory");
+          if (issuer) {
+            const CUtensorMap* om = pass == 0 ? &map_ho : &map_lo;
+            tma_store_3d(om, stg_addr, (hf * 2) * WL_BK, l0, b);
+            tma_store_3d(om, stg_addr + WL_A_BYTES, (hf * 2 + 1) * WL_BK, l0, b);
+            bulk_commit();
+          }
         }
+        if (issuer) bulk_wait_read0();   // staging tile may be overwritten by the next gate epilogue
+        if (tmr) t_e2 += clock64() - t1;
       }
-      // (a) the transposition scratch aliases the acts tile, (b) s_o8 is reused by the next tile:
-      // no epilogue warp may run ahead into the next tile before all are done with this one
+      // s_o8 and the staging tile are reused by the next tile: no epilogue warp may run ahead
       asm volatile("bar.sync 1, %0;" ::"n"(WL_EPI_THREADS) : "memory");
+    }
+    if (!LAST && lane == 0 && (we == 0 || we == 4)) bulk_wait0();   // all TMA stores of this CTA have landed
+    if (tmr) {
+      atomicAdd(p.timing + 3, static_cast<unsigned long long>(t_w0));
+      atomicAdd(p.timing + 4, static_cast<unsigned long long>(t_w1));
+      atomicAdd(p.timing + 5, static_cast<unsigned long long>(t_w2));
+      atomicAdd(p.timing + 6, static_cast<unsigned long long>(t_e1));
+      atomicAdd(p.timing + 7, static_cast<unsigned long long>(t_e2));
     }
   }
   tc_fence_before();
@@ -654,27 +823,28 @@ inline void make_map_3d(CUtensorMap* m, const void* ptr, uint64_t batch, uint64_
 }
 
 struct TcPlan {
-  CUtensorMap m_aup, m_wup, m_w1, m_w2, m_h16[2], m_spect;
+  CUtensorMap m_aup, m_wup, m_w1, m_w2, m_h16[2], m_lo, m_spect;
   int sm_count = 0, B = 0, T = 0, L = 0, C = 0, S = 0, Kup = 0, n_mel = 0, NupN = 0;
   int tiles_per_b = 0, n_tiles = 0;
-  __nv_bfloat16 *aup16 = nullptr, *spect16 = nullptr, *h16[2] = {nullptr, nullptr};
+  __nv_bfloat16 *aup16 = nullptr, *spect16 = nullptr, *h16[2] = {nullptr, nullptr}, *hlo = nullptr;
 };
 
 inline void tc_prepare(TcPlan& pl, int sm_count, int B, int T, int L, int C, int S, int Kup, int n_mel,
                        int n_layers_total, const __nv_bfloat16* Wup16, int NupN, const __nv_bfloat16* W1,
                        const __nv_bfloat16* W2, __nv_bfloat16* aup16, __nv_bfloat16* spect16, __nv_bfloat16* h16a,
-                       __nv_bfloat16* h16b) {
+                       __nv_bfloat16* h16b, __nv_bfloat16* hlo) {
   if (C != WL_C || S != WL_S) fail(WG_ERR_UNSUPPORTED, "tensor path is built for C=256, S=640 (got C=%d, S=%d)", C, S);
   pl.sm_count = sm_count; pl.B = B; pl.T = T; pl.L = L; pl.C = C; pl.S = S; pl.Kup = Kup; pl.n_mel = n_mel; pl.NupN = NupN;
   pl.tiles_per_b = (L + WL_BM - 1) / WL_BM;
   pl.n_tiles = pl.tiles_per_b * B;
-  pl.aup16 = aup16; pl.spect16 = spect16; pl.h16[0] = h16a; pl.h16[1] = h16b;
+  pl.aup16 = aup16; pl.spect16 = spect16; pl.h16[0] = h16a; pl.h16[1] = h16b; pl.hlo = hlo;
   make_map_2d(&pl.m_aup, aup16, (uint64_t)B * T, Kup, TG_BM);
   make_map_2d(&pl.m_wup, Wup16, NupN, Kup, TG_BN);
   make_map_2d(&pl.m_w1, W1, (uint64_t)n_layers_total * 2 * C, 3 * C + S, 256);
   make_map_2d(&pl.m_w2, W2, (uint64_t)n_layers_total * C, C, 256);
   make_map_3d(&pl.m_h16[0], h16a, B, L, C, WL_BM);
   make_map_3d(&pl.m_h16[1], h16b, B, L, C, WL_BM);
+  make_map_3d(&pl.m_lo, hlo, B, L, C, WL_BM);
   make_map_3d(&pl.m_spect, spect16, B, L, S, WL_BM);
 }
 
@@ -689,19 +859,27 @@ inline int tc_upsample(const TcPlan& pl, const float* mel, const float* bup, cud
   return 2;
 }
 
-inline int tc_wn_layer(const TcPlan& pl, int layer, int dilation, bool last, bool /*first*/, int hcur, float* h32,
-                       float* acc8, const float* b1, const float* b2, const float* Wse, const float* /*bse8*/,
-                       cudaStream_t st) {
+inline int tc_wn_layer(const TcPlan& pl, int layer, int dilation, bool last, int hcur, float* acc8, const float* b1,
+                       const float* b2, const float* wse_host, unsigned long long* timing, int flags, cudaStream_t st) {
   WnLayerParams p{};
   p.L = pl.L; p.tiles_per_b = pl.tiles_per_b; p.n_tiles = pl.n_tiles; p.layer = layer; p.dilation = dilation;
-  p.b1 = b1; p.b2 = b2; p.Wse = Wse; p.h32 = h32; p.h16_out = pl.h16[hcur ^ 1]; p.acc8 = acc8;
+  p.b1 = b1; p.b2 = b2; p.hi_out = pl.h16[hcur ^ 1]; p.lo = pl.hlo; p.acc8 = acc8; p.timing = timing; p.flags = flags;
+  WnLayerConst cw;
+  std::memcpy(cw.wse, wse_host, sizeof cw.wse);
   const int grid = pl.n_tiles < pl.sm_count ? pl.n_tiles : pl.sm_count;
   if (last)
-    tc_wn_layer_kernel<true><<<grid, WL_THREADS, WL_SMEM, st>>>(pl.m_h16[hcur], pl.m_spect, pl.m_w1, pl.m_w2, p);
+    tc_wn_layer_kernel<true><<<grid, WL_THREADS, WL_SMEM, st>>>(pl.m_h16[hcur], pl.m_h16[hcur ^ 1], pl.m_lo, pl.m_spect, pl.m_w1, pl.m_w2, p, cw);
   else
-    tc_wn_layer_kernel<false><<<grid, WL_THREADS, WL_SMEM, st>>>(pl.m_h16[hcur], pl.m_spect, pl.m_w1, pl.m_w2, p);
+    tc_wn_layer_kernel<false><<<grid, WL_THREADS, WL_SMEM, st>>>(pl.m_h16[hcur], pl.m_h16[hcur ^ 1], pl.m_lo, pl.m_spect, pl.m_w1, pl.m_w2, p, cw);
   WG_CK(cudaGetLastError());
   return 1;
+}
+
+// debug: h = hi + lo as float32
+__global__ void hilo_to_f32_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                   float* __restrict__ out, size_t n) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx < n) out[idx] = __bfloat162float(hi[idx]) + __bfloat162float(lo[idx]);
 }
 
 inline void tc_bf16_to_f32(const __nv_bfloat16* in, float* out, size_t n, cudaStream_t st) {

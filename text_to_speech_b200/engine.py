@@ -87,6 +87,11 @@ class WaveGlowEngine:
         self._check(self._lib.wg_profile_read(self._h, ctypes.byref(ms), ctypes.byref(n)), "wg_profile_read")
         return ms.value, n.value
 
+    def read_layer_timing(self):
+        buf = (ctypes.c_uint64 * 16)()
+        self._check(self._lib.wg_debug_read_timing(self._h, buf), "wg_debug_read_timing")
+        return list(buf)
+
     # -- device-resident call (inputs already in HBM) ------------------------------------------------
     def infer_device(self, mel, z=None, sigma=1.0, deterministic=False, out=None):
         """mel [B,T,n_mel] / z [B,32T,8] / out [B,256T]: float32 CUDA tensors on this engine's device.

@@ -90,6 +90,25 @@ def stage_bf16():
     print("launches", eng.last_launch_count)
 
 
+def stage_accuracy():
+    """bf16 engine vs the CPU oracle on a larger sample (slow: CPU oracle)."""
+    hp = WaveGlowHParams()
+    w = generate_weights(hp, 1234)
+    B, T = 4, 860
+    mel, z = synthetic_inputs(2024, B, T, hp)
+    t = time.time()
+    ref = OracleWaveGlow(hp, w)(mel, z, 0.6).numpy()
+    print(f"oracle {B}x{T}: {time.time()-t:.1f}s on {torch.get_num_threads()} threads")
+    for mode in ("bf16", "fp32"):
+        eng = WaveGlowEngine(hp, w, mode=mode)
+        out = eng.infer_device(torch.from_numpy(mel).cuda(), torch.from_numpy(z).cuda(), sigma=0.6)
+        torch.cuda.synchronize()
+        stats(f"waveform {mode} {B}x{T}", out.cpu().numpy(), ref)
+        e = np.abs(out.cpu().numpy() - ref)
+        print("   |err| quantiles 99.9/99.99/99.999%:", np.quantile(e, [0.999, 0.9999, 0.99999]))
+        eng.close()
+
+
 def stage_time():
     hp = WaveGlowHParams()
     w = generate_weights(hp, 1234)
@@ -111,6 +130,13 @@ def stage_time():
         ms = e0.elapsed_time(e1) / n
         flop = 20308852.0 * B * T * 256
         print(f"time {mode} B={B} T={T}: {ms:.2f} ms/infer, {B*T*256/ms*1e3/1e6:.2f} Msamples/s, {flop/ms/1e9:.1f} TFLOP/s algorithmic")
+        if mode == "bf16" and os.environ.get("WG_LAYER_TIMING") == "1":
+            t = eng.read_layer_timing()      # summed over CTAs and all launches of the timed + warm-up infers
+            names = ["mma total", "mma wait TMA", "mma wait epilogue", "epi wait chunk a", "epi wait chunk b",
+                     "epi wait gemm2", "epi gate work", "epi residual work", "tma wait free stage"]
+            tot = max(t[0], 1)
+            for nm, v in zip(names, t):
+                print(f"    {nm:22s} {v/1e6:12.1f} Mcycles  {100.0*v/tot:6.1f}% of mma total")
         eng.close()
 
 
