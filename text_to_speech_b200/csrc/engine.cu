@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "simt_kernels.cuh"
 #include "tc_kernels.cuh"
+#include "tc_pair_kernel.cuh"
 
 namespace {
 
@@ -83,6 +84,7 @@ struct wg_engine {
   size_t cap_mel = 0, cap_z = 0, cap_out = 0, cap_ws = 0;
   // per-kernel profiling (wg_profile_enable / wg_profile_read)
   unsigned long long* timing = nullptr;   // WG_LAYER_TIMING=1: in-kernel cycle counters (debug)
+  bool use_pair = true;                   // CTA-pair (cta_group::2) WN-layer kernel; WG_PAIR=0 selects the 1-CTA kernel
   int dbg_flags = 0;                      // WG_DEBUG_FLAGS (see WnLayerParams::flags)
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;   // pairs: [2i] start, [2i+1] stop
@@ -236,6 +238,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
   const float* zz = deterministic ? nullptr : z;
 
   TcPlan plan;
+  TcPairMaps pmaps;
   // ---- (1) upsample + trim + regroup: spect[B*L, S]  (waveglow_arch.py:245-253) ---------------
   if (!bf16) {
     GemmArgs g{};
@@ -248,6 +251,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
   } else {
     tc_prepare(plan, e->sm_count, B, T, L, C, S, e->Kup, c.n_mel_channels, c.n_flows * c.n_layers,
                e->Wup16, R * S, e->W1, e->W2, aup16, spect16, h16[0], h16[1], hlo);
+    if (e->use_pair) tc_pair_prepare(pmaps, c.n_flows * c.n_layers, C, S, e->W1, e->W2);
     e->launches += tc_upsample(plan, mel, e->bup, st);
   }
 
@@ -315,8 +319,12 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
         launch_gemm<EPI_RES_SKIP>(e, r, st);
       } else {
         prof_mark();
-        e->launches += tc_wn_layer(plan, k * c.n_layers + i, d, last, hcur, acc8, lw.b1, lw.b2, lw.wse_h.data(),
-                                   e->timing, e->dbg_flags, st);
+        if (e->use_pair)
+          e->launches += tc_wn_layer_pair(plan, pmaps, k * c.n_layers + i, d, last, hcur, acc8, lw.b1, lw.b2,
+                                          lw.wse_h.data(), e->timing, e->dbg_flags, st);
+        else
+          e->launches += tc_wn_layer(plan, k * c.n_layers + i, d, last, hcur, acc8, lw.b1, lw.b2, lw.wse_h.data(),
+                                     e->timing, e->dbg_flags, st);
         prof_mark();
         if (!last) hcur ^= 1;
       }
@@ -571,6 +579,8 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
     e->W1 = upload(e, w1all);
     e->W2 = upload(e, w2all);
     tc_init();
+    tc_pair_init();
+    if (const char* pr = std::getenv("WG_PAIR")) e->use_pair = pr[0] != '0';
     if (const char* f = std::getenv("WG_DEBUG_FLAGS")) e->dbg_flags = std::atoi(f);
     if (const char* t = std::getenv("WG_LAYER_TIMING")) {
       if (t[0] == '1') {

@@ -137,6 +137,11 @@ def stage_time():
             tot = max(t[0], 1)
             for nm, v in zip(names, t):
                 print(f"    {nm:22s} {v/1e6:12.1f} Mcycles  {100.0*v/tot:6.1f}% of mma total")
+            if t[10]:
+                print(f"    commit issue -> producer awake: {t[9]/t[10]:8.0f} cycles avg over {t[10]} stages")
+            if t[12]:
+                print(f"    TMA issue -> MMA thread sees data: {t[11]/t[12]:8.0f} cycles avg (all), "
+                      f"{t[13]/max(t[14],1):8.0f} cycles avg over the {t[14]} stages the MMA waited for")
         eng.close()
 
 

@@ -1,0 +1,15 @@
+"""One warm-up + one K2 infer (BF16): the command ncu wraps for the per-kernel captures."""
+import os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from text_to_speech_b200.engine import WaveGlowEngine
+from text_to_speech_b200.weights import WaveGlowHParams, generate_weights, synthetic_inputs
+hp = WaveGlowHParams(); w = generate_weights(hp, 1234)
+B, T = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (16, 860)
+eng = WaveGlowEngine(hp, w, mode="bf16")
+mel, z = synthetic_inputs(1, B, T, hp)
+md, zd = torch.from_numpy(mel).cuda(), torch.from_numpy(z).cuda()
+for _ in range(2):
+    out = eng.infer_device(md, zd, 0.6)
+torch.cuda.synchronize()
+print("ok", float(out.abs().max()))

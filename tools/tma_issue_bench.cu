@@ -1,0 +1,66 @@
+// Is TMA throughput per SM limited by the ISSUING THREAD (one box every ~N cycles) or by the TMA unit?
+// W producer warps per CTA, each streams 16 KB boxes into its own 2 slots. nvcc -arch=sm_100a
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e_)); exit(1); } } while (0)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t c) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(c) : "memory"); }
+__device__ __forceinline__ void mbar_expect(uint32_t bar, uint32_t b) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(b) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t ph) {
+  uint32_t d = 0;
+  while (!d) asm volatile("{.reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0,1,0,p;}" : "=r"(d) : "r"(bar), "r"(ph) : "memory");
+}
+__device__ __forceinline__ void tma2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"((uint64_t)m), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+constexpr int BOX = 128 * 128, SLOTS = 4;   // per warp: 4 slots of 16 KB
+template <int W>
+__global__ void __launch_bounds__(W * 32, 1) k(const __grid_constant__ CUtensorMap map, int iters, int boxes_per_phase) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = (uint64_t*)(smem + W * SLOTS * BOX);
+  const uint32_t base = smem_u32(smem), bb = smem_u32(bars);
+  const int w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { for (int s = 0; s < W * SLOTS; ++s) mbar_init(bb + 8 * s, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) {
+    const int row0 = (blockIdx.x * W + w) * 1024;
+    int s = 0; uint32_t ph = 0;
+    for (int i = 0; i < iters; ++i) {
+      const uint32_t bar = bb + 8 * (w * SLOTS + s);
+      if (i >= SLOTS) mbar_wait(bar, ph ^ 1);
+      mbar_expect(bar, BOX);
+      tma2d(base + (w * SLOTS + s) * BOX, &map, bar, 0, row0 + (i & 7) * 128);
+      if (++s == SLOTS) { s = 0; ph ^= 1; }
+    }
+    for (int j = 0; j < SLOTS; ++j) { mbar_wait(bb + 8 * (w * SLOTS + s), ph ^ 1); if (++s == SLOTS) { s = 0; ph ^= 1; } }
+  }
+}
+typedef CUresult (*PFN_enc)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+template <int W> void run(const CUtensorMap& map, int sms) {
+  const int smem = W * SLOTS * BOX + 256, iters = 4000;
+  CK(cudaFuncSetAttribute(k<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  for (int rep = 0; rep < 2; ++rep) {
+    CK(cudaEventRecord(e0)); k<W><<<sms, W * 32, smem>>>(map, iters, 1); CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep) printf("%d producer warps x %d slots: %.3f ms, %.0f ns per box per warp, %.0f ns per box per SM, %.2f TB/s\n", W, SLOTS, ms,
+                    ms * 1e6 / iters, ms * 1e6 / iters / W, (double)iters * W * BOX * sms / ms / 1e9);
+  }
+}
+int main() {
+  void* f = nullptr; cudaDriverEntryPointQueryResult q;
+  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q));
+  PFN_enc enc = (PFN_enc)f;
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
+  const int sms = prop.multiProcessorCount;
+  const size_t rows = (size_t)1024 * 4 * sms;   // 77 MB
+  void* d; CK(cudaMalloc(&d, rows * 128)); CK(cudaMemset(d, 0, rows * 128));
+  CUtensorMap map; cuuint64_t gdim[2] = {64, rows}, gstr[1] = {128}; cuuint32_t box[2] = {64, 128}, es[2] = {1, 1};
+  if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return 1;
+  run<1>(map, sms); run<2>(map, sms); run<3>(map, sms);
+  return 0;
+}
