@@ -85,3 +85,20 @@ def padding_waste(batches: Sequence[Batch], lengths: Sequence[int]) -> float:
     real = sum(int(lengths[i]) for b in batches for i in b.indices)
     padded = sum(b.T * len(b.indices) for b in batches)
     return 0.0 if padded == 0 else 1.0 - real / padded
+
+
+def run_rank(vocoder, mels, plan_for_rank, pad_mel_value=-11.0, hop=256):
+    """Runs one rank's batches through `vocoder(mel[B,T,80]) -> [B, hop*T]` and returns {utterance id:
+    waveform trimmed to its own length} (models/tts/waveglow.py:82 trims the same way). `mels` is the
+    global list of [T_i, 80] arrays; only this rank's utterances are touched."""
+    import numpy as np
+    out = {}
+    for batch in plan_for_rank:
+        n_mel = mels[batch.indices[0]].shape[1]
+        x = np.full((len(batch.indices), batch.T, n_mel), pad_mel_value, dtype=np.float32)
+        for j, i in enumerate(batch.indices):
+            x[j, :mels[i].shape[0]] = mels[i]
+        y = np.asarray(vocoder(x))
+        for j, i in enumerate(batch.indices):
+            out[i] = y[j, :mels[i].shape[0] * hop].copy()
+    return out
