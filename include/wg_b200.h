@@ -117,7 +117,7 @@ int wg_profile_read(wg_handle h, double* layer_ms_sum, int32_t* layer_launches);
  * [0] MMA-warp total, [1] MMA waiting for TMA data, [2] MMA waiting for the epilogue, [3..5] epilogue
  * waiting for chunk a / chunk b / GEMM2 accumulators, [6] gate-epilogue work, [7] residual-epilogue work,
  * [8] TMA producer waiting for free stages. */
-int wg_debug_read_timing(wg_handle h, uint64_t* out16);
+int wg_debug_read_timing(wg_handle h, uint64_t* out128);   /* [16..80): MMA wait-for-data cycles by stage position in the tile */
 
 /* Runs wg_infer but stops after WN layer `stop_layer` of flow `stop_flow` (flows run 11..0) and
  * copies the residual stream h [B*L, C] (float32) and the pre-coupling accumulator [B*L, 8] to

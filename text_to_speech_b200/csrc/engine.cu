@@ -88,6 +88,7 @@ struct wg_engine {
   int dbg_flags = 0;                      // WG_DEBUG_FLAGS (see WnLayerParams::flags)
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;   // pairs: [2i] start, [2i+1] stop
+  std::vector<char> ev_last;          // per pair: 1 = last layer of a flow
   size_t ev_used = 0;
 };
 
@@ -319,6 +320,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
         launch_gemm<EPI_RES_SKIP>(e, r, st);
       } else {
         prof_mark();
+        if (e->profiling) e->ev_last.push_back(last ? 1 : 0);
         if (e->use_pair)
           e->launches += tc_wn_layer_pair(plan, pmaps, k * c.n_layers + i, d, last, hcur, acc8, lw.b1, lw.b2,
                                           lw.wse_h.data(), e->timing, e->dbg_flags, st);
@@ -584,9 +586,9 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
     if (const char* f = std::getenv("WG_DEBUG_FLAGS")) e->dbg_flags = std::atoi(f);
     if (const char* t = std::getenv("WG_LAYER_TIMING")) {
       if (t[0] == '1') {
-        CK(cudaMalloc(&e->timing, 16 * sizeof(unsigned long long)));
+        CK(cudaMalloc(&e->timing, 128 * sizeof(unsigned long long)));
         e->allocs.push_back(e->timing);
-        CK(cudaMemset(e->timing, 0, 16 * sizeof(unsigned long long)));
+        CK(cudaMemset(e->timing, 0, 128 * sizeof(unsigned long long)));
       }
     }
   }
@@ -729,6 +731,7 @@ int wg_profile_enable(wg_handle h, int32_t enable) {
   if (!h) return WG_ERR_INVALID;
   h->profiling = enable != 0;
   h->ev_used = 0;
+  h->ev_last.clear();
   return WG_OK;
 }
 
@@ -744,17 +747,28 @@ int wg_profile_read(wg_handle h, double* layer_ms_sum, int32_t* layer_launches) 
     }
     *layer_ms_sum = sum;
     *layer_launches = (int32_t)(h->ev_used / 2);
+    if (std::getenv("WG_PROFILE_SPLIT")) {   // development aid: last-layer launches vs the others
+      double s_last = 0, s_other = 0; int n_last = 0, n_other = 0;
+      for (size_t i = 0; i + 1 < h->ev_used && i / 2 < h->ev_last.size(); i += 2) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev_pool[i], h->ev_pool[i + 1]);
+        if (h->ev_last[i / 2]) { s_last += ms; ++n_last; } else { s_other += ms; ++n_other; }
+      }
+      fprintf(stderr, "wg profile split: last-layer launches %d avg %.1f us | other layers %d avg %.1f us\n", n_last,
+              n_last ? 1e3 * s_last / n_last : 0.0, n_other, n_other ? 1e3 * s_other / n_other : 0.0);
+    }
     h->ev_used = 0;
+    h->ev_last.clear();
   });
 }
 
-int wg_debug_read_timing(wg_handle h, uint64_t* out16) {
-  if (!h || !out16) return WG_ERR_INVALID;
+int wg_debug_read_timing(wg_handle h, uint64_t* out128) {
+  if (!h || !out128) return WG_ERR_INVALID;
   return guarded(h, [&] {
     if (!h->timing) fail(WG_ERR_INVALID, "layer timing is off (set WG_LAYER_TIMING=1 before wg_create, BF16 mode)");
     CK(cudaDeviceSynchronize());
-    CK(cudaMemcpy(out16, h->timing, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    CK(cudaMemset(h->timing, 0, 16 * sizeof(unsigned long long)));
+    CK(cudaMemcpy(out128, h->timing, 128 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CK(cudaMemset(h->timing, 0, 128 * sizeof(unsigned long long)));
   });
 }
 

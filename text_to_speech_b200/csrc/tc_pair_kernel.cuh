@@ -89,6 +89,15 @@ __device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t adesc, uint
       : "memory");
 }
 
+// One lane of a fully converged warp. Keeping the whole warp in the producer / MMA loops (and electing only
+// around the asm) lets ptxas keep descriptors and coordinates in UNIFORM registers; a loop entered by
+// `if (lane == 0)` made every UTCHMMA / UTMALDG pay an ELECT + R2UR.BROADCAST waterfall.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of CTA 1 -> same offset in CTA 0
 
 // ---- geometry -------------------------------------------------------------------------------------
@@ -107,7 +116,7 @@ struct WpGeom {
   static constexpr int OFF_O8 = OFF_B2 + WL_C * 4;
   static constexpr int OFF_BARS = OFF_O8 + WL_BM * 8 * 4;
   static constexpr int NBARS = 2 * STAGES + 3 + 2 + 3;
-  static constexpr int SMEM = OFF_BARS + NBARS * 8 + 16 + 2 * STAGES * 8;   // + debug timestamps
+  static constexpr int SMEM = OFF_BARS + NBARS * 8 + 16 + 2 * STAGES * 8 + 64 * 8;   // + debug timestamps + wait histogram
   static_assert(SMEM <= 232448, "shared memory budget");
 };
 
@@ -129,6 +138,7 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + WP_NBARS);
   volatile long long* ts_issue = reinterpret_cast<volatile long long*>(smem + WP_OFF_BARS + WP_NBARS * 8 + 16);
   volatile long long* ts_commit = ts_issue + WP_STAGES;
+  volatile long long* wait_pos = ts_commit + WP_STAGES;     // [64] MMA wait-for-data cycles by stage position in the tile
   const uint32_t bar_base = smem_base + WP_OFF_BARS;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };                            // leader only
   auto empty_bar = [&](int s) { return bar_base + 8u * (WP_STAGES + s); };             // both CTAs
@@ -139,6 +149,8 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
   const uint32_t epi2_bar = bar_base + 8u * (2 * WP_STAGES + 7);                       // leader only
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nst_req = (p.flags >> 8) & 15;                                   // probe: use fewer ring slots
+  const uint32_t nst = (nst_req > 0 && nst_req < WP_STAGES) ? nst_req : WP_STAGES;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   if ((smem_base & 1023u) != 0u) __trap();
@@ -202,22 +214,23 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
 
   if (warp == 0) {
     // ===================================== TMA producer (both CTAs) ============================
-    if (lane == 0) {
+    {
       uint32_t it = 0;
       long long t_wait = 0, t_c2p = 0, n_c2p = 0;
       auto acquire = [&](uint32_t pair_bytes) -> uint32_t {
-        const int s = it % WP_STAGES;
-        const uint32_t ph = (it / WP_STAGES) & 1;
+        const int s = it % nst;
+        const uint32_t ph = (it / nst) & 1;
         long long t0 = 0;
         if (timing) t0 = clock64();
-        mbar_wait_cluster(empty_bar(s), ph ^ 1);
+        mbar_wait(empty_bar(s), ph ^ 1);
         if (timing) {
           const long long now = clock64();
           t_wait += now - t0;
-          if (leader && it >= WP_STAGES) { t_c2p += now - ts_commit[s]; ++n_c2p; }
-          if (leader) ts_issue[s] = now;
+          if (leader && it >= nst) { t_c2p += now - ts_commit[s]; ++n_c2p; }
+          if (leader && lane == 0) ts_issue[s] = now;
         }
-        if (leader) mbar_expect_tx(full_bar(s), pair_bytes);   // bytes of BOTH CTAs land on the leader's barrier
+        if (leader && elect_one()) mbar_expect_tx(full_bar(s), pair_bytes);   // bytes of BOTH CTAs land on the leader's barrier
+        __syncwarp();
         return static_cast<uint32_t>(s);
       };
       for (int i = 0; i < n_iter && !(p.flags & 16); ++i) {
@@ -237,15 +250,18 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
             const uint32_t s = acquire(2 * ((skip_a ? 0 : WP_A_BYTES) + (skip_b ? 0 : WP_B_BYTES)));
             const uint32_t fb = full_bar(s) & kPeerBitMask;
             const uint32_t a_dst = smem_base + s * WP_STAGE_BYTES;
-            if (kb < WL_KB_CONV) {
-              const int tap = kb >> 2, cblk = kb & 3;
-              if (!skip_a) tma2_load_3d(a_dst, &map_h, fb, cblk * WL_BK, l0 + (tap - 1) * p.dilation, b);
-              if (pf_on && q == 1 && tap == 1) tma_prefetch_3d(&map_h, cblk * WL_BK, nl0, nb);   // centre rows cover most of the halo
-            } else {
-              if (!skip_a) tma2_load_3d(a_dst, &map_spect, fb, (kb - WL_KB_CONV) * WL_BK, l0, b);
-              if (pf_on && q == 1) tma_prefetch_3d(&map_spect, (kb - WL_KB_CONV) * WL_BK, nl0, nb);
+            if (elect_one()) {
+              if (kb < WL_KB_CONV) {
+                const int tap = kb >> 2, cblk = kb & 3;
+                if (!skip_a) tma2_load_3d(a_dst, &map_h, fb, cblk * WL_BK, l0 + (tap - 1) * p.dilation, b);
+                if (pf_on && q == 1 && tap == 1) tma_prefetch_3d(&map_h, cblk * WL_BK, nl0, nb);   // centre rows cover most of the halo
+              } else {
+                if (!skip_a) tma2_load_3d(a_dst, &map_spect, fb, (kb - WL_KB_CONV) * WL_BK, l0, b);
+                if (pf_on && q == 1) tma_prefetch_3d(&map_spect, (kb - WL_KB_CONV) * WL_BK, nl0, nb);
+              }
+              if (!skip_b) tma2_load_2d(a_dst + WP_A_BYTES, &map_w1h, fb, kb * WL_BK, p.layer * 2 * WL_C + q * 256 + rank * 128);
             }
-            if (!skip_b) tma2_load_2d(a_dst + WP_A_BYTES, &map_w1h, fb, kb * WL_BK, p.layer * 2 * WL_C + q * 256 + rank * 128);
+            __syncwarp();
           }
         }
         if (!LAST) {
@@ -254,19 +270,22 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
             const uint32_t s = acquire(2 * WP_STAGE_BYTES);
             const uint32_t fb = full_bar(s) & kPeerBitMask;
             const uint32_t dst = smem_base + s * WP_STAGE_BYTES;
-            if (step == 2 || step == 3) {
-              const int kb = (step - 2) * 2;
-              tma2_load_3d(dst, &map_lo, fb, kb * WL_BK, l0, b);
-              tma2_load_3d(dst + WP_A_BYTES, &map_lo, fb, (kb + 1) * WL_BK, l0, b);
-            } else {
-              const int kb = step < 2 ? step : step - 2;
-              tma2_load_3d(dst, &map_h, fb, kb * WL_BK, l0, b);
-              tma2_load_2d(dst + WP_A_BYTES, &map_w2h, fb, kb * WL_BK, p.layer * WL_C + rank * 128);
+            if (elect_one()) {
+              if (step == 2 || step == 3) {
+                const int kb = (step - 2) * 2;
+                tma2_load_3d(dst, &map_lo, fb, kb * WL_BK, l0, b);
+                tma2_load_3d(dst + WP_A_BYTES, &map_lo, fb, (kb + 1) * WL_BK, l0, b);
+              } else {
+                const int kb = step < 2 ? step : step - 2;
+                tma2_load_3d(dst, &map_h, fb, kb * WL_BK, l0, b);
+                tma2_load_2d(dst + WP_A_BYTES, &map_w2h, fb, kb * WL_BK, p.layer * WL_C + rank * 128);
+              }
             }
+            __syncwarp();
           }
         }
       }
-      if (timing && leader) {
+      if (timing && leader && lane == 0) {
         atomicAdd(p.timing + 8, static_cast<unsigned long long>(t_wait));
         atomicAdd(p.timing + 9, static_cast<unsigned long long>(t_c2p));    // sum (producer wake - commit issue)
         atomicAdd(p.timing + 10, static_cast<unsigned long long>(n_c2p));
@@ -274,23 +293,30 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
     }
   } else if (warp == 1) {
     // ====================================== MMA issuer (leader CTA only) =======================
-    if (leader && lane == 0) {
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(256, 256);
       constexpr uint32_t idesc_id = umma_idesc_bf16(256, 64);
       const uint64_t idesc64 = umma_desc_sw128(smem_base + WP_OFF_I64);
       uint32_t it = 0;
       long long t_full = 0, t_epi = 0, t_begin = 0, t_i2f = 0, n_i2f = 0, t_i2f_w = 0, n_i2f_w = 0;
-      if (timing) t_begin = clock64();
+      if (timing) {
+        t_begin = clock64();
+        if (lane == 0) for (int i = 0; i < 64; ++i) wait_pos[i] = 0;
+        __syncwarp();
+      }
+      uint32_t pos = 0;   // stage position inside the current tile
       auto wait_full = [&]() -> uint32_t {
-        const int s = it % WP_STAGES;
-        const uint32_t ph = (it / WP_STAGES) & 1;
+        const int s = it % nst;
+        const uint32_t ph = (it / nst) & 1;
         long long t0 = 0;
         if (timing) t0 = clock64();
-        if (!(p.flags & 16)) mbar_wait_cluster(full_bar(s), ph);   // flag 16: tensor-pipe-only probe (no TMA)
+        if (!(p.flags & 16)) mbar_wait(full_bar(s), ph);   // flag 16: tensor-pipe-only probe (no TMA)
         if (timing) {
           const long long now = clock64();
           t_full += now - t0;
           t_i2f += now - ts_issue[s]; ++n_i2f;                       // TMA issue -> data seen by the MMA thread
+          if (lane == 0) wait_pos[pos & 63] += now - t0;
+          ++pos;
           if (now - t0 > 64) { t_i2f_w += now - ts_issue[s]; ++n_i2f_w; }   // ... only when the MMA really waited
         }
         tc_fence_after();
@@ -299,13 +325,14 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
       auto wait_epi = [&](uint32_t bar, uint32_t ph) {
         long long t0 = 0;
         if (timing) t0 = clock64();
-        mbar_wait_cluster(bar, ph);
+        mbar_wait(bar, ph);
         if (timing) t_epi += clock64() - t0;
         tc_fence_after();
       };
       for (int n = 0; n < n_iter; ++n) {
         const uint32_t par = LAST ? 0u : (static_cast<uint32_t>(n) & 1u);
         const uint32_t prev_ph = static_cast<uint32_t>(n - 1) & 1u;
+        pos = 0;
         for (int q = 0; q < 2; ++q) {
           const uint32_t d_tmem = tmem_base + 256u * (q == 0 ? par : (par ^ 1u));
           if (n > 0) {
@@ -315,13 +342,16 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
           for (int kb = 0; kb < WL_KB1; ++kb, ++it) {
             const uint32_t a_addr = wait_full();
             const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + WP_A_BYTES);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < WL_BK / 16; ++k)
-              umma2_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
-            if (timing) ts_commit[it % WP_STAGES] = clock64();
-            tc2_commit(empty_bar(it % WP_STAGES));
+              for (int k = 0; k < WL_BK / 16; ++k)
+                umma2_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+              if (timing) ts_commit[it % nst] = clock64();
+              tc2_commit(empty_bar(it % nst));
+              if (kb == WL_KB1 - 1) tc2_commit(dfull_bar(q));
+            }
+            __syncwarp();
           }
-          tc2_commit(dfull_bar(q));
         }
         if (!LAST) {
           const uint32_t d_tmem = tmem_base + 256u * par;
@@ -329,34 +359,37 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
           for (int step = 0; step < 6; ++step, ++it) {
             if (step == 4) wait_epi(acts_bar, static_cast<uint32_t>(n) & 1u);
             const uint32_t st_addr = wait_full();
-            if (step == 2 || step == 3) {
-              const int kb = (step - 2) * 2;
+            if (elect_one()) {
+              if (step == 2 || step == 3) {
+                const int kb = (step - 2) * 2;
 #pragma unroll
-              for (int h2 = 0; h2 < 2; ++h2) {
-                const uint64_t adesc = umma_desc_sw128(st_addr + h2 * WP_A_BYTES);
+                for (int h2 = 0; h2 < 2; ++h2) {
+                  const uint64_t adesc = umma_desc_sw128(st_addr + h2 * WP_A_BYTES);
+#pragma unroll
+                  for (int k = 0; k < WL_BK / 16; ++k)
+                    umma2_bf16(d_tmem + 64u * (kb + h2), adesc + 2 * k, idesc64 + 2 * k, idesc_id, 1u);
+                }
+              } else {
+                const int kb = step < 2 ? step : step - 2;
+                const uint64_t adesc = umma_desc_sw128(smem_base + WP_OFF_ACTS + kb * WL_A_BYTES);
+                const uint64_t bdesc = umma_desc_sw128(st_addr + WP_A_BYTES);
 #pragma unroll
                 for (int k = 0; k < WL_BK / 16; ++k)
-                  umma2_bf16(d_tmem + 64u * (kb + h2), adesc + 2 * k, idesc64 + 2 * k, idesc_id, 1u);
+                  umma2_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (step | k) ? 1u : 0u);
+                const uint64_t hdesc = umma_desc_sw128(st_addr);
+#pragma unroll
+                for (int k = 0; k < WL_BK / 16; ++k)
+                  umma2_bf16(d_tmem + 64u * kb, hdesc + 2 * k, idesc64 + 2 * k, idesc_id, 1u);
               }
-            } else {
-              const int kb = step < 2 ? step : step - 2;
-              const uint64_t adesc = umma_desc_sw128(smem_base + WP_OFF_ACTS + kb * WL_A_BYTES);
-              const uint64_t bdesc = umma_desc_sw128(st_addr + WP_A_BYTES);
-#pragma unroll
-              for (int k = 0; k < WL_BK / 16; ++k)
-                umma2_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (step | k) ? 1u : 0u);
-              const uint64_t hdesc = umma_desc_sw128(st_addr);
-#pragma unroll
-              for (int k = 0; k < WL_BK / 16; ++k)
-                umma2_bf16(d_tmem + 64u * kb, hdesc + 2 * k, idesc64 + 2 * k, idesc_id, 1u);
+              if (timing) ts_commit[it % nst] = clock64();
+              tc2_commit(empty_bar(it % nst));
+              if (step == 5) tc2_commit(dfull_bar(2));
             }
-            if (timing) ts_commit[it % WP_STAGES] = clock64();
-            tc2_commit(empty_bar(it % WP_STAGES));
+            __syncwarp();
           }
-          tc2_commit(dfull_bar(2));
         }
       }
-      if (timing) {
+      if (timing && lane == 0) {
         atomicAdd(p.timing + 0, static_cast<unsigned long long>(clock64() - t_begin));
         atomicAdd(p.timing + 1, static_cast<unsigned long long>(t_full));
         atomicAdd(p.timing + 2, static_cast<unsigned long long>(t_epi));
@@ -364,6 +397,7 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
         atomicAdd(p.timing + 12, static_cast<unsigned long long>(n_i2f));
         atomicAdd(p.timing + 13, static_cast<unsigned long long>(t_i2f_w));
         atomicAdd(p.timing + 14, static_cast<unsigned long long>(n_i2f_w));
+        for (int i = 0; i < 64; ++i) atomicAdd(p.timing + 16 + i, static_cast<unsigned long long>(wait_pos[i]));
       }
     }
   } else {
@@ -395,7 +429,7 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
       for (int q = 0; q < 2; ++q) {
         long long t0 = 0;
         if (tmr) t0 = clock64();
-        mbar_wait_cluster(dfull_bar(q), ph);
+        mbar_wait(dfull_bar(q), ph);
         tc_fence_after();
         long long t1 = 0;
         if (tmr) { t1 = clock64(); (q == 0 ? t_w0 : t_w1) += t1 - t0; }
@@ -447,7 +481,7 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
       if (!LAST) {
         long long t0 = 0;
         if (tmr) t0 = clock64();
-        mbar_wait_cluster(dfull_bar(2), ph);
+        mbar_wait(dfull_bar(2), ph);
         tc_fence_after();
         long long t1 = 0;
         if (tmr) { t1 = clock64(); t_w2 += t1 - t0; }

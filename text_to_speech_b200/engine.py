@@ -88,7 +88,7 @@ class WaveGlowEngine:
         return ms.value, n.value
 
     def read_layer_timing(self):
-        buf = (ctypes.c_uint64 * 16)()
+        buf = (ctypes.c_uint64 * 128)()
         self._check(self._lib.wg_debug_read_timing(self._h, buf), "wg_debug_read_timing")
         return list(buf)
 

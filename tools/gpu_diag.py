@@ -120,6 +120,8 @@ def stage_time():
         for _ in range(2):
             eng.infer_device(md, zd, 0.6, out=out)
         torch.cuda.synchronize()
+        if os.environ.get("WG_PROFILE_SPLIT"):
+            eng.profile_enable(True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         n = 3
@@ -128,6 +130,8 @@ def stage_time():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / n
+        if os.environ.get("WG_PROFILE_SPLIT"):
+            eng.profile_read()
         flop = 20308852.0 * B * T * 256
         print(f"time {mode} B={B} T={T}: {ms:.2f} ms/infer, {B*T*256/ms*1e3/1e6:.2f} Msamples/s, {flop/ms/1e9:.1f} TFLOP/s algorithmic")
         if mode == "bf16" and os.environ.get("WG_LAYER_TIMING") == "1":
@@ -137,6 +141,11 @@ def stage_time():
             tot = max(t[0], 1)
             for nm, v in zip(names, t):
                 print(f"    {nm:22s} {v/1e6:12.1f} Mcycles  {100.0*v/tot:6.1f}% of mma total")
+            hist = t[16:16 + 52]
+            if sum(hist):
+                print("    MMA wait-for-data by stage position in the tile (% of all such waiting):")
+                tot_h = sum(hist)
+                print("     ", " ".join(f"{100.0 * v / tot_h:4.1f}" for v in hist))
             if t[10]:
                 print(f"    commit issue -> producer awake: {t[9]/t[10]:8.0f} cycles avg over {t[10]} stages")
             if t[12]:

@@ -17,9 +17,13 @@ __device__ __forceinline__ void tma2d(uint32_t dst, const CUtensorMap* m, uint32
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(dst), "l"((uint64_t)m), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void bulk1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"((uint64_t)src), "r"(bytes), "r"(bar) : "memory");
+}
 constexpr int BOX = 128 * 128, SLOTS = 4;   // per warp: 4 slots of 16 KB
 template <int W>
-__global__ void __launch_bounds__(W * 32, 1) k(const __grid_constant__ CUtensorMap map, int iters, int boxes_per_phase) {
+__global__ void __launch_bounds__(W * 32, 1) k(const __grid_constant__ CUtensorMap map, int iters, int mode, const char* gbase) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = (uint64_t*)(smem + W * SLOTS * BOX);
   const uint32_t base = smem_u32(smem), bb = smem_u32(bars);
@@ -33,21 +37,25 @@ __global__ void __launch_bounds__(W * 32, 1) k(const __grid_constant__ CUtensorM
       const uint32_t bar = bb + 8 * (w * SLOTS + s);
       if (i >= SLOTS) mbar_wait(bar, ph ^ 1);
       mbar_expect(bar, BOX);
-      tma2d(base + (w * SLOTS + s) * BOX, &map, bar, 0, row0 + (i & 7) * 128);
+      if (mode == 0) tma2d(base + (w * SLOTS + s) * BOX, &map, bar, 0, row0 + (i & 7) * 128);
+      else if (mode == 1) bulk1d(base + (w * SLOTS + s) * BOX, gbase + (size_t)(row0 + (i & 7) * 128) * 128, BOX, bar);
+      else {   // one tensor box (8 KB = 64 rows) + one bulk copy (8 KB)
+        tma2d(base + (w * SLOTS + s) * BOX, &map, bar, 0, row0 + (i & 7) * 128);
+      }
       if (++s == SLOTS) { s = 0; ph ^= 1; }
     }
     for (int j = 0; j < SLOTS; ++j) { mbar_wait(bb + 8 * (w * SLOTS + s), ph ^ 1); if (++s == SLOTS) { s = 0; ph ^= 1; } }
   }
 }
 typedef CUresult (*PFN_enc)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-template <int W> void run(const CUtensorMap& map, int sms) {
+template <int W> void run(const CUtensorMap& map, int sms, int mode, const char* gbase) {
   const int smem = W * SLOTS * BOX + 256, iters = 4000;
   CK(cudaFuncSetAttribute(k<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   for (int rep = 0; rep < 2; ++rep) {
-    CK(cudaEventRecord(e0)); k<W><<<sms, W * 32, smem>>>(map, iters, 1); CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0)); k<W><<<sms, W * 32, smem>>>(map, iters, mode, gbase); CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
-    if (rep) printf("%d producer warps x %d slots: %.3f ms, %.0f ns per box per warp, %.0f ns per box per SM, %.2f TB/s\n", W, SLOTS, ms,
+    if (rep) printf("mode %d (%s) %d producer warps x %d slots: %.3f ms, %.0f ns per box per warp, %.0f ns per box per SM, %.2f TB/s\n", mode, mode == 0 ? "tensor box 128 rows x 128 B" : "bulk 1-D copy of 16 KB", W, SLOTS, ms,
                     ms * 1e6 / iters, ms * 1e6 / iters / W, (double)iters * W * BOX * sms / ms / 1e9);
   }
 }
@@ -61,6 +69,6 @@ int main() {
   void* d; CK(cudaMalloc(&d, rows * 128)); CK(cudaMemset(d, 0, rows * 128));
   CUtensorMap map; cuuint64_t gdim[2] = {64, rows}, gstr[1] = {128}; cuuint32_t box[2] = {64, 128}, es[2] = {1, 1};
   if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return 1;
-  run<1>(map, sms); run<2>(map, sms); run<3>(map, sms);
+  for (int mode = 0; mode < 2; ++mode) { run<1>(map, sms, mode, (const char*)d); run<2>(map, sms, mode, (const char*)d); }
   return 0;
 }
