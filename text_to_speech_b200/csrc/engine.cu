@@ -84,7 +84,7 @@ struct wg_engine {
   size_t cap_mel = 0, cap_z = 0, cap_out = 0, cap_ws = 0;
   // per-kernel profiling (wg_profile_enable / wg_profile_read)
   unsigned long long* timing = nullptr;   // WG_LAYER_TIMING=1: in-kernel cycle counters (debug)
-  bool use_pair = true;                   // CTA-pair (cta_group::2) WN-layer kernel; WG_PAIR=0 selects the 1-CTA kernel
+  bool use_pair = false;                  // WG_PAIR=1 selects the CTA-pair (cta_group::2) kernel (measured slower, kept for A/B)
   int dbg_flags = 0;                      // WG_DEBUG_FLAGS (see WnLayerParams::flags)
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;   // pairs: [2i] start, [2i+1] stop
@@ -582,7 +582,7 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
     e->W2 = upload(e, w2all);
     tc_init();
     tc_pair_init();
-    if (const char* pr = std::getenv("WG_PAIR")) e->use_pair = pr[0] != '0';
+    if (const char* pr = std::getenv("WG_PAIR")) e->use_pair = pr[0] == '1';
     if (const char* f = std::getenv("WG_DEBUG_FLAGS")) e->dbg_flags = std::atoi(f);
     if (const char* t = std::getenv("WG_LAYER_TIMING")) {
       if (t[0] == '1') {

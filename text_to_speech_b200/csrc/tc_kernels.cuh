@@ -130,6 +130,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// One lane of a fully converged warp (see tc_pair_kernel.cuh for why the issue loops keep the whole warp).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -307,7 +313,7 @@ constexpr int WL_OFF_B1 = WL_OFF_I64 + 64 * 128;
 constexpr int WL_OFF_B2 = WL_OFF_B1 + 2 * WL_C * 4;
 constexpr int WL_OFF_O8 = WL_OFF_B2 + WL_C * 4;           // [128][8] fp32: partial fold sums of the hf=1 warps
 constexpr int WL_OFF_BARS = WL_OFF_O8 + WL_BM * 8 * 4;
-constexpr int WL_NBARS = 2 * WL_STAGES + 3 + 2 + 3;
+constexpr int WL_NBARS = 2 * WL_STAGES + 3 + 2 + 4;
 constexpr int WL_SMEM = WL_OFF_BARS + WL_NBARS * 8 + 16;
 static_assert(WL_SMEM <= 232448, "shared memory budget");
 
@@ -407,6 +413,7 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
   const uint32_t actsa_bar = bar_base + 8u * (2 * WL_STAGES + 5);                     // acts K-blocks 0,1 in smem, D1a read out
   const uint32_t acts_bar = bar_base + 8u * (2 * WL_STAGES + 6);                      // acts K-blocks 2,3 in smem, D1b read out
   const uint32_t epi2_bar = bar_base + 8u * (2 * WL_STAGES + 7);                      // GEMM2 accumulator read out
+  const uint32_t acts2_bar = bar_base + 8u * (2 * WL_STAGES + 8);                     // acts K-block 2 in smem
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((smem_base & 1023u) != 0u) __trap();   // SWIZZLE_128B tiles need 1024-byte aligned bases
@@ -427,6 +434,7 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
     mbar_init(actsa_bar, WL_EPI_THREADS);
     mbar_init(acts_bar, WL_EPI_THREADS);
     mbar_init(epi2_bar, WL_EPI_THREADS);
+    mbar_init(acts2_bar, WL_EPI_THREADS);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -458,7 +466,7 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
 
   if (warp == 0) {
     // ===================================== TMA producer ======================================
-    if (lane == 0) {
+    {
       uint32_t it = 0;  // running stage counter
       long long t_wait = 0;
       auto acquire = [&](uint32_t bytes) -> uint32_t {
@@ -468,7 +476,8 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
         if (timing) t0 = clock64();
         mbar_wait(empty_bar(s), ph ^ 1);
         if (timing) t_wait += clock64() - t0;
-        mbar_expect_tx(full_bar(s), bytes);
+        if (elect_one()) mbar_expect_tx(full_bar(s), bytes);
+        __syncwarp();
         return static_cast<uint32_t>(s);
       };
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -483,15 +492,18 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
             const bool skip_b = (p.flags & 1) && (kb & 1), skip_a = (p.flags & 2) && (kb & 1);
             const uint32_t s = acquire((skip_a ? 0 : WL_A_BYTES) + (skip_b ? 0 : WL_B_BYTES));
             const uint32_t a_dst = smem_base + s * WL_STAGE_BYTES;
-            if (kb < WL_KB_CONV) {
-              const int tap = kb >> 2, cblk = kb & 3;
-              if (!skip_a) tma_load_3d(a_dst, &map_h, full_bar(s), cblk * WL_BK, l0 + (tap - 1) * p.dilation, b);
-              if (pf) tma_prefetch_3d(&map_h, cblk * WL_BK, nl0 + (tap - 1) * p.dilation, nb);
-            } else {
-              if (!skip_a) tma_load_3d(a_dst, &map_spect, full_bar(s), (kb - WL_KB_CONV) * WL_BK, l0, b);
-              if (pf) tma_prefetch_3d(&map_spect, (kb - WL_KB_CONV) * WL_BK, nl0, nb);
+            if (elect_one()) {
+              if (kb < WL_KB_CONV) {
+                const int tap = kb >> 2, cblk = kb & 3;
+                if (!skip_a) tma_load_3d(a_dst, &map_h, full_bar(s), cblk * WL_BK, l0 + (tap - 1) * p.dilation, b);
+                if (pf) tma_prefetch_3d(&map_h, cblk * WL_BK, nl0 + (tap - 1) * p.dilation, nb);
+              } else {
+                if (!skip_a) tma_load_3d(a_dst, &map_spect, full_bar(s), (kb - WL_KB_CONV) * WL_BK, l0, b);
+                if (pf) tma_prefetch_3d(&map_spect, (kb - WL_KB_CONV) * WL_BK, nl0, nb);
+              }
+              if (!skip_b) tma_load_2d(a_dst + WL_A_BYTES, &map_w1, full_bar(s), kb * WL_BK, p.layer * 2 * WL_C + q * 256);
             }
-            if (!skip_b) tma_load_2d(a_dst + WL_A_BYTES, &map_w1, full_bar(s), kb * WL_BK, p.layer * 2 * WL_C + q * 256);
+            __syncwarp();
           }
         }
         if (!LAST) {
@@ -501,23 +513,28 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
               const uint32_t s = acquire(2 * WL_A_BYTES);
               const uint32_t dst = smem_base + s * WL_STAGE_BYTES;
               const int kb = (step - 2) * 2;
-              tma_load_3d(dst, &map_lo, full_bar(s), kb * WL_BK, l0, b);
-              tma_load_3d(dst + WL_A_BYTES, &map_lo, full_bar(s), (kb + 1) * WL_BK, l0, b);
+              if (elect_one()) {
+                tma_load_3d(dst, &map_lo, full_bar(s), kb * WL_BK, l0, b);
+                tma_load_3d(dst + WL_A_BYTES, &map_lo, full_bar(s), (kb + 1) * WL_BK, l0, b);
+              }
             } else {
               const int kb = step < 2 ? step : step - 2;
               const uint32_t s = acquire(WL_STAGE_BYTES);
               const uint32_t dst = smem_base + s * WL_STAGE_BYTES;
-              tma_load_3d(dst, &map_h, full_bar(s), kb * WL_BK, l0, b);
-              tma_load_2d(dst + WL_A_BYTES, &map_w2, full_bar(s), kb * WL_BK, p.layer * WL_C);
+              if (elect_one()) {
+                tma_load_3d(dst, &map_h, full_bar(s), kb * WL_BK, l0, b);
+                tma_load_2d(dst + WL_A_BYTES, &map_w2, full_bar(s), kb * WL_BK, p.layer * WL_C);
+              }
             }
+            __syncwarp();
           }
         }
       }
-      if (timing) atomicAdd(p.timing + 8, static_cast<unsigned long long>(t_wait));
+      if (timing && lane == 0) atomicAdd(p.timing + 8, static_cast<unsigned long long>(t_wait));
     }
   } else if (warp == 1) {
     // ====================================== MMA issuer =======================================
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(128, 256);
       constexpr uint32_t idesc_id = umma_idesc_bf16(128, 64);
       const uint64_t idesc64 = umma_desc_sw128(smem_base + WL_OFF_I64);
@@ -554,47 +571,54 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
           for (int kb = 0; kb < WL_KB1; ++kb, ++it) {
             const uint32_t a_addr = wait_full();
             const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + WL_A_BYTES);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < WL_BK / 16; ++k)
-              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
-            tc_commit(empty_bar(it % WL_STAGES));
+              for (int k = 0; k < WL_BK / 16; ++k)
+                umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+              tc_commit(empty_bar(it % WL_STAGES));
+              if (kb == WL_KB1 - 1) tc_commit(dfull_bar(q));
+            }
+            __syncwarp();
           }
-          tc_commit(dfull_bar(q));
         }
         if (!LAST) {
           const uint32_t d_tmem = tmem_base + 256u * par;
           wait_epi(actsa_bar, n & 1u);   // acts blocks 0,1 written, D1a (this region) read out
           for (int step = 0; step < 6; ++step, ++it) {
-            if (step == 4) wait_epi(acts_bar, n & 1u);   // acts blocks 2,3 written, D1b read out
+            if (step == 4) wait_epi(acts2_bar, n & 1u);  // acts block 2 written (all epilogue warps work on it first)
+            if (step == 5) wait_epi(acts_bar, n & 1u);   // acts block 3 written, D1b read out
             const uint32_t st_addr = wait_full();
-            if (step == 2 || step == 3) {
-              // lo blocks 2j, 2j+1 -> identity add into columns [128 j', ...)
-              const int kb = (step - 2) * 2;
+            if (elect_one()) {
+              if (step == 2 || step == 3) {
+                // lo blocks 2j, 2j+1 -> identity add into their 64-column slices
+                const int kb = (step - 2) * 2;
 #pragma unroll
-              for (int h2 = 0; h2 < 2; ++h2) {
-                const uint64_t adesc = umma_desc_sw128(st_addr + h2 * WL_A_BYTES);
+                for (int h2 = 0; h2 < 2; ++h2) {
+                  const uint64_t adesc = umma_desc_sw128(st_addr + h2 * WL_A_BYTES);
+#pragma unroll
+                  for (int k = 0; k < WL_BK / 16; ++k)
+                    umma_bf16(d_tmem + 64u * (kb + h2), adesc + 2 * k, idesc64 + 2 * k, idesc_id, 1u);
+                }
+              } else {
+                const int kb = step < 2 ? step : step - 2;
+                const uint64_t adesc = umma_desc_sw128(smem_base + WL_OFF_ACTS + kb * WL_A_BYTES);
+                const uint64_t bdesc = umma_desc_sw128(st_addr + WL_A_BYTES);
 #pragma unroll
                 for (int k = 0; k < WL_BK / 16; ++k)
-                  umma_bf16(d_tmem + 64u * (kb + h2), adesc + 2 * k, idesc64 + 2 * k, idesc_id, 1u);
+                  umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (step | k) ? 1u : 0u);
+                const uint64_t hdesc = umma_desc_sw128(st_addr);   // hi block kb (centre tap rows)
+#pragma unroll
+                for (int k = 0; k < WL_BK / 16; ++k)
+                  umma_bf16(d_tmem + 64u * kb, hdesc + 2 * k, idesc64 + 2 * k, idesc_id, 1u);
               }
-            } else {
-              const int kb = step < 2 ? step : step - 2;
-              const uint64_t adesc = umma_desc_sw128(smem_base + WL_OFF_ACTS + kb * WL_A_BYTES);
-              const uint64_t bdesc = umma_desc_sw128(st_addr + WL_A_BYTES);
-#pragma unroll
-              for (int k = 0; k < WL_BK / 16; ++k)
-                umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (step | k) ? 1u : 0u);
-              const uint64_t hdesc = umma_desc_sw128(st_addr);   // hi block kb (centre tap rows)
-#pragma unroll
-              for (int k = 0; k < WL_BK / 16; ++k)
-                umma_bf16(d_tmem + 64u * kb, hdesc + 2 * k, idesc64 + 2 * k, idesc_id, 1u);
+              tc_commit(empty_bar(it % WL_STAGES));
+              if (step == 5) tc_commit(dfull_bar(2));
             }
-            tc_commit(empty_bar(it % WL_STAGES));
+            __syncwarp();
           }
-          tc_commit(dfull_bar(2));
         }
       }
-      if (timing) {
+      if (timing && lane == 0) {
         atomicAdd(p.timing + 0, static_cast<unsigned long long>(clock64() - t_begin));
         atomicAdd(p.timing + 1, static_cast<unsigned long long>(t_full));
         atomicAdd(p.timing + 2, static_cast<unsigned long long>(t_epi));
@@ -631,26 +655,34 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
         tc_fence_after();
         long long t1 = 0;
         if (tmr) { t1 = clock64(); (q == 0 ? t_w0 : t_w1) += t1 - t0; }
-        const uint32_t taddr = tmem_base + lane_addr + 256u * (q == 0 ? par : (par ^ 1u)) + hf * 64;
-        uint8_t* kblk = acts + (q * 2 + hf) * WL_A_BYTES + row * 128;   // K-block (64 channels) row
-        const float* bT0 = s_b1 + q * 256 + hf * 64;
-        const float* wse0 = cw.wse + (q * 128 + hf * 64) * 8;
+        // All eight warps work on the same 64-channel K-block (two blocks per chunk, one after the other):
+        // thread = (row, hf) handles channels [32 hf, 32 hf + 32) of the block in two steps of 16. The first
+        // block of chunk b is therefore complete half-way through this epilogue and GEMM2 can consume it
+        // while the second is still being gated.
+        const uint32_t taddr = tmem_base + lane_addr + 256u * (q == 0 ? par : (par ^ 1u)) + hf * 32;
         uint32_t t0r[16], g0r[16], t1r[16], g1r[16];
         tmem_ld16(taddr, t0r);
         tmem_ld16(taddr + 128, g0r);
 #pragma unroll 1
-        for (int sp = 0; sp < 2; ++sp) {          // two steps of 16 channels per iteration (double-buffered)
-          const int st = 2 * sp;
+        for (int blk = 0; blk < 2; ++blk) {
+          uint8_t* kblk = acts + (q * 2 + blk) * WL_A_BYTES + row * 128;   // K-block (64 channels) row
+          const int ch0 = blk * 64 + hf * 32;                                // first channel inside the chunk
+          const float* bT0 = s_b1 + q * 256 + ch0;
+          const float* wse0 = cw.wse + (q * 128 + ch0) * 8;
           tmem_ld_wait();
-          tmem_ld16(taddr + (st + 1) * 16, t1r);
-          tmem_ld16(taddr + 128 + (st + 1) * 16, g1r);
-          gate_step<LAST>(t0r, g0r, bT0 + st * 16, wse0 + st * 128, kblk, st, row, o8);
+          tmem_ld16(taddr + blk * 64 + 16, t1r);
+          tmem_ld16(taddr + 128 + blk * 64 + 16, g1r);
+          gate_step<LAST>(t0r, g0r, bT0, wse0, kblk, hf * 2, row, o8);
           tmem_ld_wait();
-          if (sp == 0) {
-            tmem_ld16(taddr + (st + 2) * 16, t0r);
-            tmem_ld16(taddr + 128 + (st + 2) * 16, g0r);
+          if (blk == 0) {
+            tmem_ld16(taddr + 64, t0r);
+            tmem_ld16(taddr + 128 + 64, g0r);
           }
-          gate_step<LAST>(t1r, g1r, bT0 + (st + 1) * 16, wse0 + (st + 1) * 128, kblk, st + 1, row, o8);
+          gate_step<LAST>(t1r, g1r, bT0 + 16, wse0 + 128, kblk, hf * 2 + 1, row, o8);
+          if (!LAST && q == 1 && blk == 0) {
+            fence_proxy_async_smem();
+            mbar_arrive(acts2_bar);
+          }
         }
         tc_fence_before();
         if (LAST) {

@@ -89,14 +89,9 @@ __device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t adesc, uint
       : "memory");
 }
 
-// One lane of a fully converged warp. Keeping the whole warp in the producer / MMA loops (and electing only
-// around the asm) lets ptxas keep descriptors and coordinates in UNIFORM registers; a loop entered by
-// `if (lane == 0)` made every UTCHMMA / UTMALDG pay an ELECT + R2UR.BROADCAST waterfall.
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
+// (elect_one() lives in tc_kernels.cuh: keeping the whole warp in the producer / MMA loops and electing only
+// around the asm lets ptxas keep descriptors and coordinates in UNIFORM registers; a loop entered by
+// `if (lane == 0)` made every UTCHMMA / UTMALDG pay an ELECT + R2UR.BROADCAST waterfall.)
 
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of CTA 1 -> same offset in CTA 0
 
@@ -299,6 +294,7 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
       const uint64_t idesc64 = umma_desc_sw128(smem_base + WP_OFF_I64);
       uint32_t it = 0;
       long long t_full = 0, t_epi = 0, t_begin = 0, t_i2f = 0, n_i2f = 0, t_i2f_w = 0, n_i2f_w = 0;
+      long long t_issue_mma = 0, t_issue_commit = 0, t_syncwarp = 0;
       if (timing) {
         t_begin = clock64();
         if (lane == 0) for (int i = 0; i < 64; ++i) wait_pos[i] = 0;
@@ -343,13 +339,19 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
             const uint32_t a_addr = wait_full();
             const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + WP_A_BYTES);
             if (elect_one()) {
+              long long c0 = 0, c1 = 0;
+              if (timing) c0 = clock64();
+              if (!(p.flags & 64)) {   // flag 64: feed-only probe (no MMA issued, stages are released at once)
 #pragma unroll
-              for (int k = 0; k < WL_BK / 16; ++k)
-                umma2_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
-              if (timing) ts_commit[it % nst] = clock64();
+                for (int k = 0; k < WL_BK / 16; ++k)
+                  umma2_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+              }
+              if (timing) { c1 = clock64(); ts_commit[it % nst] = c1; t_issue_mma += c1 - c0; }
               tc2_commit(empty_bar(it % nst));
               if (kb == WL_KB1 - 1) tc2_commit(dfull_bar(q));
+              if (timing) t_issue_commit += clock64() - c1;
             }
+            if (timing) { const long long c2 = clock64(); __syncwarp(); t_syncwarp += clock64() - c2; } else
             __syncwarp();
           }
         }
@@ -398,6 +400,17 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
         atomicAdd(p.timing + 13, static_cast<unsigned long long>(t_i2f_w));
         atomicAdd(p.timing + 14, static_cast<unsigned long long>(n_i2f_w));
         for (int i = 0; i < 64; ++i) atomicAdd(p.timing + 16 + i, static_cast<unsigned long long>(wait_pos[i]));
+      }
+      if (timing) {   // elected-lane counters: reduce over the warp (only the elected lane accumulated)
+        for (int o = 16; o > 0; o >>= 1) {
+          t_issue_mma += __shfl_xor_sync(0xffffffffu, t_issue_mma, o);
+          t_issue_commit += __shfl_xor_sync(0xffffffffu, t_issue_commit, o);
+        }
+        if (lane == 0) {
+          atomicAdd(p.timing + 80, static_cast<unsigned long long>(t_issue_mma));
+          atomicAdd(p.timing + 81, static_cast<unsigned long long>(t_issue_commit));
+          atomicAdd(p.timing + 82, static_cast<unsigned long long>(t_syncwarp));
+        }
       }
     }
   } else {

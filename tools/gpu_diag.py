@@ -112,7 +112,8 @@ def stage_accuracy():
 def stage_time():
     hp = WaveGlowHParams()
     w = generate_weights(hp, 1234)
-    for mode, (B, T) in (("bf16", (16, 860)), ("fp32", (1, 200))):
+    bt = tuple(int(x) for x in os.environ.get("WG_BT", "16,860").split(","))
+    for mode, (B, T) in (("bf16", bt), ("fp32", (1, 200))):
         eng = WaveGlowEngine(hp, w, mode=mode)
         mel, z = synthetic_inputs(1, B, T, hp)
         md, zd = torch.from_numpy(mel).cuda(), torch.from_numpy(z).cuda()
@@ -141,6 +142,7 @@ def stage_time():
             tot = max(t[0], 1)
             for nm, v in zip(names, t):
                 print(f"    {nm:22s} {v/1e6:12.1f} Mcycles  {100.0*v/tot:6.1f}% of mma total")
+            print(f"    MMA thread: issuing MMAs {100.0*t[80]/tot:5.1f}%  commit instructions {100.0*t[81]/tot:5.1f}%  syncwarp {100.0*t[82]/tot:5.1f}% (GEMM1 stages only)")
             hist = t[16:16 + 52]
             if sum(hist):
                 print("    MMA wait-for-data by stage position in the tile (% of all such waiting):")

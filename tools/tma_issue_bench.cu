@@ -65,10 +65,20 @@ int main() {
   PFN_enc enc = (PFN_enc)f;
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   const int sms = prop.multiProcessorCount;
-  const size_t rows = (size_t)1024 * 4 * sms;   // 77 MB
+  const size_t rows = (size_t)1024 * 24 * sms;   // 465 MB (strided views need room; L2-resident working set stays 1024 rows x stride per CTA)
   void* d; CK(cudaMalloc(&d, rows * 128)); CK(cudaMemset(d, 0, rows * 128));
   CUtensorMap map; cuuint64_t gdim[2] = {64, rows}, gstr[1] = {128}; cuuint32_t box[2] = {64, 128}, es[2] = {1, 1};
   if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return 1;
-  for (int mode = 0; mode < 2; ++mode) { run<1>(map, sms, mode, (const char*)d); run<2>(map, sms, mode, (const char*)d); }
+  for (int mode = 0; mode < 2; ++mode) { run<1>(map, sms, mode, (const char*)d); }
+  for (int stride : {128, 512, 1280, 2816}) {
+    // view the same buffer as [rows2, stride/2] bf16 and take the first 64 columns of each row
+    const size_t rows2 = rows * 128 / stride;
+    CUtensorMap m2; cuuint64_t gd[2] = {(cuuint64_t)stride / 2, rows2}, gs[1] = {(cuuint64_t)stride};
+    if (enc(&m2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d, gd, gs, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { printf("enc fail\n"); return 1; }
+    printf("row stride %d B: ", stride);
+    // each warp's region: 1024 rows of the strided view must stay inside the buffer: rows2 >= sms*1024?
+    if (rows2 < (size_t)sms * 1024) { printf("skipped (buffer too small)\n"); continue; }
+    run<1>(m2, sms, 0, (const char*)d);
+  }
   return 0;
 }
