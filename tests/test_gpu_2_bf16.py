@@ -51,7 +51,8 @@ def test_bf16_matches_golden(lib_built, case):
     eng.close()
 
 
-def test_bf16_intermediates_against_oracle_taps(lib_built):
+def test_bf16_intermediates_against_oracle_taps(lib_built, monkeypatch):
+    monkeypatch.setenv("WG_PM", "0")     # spect is only materialised by the position-major path
     hp = WaveGlowHParams()
     w = generate_weights(hp, 1234, bias_std=0.05)
     mel, z = synthetic_inputs(5, 2, 7, hp)        # L = 224: a full tile + a ragged tile per utterance
@@ -88,6 +89,30 @@ def test_bf16_ragged_shapes_against_oracle(lib_built, B, T):
     ref = OracleWaveGlow(hp, w)(mel, z, 0.6).numpy()
     out = _run(_engine(hp, w), mel, z, 0.6)
     assert np.abs(out - ref).max() <= TOL_BF16_ABS and snr_db(ref, out) >= TOL_BF16_SNR
+
+
+@pytest.mark.parametrize("pm", ["0", "1"])
+@pytest.mark.parametrize("B,T", [(2, 5), (3, 33), (1, 130), (2, 200)])
+def test_bf16_both_row_layouts_against_oracle(lib_built, monkeypatch, pm, B, T):
+    """WG_PM=0: position-major rows + materialised spect; WG_PM=1: phase-major rows, conditioning folded to
+    its rank-320 form (Wup_r @ Wcond). Both must meet the BF16 bar on ragged and multi-tile shapes."""
+    monkeypatch.setenv("WG_PM", pm)
+    hp = WaveGlowHParams()
+    w = generate_weights(hp, 1234, bias_std=0.05)
+    mel, z = synthetic_inputs(300 + B * 10 + T, B, T, hp)
+    ref = OracleWaveGlow(hp, w)(mel, z, 0.6).numpy()
+    eng = _engine(hp, w)
+    out = _run(eng, mel, z, 0.6)
+    err, snr = np.abs(out - ref).max(), snr_db(ref, out)
+    print(f"pm={pm} B={B} T={T}: max-abs {err:.3e} SNR {snr:.1f} dB")
+    assert err <= TOL_BF16_ABS and snr >= TOL_BF16_SNR
+    taps = {}
+    OracleWaveGlow(hp, w).infer(mel, z, 0.6, taps=taps)
+    h, acc = eng.debug_prefix(torch.from_numpy(mel).cuda(), torch.from_numpy(z).cuda(), 0.6, 11, 7)
+    torch.cuda.synchronize()
+    ref_h = taps["flow11/layer7/audio"].reshape(-1, hp.n_channels).numpy()
+    assert np.abs(h.cpu().numpy() - ref_h).max() <= 5e-2 * max(1.0, np.abs(ref_h).max())
+    eng.close()
 
 
 def test_bf16_agrees_with_fp32_engine_and_is_reproducible(lib_built):

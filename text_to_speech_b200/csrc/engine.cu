@@ -53,6 +53,7 @@ struct LayerW {
   int rs_cols = 0;
   // bf16 mode (fp32 side arrays; the bf16 matrices live in the stacked arrays below)
   float* b1 = nullptr;    // [2C] chunk-packed order
+  float* b1_pm = nullptr; // same + the upsample bias pushed through the cond weights (phase-major path)
   float* b2 = nullptr;    // [C]
   std::vector<float> wse_h;  // [C, 8] = Wskip @ Wend (fp32), host copy: passed in the kernel parameter bank
 };
@@ -71,6 +72,8 @@ struct wg_engine {
   __nv_bfloat16* Wup16 = nullptr;  // [R*S, Kup_pad]
   __nv_bfloat16* W1 = nullptr;     // [n_flows*n_layers*2C, 3C+S]
   __nv_bfloat16* W2 = nullptr;     // [n_flows*n_layers*C, C]
+  __nv_bfloat16* V = nullptr;      // [n_flows*n_layers*R*2C, Kup]: (Wup_r @ Wcond) per layer and upsample phase
+  int pm_policy = -1;               // WG_PM: -1 auto (by tile efficiency), 0 never, 1 always
   int Kup = 0;
   std::vector<void*> allocs;
   std::string err;
@@ -159,6 +162,15 @@ struct Ws {  // workspace carving for one (B, T)
   size_t total = 0;
 };
 
+// phase-major layout pays when 128-frame tiles are reasonably full
+bool use_pm(const wg_engine* e, int T) {
+  if (e->cfg.mode != WG_MODE_BF16 || !e->V) return false;
+  if (e->pm_policy == 0) return false;
+  if (e->pm_policy == 1) return true;
+  const int tiles = (T + 127) / 128;
+  return T * 10 >= tiles * 128 * 7;
+}
+
 Ws carve(const wg_engine* e, int B, int T) {
   Ws w;
   const size_t M = (size_t)B * T * e->R;
@@ -177,7 +189,7 @@ Ws carve(const wg_engine* e, int B, int T) {
     w.acts = take(M * e->C * 4);
     w.skip = take(M * e->C * 4);
   } else {
-    w.spect16 = take(M * e->S * 2);
+    if (!use_pm(e, T)) w.spect16 = take(M * e->S * 2);
     w.h16a = take(M * e->C * 2);
     w.h16b = take(M * e->C * 2);
     w.hlo = take(M * e->C * 2);
@@ -225,6 +237,8 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
   const wg_config& c = e->cfg;
   const int C = e->C, S = e->S, R = e->R, L = T * R, M = B * L;
   const bool bf16 = c.mode == WG_MODE_BF16;
+  const bool pm = use_pm(e, T);
+  const int geomR = pm ? R : 1, geomT = pm ? T : L;
   float* h32 = bf16 ? nullptr : reinterpret_cast<float*>(base + w.h32);
   float* acc8 = reinterpret_cast<float*>(base + w.acc8);
   float* audio[2] = {reinterpret_cast<float*>(base + w.audio0), reinterpret_cast<float*>(base + w.audio1)};
@@ -251,8 +265,8 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
     launch_gemm<EPI_STORE>(e, g, st);
   } else {
     tc_prepare(plan, e->sm_count, B, T, L, C, S, e->Kup, c.n_mel_channels, c.n_flows * c.n_layers,
-               e->Wup16, R * S, e->W1, e->W2, aup16, spect16, h16[0], h16[1], hlo);
-    if (e->use_pair) tc_pair_prepare(pmaps, c.n_flows * c.n_layers, C, S, e->W1, e->W2);
+               e->Wup16, R * S, e->W1, e->W2, aup16, spect16, h16[0], h16[1], hlo, pm, R, e->V);
+    if (e->use_pair && !pm) tc_pair_prepare(pmaps, c.n_flows * c.n_layers, C, S, e->W1, e->W2);
     e->launches += tc_upsample(plan, mel, e->bup, st);
   }
 
@@ -261,6 +275,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
   int cur = 0, z_off = 0, hcur = 0;
   {
     BoundaryArgs a{};
+    a.R = geomR; a.T = geomT;
     a.first = 1; a.z = zz; a.n_group = c.n_group; a.z_off = 0; a.n_inject = e->flows[F - 1].n_rem;
     a.sigma = sigma; a.audio_out = audio[cur]; a.M = M; a.C = C;
     a.Wstart = e->flows[F - 1].Wstart; a.bstart = e->flows[F - 1].bstart;
@@ -284,10 +299,14 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
     if (h_out && !bf16) CK(cudaMemcpyAsync(h_out, h32, (size_t)M * C * 4, cudaMemcpyDeviceToDevice, st));
     if (h_out && bf16) {
       const size_t n = (size_t)M * C;
-      hilo_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h16[hcur], hlo, h_out, n);
+      hilo_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h16[hcur], hlo, h_out, (size_t)M, C, geomR, geomT);
       CK(cudaGetLastError());
     }
-    if (acc_out) CK(cudaMemcpyAsync(acc_out, acc8, (size_t)M * 8 * 4, cudaMemcpyDeviceToDevice, st));
+    if (acc_out) {
+      const size_t n = (size_t)M * 8;
+      unpermute_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc8, acc_out, (size_t)M, 8, geomR, geomT);
+      CK(cudaGetLastError());
+    }
   };
 
   for (int k = F - 1; k >= 0; --k) {
@@ -321,12 +340,12 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
       } else {
         prof_mark();
         if (e->profiling) e->ev_last.push_back(last ? 1 : 0);
-        if (e->use_pair)
+        if (e->use_pair && !pm)
           e->launches += tc_wn_layer_pair(plan, pmaps, k * c.n_layers + i, d, last, hcur, acc8, lw.b1, lw.b2,
                                           lw.wse_h.data(), e->timing, e->dbg_flags, st);
         else
-          e->launches += tc_wn_layer(plan, k * c.n_layers + i, d, last, hcur, acc8, lw.b1, lw.b2, lw.wse_h.data(),
-                                     e->timing, e->dbg_flags, st);
+          e->launches += tc_wn_layer(plan, k * c.n_layers + i, d, last, hcur, acc8, pm ? lw.b1_pm : lw.b1, lw.b2,
+                                     lw.wse_h.data(), e->timing, e->dbg_flags, st);
         prof_mark();
         if (!last) hcur ^= 1;
       }
@@ -346,6 +365,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
     }
     // coupling inverse + W^-1 + early re-injection + next start conv (:278-304)
     BoundaryArgs a{};
+    a.R = geomR; a.T = geomT;
     a.first = 0; a.acc8 = acc8; a.audio_in = audio[cur]; a.z = zz; a.n_group = c.n_group;
     a.sigma = sigma; a.c_in = 2 * fw.n_half; a.M = M; a.C = C;
     std::memcpy(a.winv, fw.winv, sizeof a.winv);
@@ -362,6 +382,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
       if (bf16) { a.acc8_rearm = acc8; std::memcpy(a.acc8_init, e->flows[k - 1].bse8, sizeof a.acc8_init); }
     } else {
       a.audio_out = out;  // [B*L, 8] == [B, 8L]  (waveglow_arch.py:306)
+      a.final_out = 1;
       a.Wstart = nullptr;
     }
     launch_boundary(e, a, st);
@@ -410,6 +431,8 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
   e->R = HOP / c.n_group;
   const int S = e->S, R = e->R, NM = c.n_mel_channels, G = c.n_group;
 
+  std::vector<float> wup_f32, ub_vec;       // host copies used while folding the conditioning weights
+  std::vector<std::vector<float>> wcond_packed;   // per layer [S, 2C] in chunk-packed column order (bf16 mode)
   std::map<std::string, TensorView> tm;
   for (int i = 0; i < n_tensors; ++i) {
     const wg_tensor& t = tensors[i];
@@ -444,16 +467,21 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
       for (int m = 0; m < NM; ++m)
         for (int g = 0; g < G; ++g) bp[(size_t)r * S + m * G + g] = ub.data[m];
     e->bup = upload(e, bp);
+    // fp32 polyphase matrix [4*n_mel, R*S]: the upsample operand of fp32 mode, and the left factor of the
+    // folded conditioning weights (Wup_r @ Wcond) of the phase-major bf16 path
+    wup_f32.assign((size_t)J * NM * N, 0.f);
+    for (int j = 0; j < J; ++j)
+      for (int i = 0; i < NM; ++i)
+        for (int r = 0; r < R; ++r)
+          for (int m = 0; m < NM; ++m)
+            for (int g = 0; g < G; ++g)
+              wup_f32[((size_t)(j * NM + i)) * N + (size_t)r * S + m * G + g] =
+                  uk.data[((size_t)(HOP * j + G * r + g) * NM + m) * NM + i];
+    ub_vec.assign(S, 0.f);
+    for (int m = 0; m < NM; ++m)
+      for (int g = 0; g < G; ++g) ub_vec[m * G + g] = ub.data[m];
     if (c.mode == WG_MODE_FP32) {
-      std::vector<float> wp((size_t)J * NM * N);
-      for (int j = 0; j < J; ++j)
-        for (int i = 0; i < NM; ++i)
-          for (int r = 0; r < R; ++r)
-            for (int m = 0; m < NM; ++m)
-              for (int g = 0; g < G; ++g)
-                wp[((size_t)(j * NM + i)) * N + (size_t)r * S + m * G + g] =
-                    uk.data[((size_t)(HOP * j + G * r + g) * NM + m) * NM + i];
-      e->Wup = upload(e, wp);
+      e->Wup = upload(e, wup_f32);
     } else {
       e->Kup = (int)align_up((size_t)J * NM, 64);
       std::vector<__nv_bfloat16> wp((size_t)N * e->Kup, f2bf(0.f));
@@ -548,6 +576,22 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
           b1[pcol] = inb.data[col] + cb.data[col];
           for (int kk = 0; kk < K1; ++kk) w1[(size_t)pcol * K1 + kk] = f2bf(wsrc(kk, col));
         }
+        {   // phase-major path: fp32 cond weights in packed column order + bias with the upsample bias folded in
+          std::vector<float> wc((size_t)S * 2 * C), b1pm((size_t)2 * C);
+          for (int pcol = 0; pcol < 2 * C; ++pcol) {
+            const int chunk = pcol >> 8, wi = pcol & 255;
+            const int col = wi < 128 ? 128 * chunk + wi : C + 128 * chunk + (wi - 128);
+            double acc = b1[pcol];
+            for (int sidx = 0; sidx < S; ++sidx) {
+              const float wv = cw.data[(size_t)sidx * 2 * C + col];
+              wc[(size_t)sidx * 2 * C + pcol] = wv;
+              acc += (double)ub_vec[sidx] * (double)wv;
+            }
+            b1pm[pcol] = (float)acc;
+          }
+          wcond_packed.push_back(std::move(wc));
+          lw.b1_pm = upload(e, b1pm);
+        }
         const int skip_off = (i < NL - 1) ? C : 0;
         if (i < NL - 1) {
           __nv_bfloat16* w2 = w2all.data() + ((size_t)k * NL + i) * C * C;
@@ -581,6 +625,37 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
     e->W1 = upload(e, w1all);
     e->W2 = upload(e, w2all);
     tc_init();
+    {   // V[(layer*R + r)*2C + n][k] = sum_s Wup_r[k][s] * Wcond_layer[s][n]   (k < 4*n_mel, padded to Kup)
+      const int Kw = (UPSAMPLE_K / HOP) * NM;       // 320
+      if (Kw % 16 == 0 && Kw == e->Kup) {
+        float* d_wup = nullptr; float* d_wc = nullptr; float* d_tmp = nullptr;
+        const size_t vcount = (size_t)F * NL * R * 2 * C * e->Kup;
+        CK(cudaMalloc(&d_wup, wup_f32.size() * 4));
+        CK(cudaMalloc(&d_wc, (size_t)S * 2 * C * 4));
+        CK(cudaMalloc(&d_tmp, (size_t)Kw * 2 * C * 4));
+        CK(cudaMalloc(&e->V, vcount * 2));
+        e->allocs.push_back(e->V);
+        CK(cudaMemcpy(d_wup, wup_f32.data(), wup_f32.size() * 4, cudaMemcpyHostToDevice));
+        for (int li = 0; li < F * NL; ++li) {
+          CK(cudaMemcpy(d_wc, wcond_packed[li].data(), (size_t)S * 2 * C * 4, cudaMemcpyHostToDevice));
+          for (int r = 0; r < R; ++r) {
+            GemmArgs g{};
+            g.nseg = 1;
+            g.seg[0] = ASeg{d_wup + (size_t)r * S, R * S, S, 0};
+            g.W = d_wc; g.bias = nullptr; g.M = Kw; g.N = 2 * C; g.L = Kw;
+            g.out0 = d_tmp; g.ld0 = 2 * C;
+            dim3 grid((g.N + SG_BN - 1) / SG_BN, (g.M + SG_BM - 1) / SG_BM);
+            gemm_f32_kernel<EPI_STORE><<<grid, SG_THREADS>>>(g);
+            const int n = Kw * 2 * C;
+            transpose_f32_to_bf16_kernel<<<(n + 255) / 256, 256>>>(d_tmp, e->V + ((size_t)li * R + r) * 2 * C * e->Kup, Kw, 2 * C);
+          }
+        }
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+        cudaFree(d_wup); cudaFree(d_wc); cudaFree(d_tmp);
+      }
+      if (const char* pmv = std::getenv("WG_PM")) e->pm_policy = std::atoi(pmv);
+    }
     tc_pair_init();
     if (const char* pr = std::getenv("WG_PAIR")) e->use_pair = pr[0] == '1';
     if (const char* f = std::getenv("WG_DEBUG_FLAGS")) e->dbg_flags = std::atoi(f);
@@ -789,6 +864,7 @@ int wg_debug_get_spect(wg_handle h, int32_t B, int32_t T, const void* workspace,
   return guarded(h, [&] {
     check_shape(h, B, T);
     if (!workspace || !spect_out) fail(WG_ERR_INVALID, "NULL argument");
+    if (use_pm(h, T)) fail(WG_ERR_UNSUPPORTED, "the phase-major path does not materialise spect (set WG_PM=0 to inspect it)");
     const Ws w = carve(h, B, T);
     const size_t n = (size_t)B * T * h->R * h->S;
     cudaStream_t st = static_cast<cudaStream_t>(stream);

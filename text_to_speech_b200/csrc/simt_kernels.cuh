@@ -225,6 +225,10 @@ struct BoundaryArgs {
   // this flow's value has been consumed
   float* acc8_rearm;      // [M,8] or null
   float acc8_init[8];
+  // Row geometry of the internal buffers: position l = R*t + r of utterance b lives at row (b*R + r)*T + t
+  // (R = 1: position-major). z and the final waveform are always position-major.
+  int R, T;
+  int final_out;          // audio_out is the caller's waveform buffer (position-major)
 };
 
 constexpr int FB_ROWS = 64, FB_THREADS = 256;
@@ -237,13 +241,20 @@ flow_boundary_kernel(const __grid_constant__ BoundaryArgs a) {
   if (tid < FB_ROWS) {
     const int m = m0 + tid;
     if (m < a.M) {
+      size_t prow = m;   // position-major row of this internal row
+      if (a.R > 1) {
+        const int per_b = a.R * a.T;
+        const int b = m / per_b, rem = m - b * per_b;
+        const int r = rem / a.T, t = rem - r * a.T;
+        prow = static_cast<size_t>(b) * per_b + static_cast<size_t>(t) * a.R + r;
+      }
       float x[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) x[j] = 0.f;
       int c = 0;
       if (a.first) {
         c = a.n_inject;
-        for (int j = 0; j < c; ++j) x[j] = a.z ? a.sigma * a.z[(size_t)m * a.n_group + a.z_off + j] : 0.f;
+        for (int j = 0; j < c; ++j) x[j] = a.z ? a.sigma * a.z[prow * a.n_group + a.z_off + j] : 0.f;
       } else {
         const int nh = a.c_in >> 1;
         const float4 i0 = *reinterpret_cast<const float4*>(a.audio_in + (size_t)m * 8);
@@ -260,12 +271,13 @@ flow_boundary_kernel(const __grid_constant__ BoundaryArgs a) {
           y[bq] = acc;
         }
         for (int j = 0; j < a.n_inject; ++j)
-          x[j] = a.z ? a.sigma * a.z[(size_t)m * a.n_group + a.z_off + j] : 0.f;
+          x[j] = a.z ? a.sigma * a.z[prow * a.n_group + a.z_off + j] : 0.f;
         for (int j = 0; j < a.c_in; ++j) x[a.n_inject + j] = y[j];
         c = a.c_in + a.n_inject;
       }
-      *reinterpret_cast<float4*>(a.audio_out + (size_t)m * 8) = make_float4(x[0], x[1], x[2], x[3]);
-      *reinterpret_cast<float4*>(a.audio_out + (size_t)m * 8 + 4) = make_float4(x[4], x[5], x[6], x[7]);
+      const size_t orow = a.final_out ? prow : static_cast<size_t>(m);
+      *reinterpret_cast<float4*>(a.audio_out + orow * 8) = make_float4(x[0], x[1], x[2], x[3]);
+      *reinterpret_cast<float4*>(a.audio_out + orow * 8 + 4) = make_float4(x[4], x[5], x[6], x[7]);
       if (a.acc8_rearm) {
         *reinterpret_cast<float4*>(a.acc8_rearm + (size_t)m * 8) =
             make_float4(a.acc8_init[0], a.acc8_init[1], a.acc8_init[2], a.acc8_init[3]);

@@ -93,6 +93,16 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src,
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -317,8 +327,19 @@ constexpr int WL_NBARS = 2 * WL_STAGES + 3 + 2 + 4;
 constexpr int WL_SMEM = WL_OFF_BARS + WL_NBARS * 8 + 16;
 static_assert(WL_SMEM <= 232448, "shared memory budget");
 
+// Row geometry. Position l of utterance b is stored at row ((b*R + r)*T + t) with l = R*t + r:
+//   R = 1  : position-major (T = L rows per utterance), conditioning = upsampled spect [.., 640] (10 K-blocks)
+//   R = 32 : phase-major (T = mel frames). All 128 rows of a tile share the upsample phase r, so the
+//            conditioning GEMM runs at its intrinsic rank: A = 4-frame mel window [.., 320] (5 K-blocks),
+//            B = (Wup_r @ Wcond) folded per (layer, phase). A row shift by s positions is the tile of phase
+//            (r+s) mod R moved by floor((r+s)/R) frames, still one contiguous TMA box.
 struct WnLayerParams {
-  int L, tiles_per_b, n_tiles;
+  int T, R, tiles_per_row, n_tiles;
+  int L, tiles_per_b;   // legacy names used by the CTA-pair kernel (position-major only): L = T, tiles_per_b = tiles_per_row
+  int n_cond_kb;        // K-blocks of the conditioning operand: 10 (spect) or 5 (mel window)
+  int wc_col0;          // first K column of the conditioning weights inside map_wc
+  int wc_row0;          // first N row of this layer's conditioning weights inside map_wc
+  int wc_rstride;       // extra N rows per phase (0 or 512)
   int layer;      // row block in the stacked W1 / W2 matrices
   int dilation;
   const float* b1;   // [512] chunk-packed
@@ -395,7 +416,8 @@ __device__ __forceinline__ void gate_step(const uint32_t (&t)[16], const uint32_
 template <bool LAST>
 __global__ void __launch_bounds__(WL_THREADS, 1)
 tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_ho,
-                   const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_spect, const __grid_constant__ CUtensorMap map_w1,
+                   const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_cond, const __grid_constant__ CUtensorMap map_w1,
+                   const __grid_constant__ CUtensorMap map_wc,
                    const __grid_constant__ CUtensorMap map_w2, const WnLayerParams p,
                    const __grid_constant__ WnLayerConst cw) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -422,7 +444,8 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
     prefetch_tmap(&map_h);
     prefetch_tmap(&map_ho);
     prefetch_tmap(&map_lo);
-    prefetch_tmap(&map_spect);
+    prefetch_tmap(&map_cond);
+    prefetch_tmap(&map_wc);
     prefetch_tmap(&map_w1);
     prefetch_tmap(&map_w2);
     for (int s = 0; s < WL_STAGES; ++s) {
@@ -463,6 +486,15 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const bool timing = p.timing != nullptr;
+  const bool pm = p.R > 1;   // phase-major: maps are (channels, frames, phases, batch); else (channels, rows, batch, 1)
+  const int kb1 = WL_KB_CONV + p.n_cond_kb;   // K-blocks of GEMM1 per chunk: 22 (spect) or 17 (mel window)
+  // tile -> (utterance b, phase r, first row t0 of the 128-row tile inside the (b, r) row block)
+  auto tile_coords = [&](int tile, int& b, int& r, int& t0) {
+    const int tt = tile % p.tiles_per_row, br = tile / p.tiles_per_row;
+    r = br % p.R;
+    b = br / p.R;
+    t0 = tt * WL_BM;
+  };
 
   if (warp == 0) {
     // ===================================== TMA producer ======================================
@@ -481,27 +513,27 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
         return static_cast<uint32_t>(s);
       };
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const int b = tile / p.tiles_per_b, l0 = (tile - b * p.tiles_per_b) * WL_BM;
+        int b, r, t0;
+        tile_coords(tile, b, r, t0);
         for (int q = 0; q < 2; ++q) {
-          // during the second chunk, pull the NEXT tile's activation rows into L2, one box per stage
-          // (spread out so the prefetches never queue ahead of a demand load in the TMA unit)
-          const int nt = tile + static_cast<int>(gridDim.x);
-          const bool pf = q == 1 && nt < p.n_tiles && (p.flags & 8);   // measured slower on B200 (r01): off unless asked
-          const int nb = nt / p.tiles_per_b, nl0 = (nt - nb * p.tiles_per_b) * WL_BM;
-          for (int kb = 0; kb < WL_KB1; ++kb, ++it) {
+          for (int kb = 0; kb < kb1; ++kb, ++it) {
             const bool skip_b = (p.flags & 1) && (kb & 1), skip_a = (p.flags & 2) && (kb & 1);
             const uint32_t s = acquire((skip_a ? 0 : WL_A_BYTES) + (skip_b ? 0 : WL_B_BYTES));
             const uint32_t a_dst = smem_base + s * WL_STAGE_BYTES;
             if (elect_one()) {
               if (kb < WL_KB_CONV) {
+                // tap shifted by sh positions: phase (r+sh) mod R, frames moved by floor((r+sh)/R)
                 const int tap = kb >> 2, cblk = kb & 3;
-                if (!skip_a) tma_load_3d(a_dst, &map_h, full_bar(s), cblk * WL_BK, l0 + (tap - 1) * p.dilation, b);
-                if (pf) tma_prefetch_3d(&map_h, cblk * WL_BK, nl0 + (tap - 1) * p.dilation, nb);
+                const int rs = r + (tap - 1) * p.dilation;
+                const int carry = (rs >= 0) ? rs / p.R : -((-rs + p.R - 1) / p.R);
+                if (!skip_a) tma_load_4d(a_dst, &map_h, full_bar(s), cblk * WL_BK, t0 + carry, pm ? rs - carry * p.R : b, pm ? b : 0);
+                if (!skip_b) tma_load_2d(a_dst + WL_A_BYTES, &map_w1, full_bar(s), kb * WL_BK, p.layer * 2 * WL_C + q * 256);
               } else {
-                if (!skip_a) tma_load_3d(a_dst, &map_spect, full_bar(s), (kb - WL_KB_CONV) * WL_BK, l0, b);
-                if (pf) tma_prefetch_3d(&map_spect, (kb - WL_KB_CONV) * WL_BK, nl0, nb);
+                const int kc = kb - WL_KB_CONV;
+                if (!skip_a) tma_load_4d(a_dst, &map_cond, full_bar(s), kc * WL_BK, t0, pm ? 0 : b, pm ? b : 0);
+                if (!skip_b) tma_load_2d(a_dst + WL_A_BYTES, &map_wc, full_bar(s), p.wc_col0 + kc * WL_BK,
+                                         p.wc_row0 + r * p.wc_rstride + q * 256);
               }
-              if (!skip_b) tma_load_2d(a_dst + WL_A_BYTES, &map_w1, full_bar(s), kb * WL_BK, p.layer * 2 * WL_C + q * 256);
             }
             __syncwarp();
           }
@@ -514,15 +546,15 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
               const uint32_t dst = smem_base + s * WL_STAGE_BYTES;
               const int kb = (step - 2) * 2;
               if (elect_one()) {
-                tma_load_3d(dst, &map_lo, full_bar(s), kb * WL_BK, l0, b);
-                tma_load_3d(dst + WL_A_BYTES, &map_lo, full_bar(s), (kb + 1) * WL_BK, l0, b);
+                tma_load_4d(dst, &map_lo, full_bar(s), kb * WL_BK, t0, pm ? r : b, pm ? b : 0);
+                tma_load_4d(dst + WL_A_BYTES, &map_lo, full_bar(s), (kb + 1) * WL_BK, t0, pm ? r : b, pm ? b : 0);
               }
             } else {
               const int kb = step < 2 ? step : step - 2;
               const uint32_t s = acquire(WL_STAGE_BYTES);
               const uint32_t dst = smem_base + s * WL_STAGE_BYTES;
               if (elect_one()) {
-                tma_load_3d(dst, &map_h, full_bar(s), kb * WL_BK, l0, b);
+                tma_load_4d(dst, &map_h, full_bar(s), kb * WL_BK, t0, pm ? r : b, pm ? b : 0);
                 tma_load_2d(dst + WL_A_BYTES, &map_w2, full_bar(s), kb * WL_BK, p.layer * WL_C);
               }
             }
@@ -568,7 +600,7 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
             if (LAST) wait_epi(drained_bar(q), prev_ph);   // this region still holds tile n-1's chunk q
             else if (q == 1) wait_epi(epi2_bar, prev_ph);  // R[p^1] held GEMM2 of tile n-1
           }
-          for (int kb = 0; kb < WL_KB1; ++kb, ++it) {
+          for (int kb = 0; kb < kb1; ++kb, ++it) {
             const uint32_t a_addr = wait_full();
             const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + WL_A_BYTES);
             if (elect_one()) {
@@ -576,7 +608,7 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
               for (int k = 0; k < WL_BK / 16; ++k)
                 umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
               tc_commit(empty_bar(it % WL_STAGES));
-              if (kb == WL_KB1 - 1) tc_commit(dfull_bar(q));
+              if (kb == kb1 - 1) tc_commit(dfull_bar(q));
             }
             __syncwarp();
           }
@@ -636,11 +668,12 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
     long long t_w0 = 0, t_w1 = 0, t_w2 = 0, t_e1 = 0, t_e2 = 0;
     uint32_t n = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++n) {
-      const int b = tile / p.tiles_per_b, l0 = (tile - b * p.tiles_per_b) * WL_BM;
+      int b, r, t0;
+      tile_coords(tile, b, r, t0);
       const uint32_t par = LAST ? 0u : (n & 1u);
       const uint32_t ph = n & 1u;
-      const bool valid = (l0 + row) < p.L;
-      const size_t m = static_cast<size_t>(b) * p.L + l0 + row;
+      const bool valid = (t0 + row) < p.T;
+      const size_t m = (static_cast<size_t>(b) * p.R + r) * p.T + t0 + row;
       float o8[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) o8[j] = 0.f;
@@ -649,12 +682,12 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
       // (loops deliberately NOT fully unrolled: the kernel must stay inside the instruction cache)
 #pragma unroll 1
       for (int q = 0; q < 2; ++q) {
-        long long t0 = 0;
-        if (tmr) t0 = clock64();
+        long long tw0 = 0;
+        if (tmr) tw0 = clock64();
         mbar_wait(dfull_bar(q), ph);
         tc_fence_after();
-        long long t1 = 0;
-        if (tmr) { t1 = clock64(); (q == 0 ? t_w0 : t_w1) += t1 - t0; }
+        long long tw1 = 0;
+        if (tmr) { tw1 = clock64(); (q == 0 ? t_w0 : t_w1) += tw1 - tw0; }
         // All eight warps work on the same 64-channel K-block (two blocks per chunk, one after the other):
         // thread = (row, hf) handles channels [32 hf, 32 hf + 32) of the block in two steps of 16. The first
         // block of chunk b is therefore complete half-way through this epilogue and GEMM2 can consume it
@@ -691,7 +724,7 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
           fence_proxy_async_smem();   // acts (generic-proxy writes) -> visible to the MMA (async proxy)
           mbar_arrive(q == 0 ? actsa_bar : acts_bar);
         }
-        if (tmr) t_e1 += clock64() - t1;
+        if (tmr) t_e1 += clock64() - tw1;
       }
       // fold accumulator: the two column halves of a row are combined in a fixed order (bit-reproducible)
       if (hf == 1) {
@@ -713,12 +746,12 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
       // Staged through the (now free) acts tile in the TMA SWIZZLE_128B layout and written with TMA
       // stores (rows beyond L are clipped by the tensor map). Two passes over the accumulator: hi, then lo.
       if (!LAST) {
-        long long t0 = 0;
-        if (tmr) t0 = clock64();
+        long long tw0 = 0;
+        if (tmr) tw0 = clock64();
         mbar_wait(dfull_bar(2), ph);
         tc_fence_after();
-        long long t1 = 0;
-        if (tmr) { t1 = clock64(); t_w2 += t1 - t0; }
+        long long tw1 = 0;
+        if (tmr) { tw1 = clock64(); t_w2 += tw1 - tw0; }
         const uint32_t taddr = tmem_base + lane_addr + 256u * par + hf * 128;
         uint8_t* stg = acts + (hf * 2) * WL_A_BYTES + row * 128;      // this half's two 64-column blocks
         const uint32_t stg_addr = smem_base + WL_OFF_ACTS + (hf * 2) * WL_A_BYTES;
@@ -750,13 +783,13 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
           else asm volatile("bar.sync 4, 128;" ::: "memory");
           if (issuer) {
             const CUtensorMap* om = pass == 0 ? &map_ho : &map_lo;
-            tma_store_3d(om, stg_addr, (hf * 2) * WL_BK, l0, b);
-            tma_store_3d(om, stg_addr + WL_A_BYTES, (hf * 2 + 1) * WL_BK, l0, b);
+            tma_store_4d(om, stg_addr, (hf * 2) * WL_BK, t0, pm ? r : b, pm ? b : 0);
+            tma_store_4d(om, stg_addr + WL_A_BYTES, (hf * 2 + 1) * WL_BK, t0, pm ? r : b, pm ? b : 0);
             bulk_commit();
           }
         }
         if (issuer) bulk_wait_read0();   // staging tile may be overwritten by the next gate epilogue
-        if (tmr) t_e2 += clock64() - t1;
+        if (tmr) t_e2 += clock64() - tw1;
       }
       // s_o8 and the staging tile are reused by the next tile: no epilogue warp may run ahead
       asm volatile("bar.sync 1, %0;" ::"n"(WL_EPI_THREADS) : "memory");
@@ -794,6 +827,14 @@ __global__ void upsample_im2col_kernel(const float* __restrict__ mel, __nv_bfloa
   float v = 0.f;
   if (j < 4 && t - j >= 0) v = mel[(bt - j) * n_mel + i];
   aup[idx] = __float2bfloat16_rn(v);
+}
+
+// weight prep: out[n*K + k] = bf16(in[k*N + n])  (fp32 [K,N] -> bf16 K-major [N,K])
+__global__ void transpose_f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int K, int N) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= K * N) return;
+  const int n = idx / K, k = idx - n * K;
+  out[idx] = __float2bfloat16_rn(in[static_cast<size_t>(k) * N + n]);
 }
 
 __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, size_t n) {
@@ -854,36 +895,81 @@ inline void make_map_3d(CUtensorMap* m, const void* ptr, uint64_t batch, uint64_
   make_map(m, ptr, 3, dims, str, box);
 }
 
+inline void make_map_4d(CUtensorMap* m, const void* ptr, uint64_t batch, uint64_t phases, uint64_t rows, uint64_t cols,
+                        uint32_t box_rows) {
+  const uint64_t dims[4] = {cols, rows, phases, batch};
+  const uint64_t str[3] = {cols * 2, rows * cols * 2, phases * rows * cols * 2};
+  const uint32_t box[4] = {64, box_rows, 1, 1};
+  cuuint64_t gdim[4], gstr[3];
+  cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
+  for (int i = 0; i < 4; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; }
+  for (int i = 0; i < 3; ++i) gstr[i] = str[i];
+  CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, bx, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) fail(WG_ERR_CUDA, "cuTensorMapEncodeTiled (4-D) failed with CUresult %d", (int)r);
+}
+
 struct TcPlan {
+  // position-major maps used by the upsample GEMM and the CTA-pair kernel
   CUtensorMap m_aup, m_wup, m_w1, m_w2, m_h16[2], m_lo, m_spect;
+  // (phase, frame) geometry of the single-CTA layer kernel: 4-D maps (channels, rows, phases, batch)
+  CUtensorMap m4_h[2], m4_lo, m4_cond, m_wc;
+  bool pm = false;           // phase-major layout (R = 32) with the rank-320 conditioning
+  int R = 1, Trows = 0, tiles_per_row = 0;
+  int n_cond_kb = 0, wc_col0 = 0, wc_rows_per_layer = 0, wc_rstride = 0;
   int sm_count = 0, B = 0, T = 0, L = 0, C = 0, S = 0, Kup = 0, n_mel = 0, NupN = 0;
   int tiles_per_b = 0, n_tiles = 0;
   __nv_bfloat16 *aup16 = nullptr, *spect16 = nullptr, *h16[2] = {nullptr, nullptr}, *hlo = nullptr;
 };
 
+// `pm`: phase-major layout. `V` = folded conditioning weights [n_layers_total * R * 2C, Kup] (pm only).
 inline void tc_prepare(TcPlan& pl, int sm_count, int B, int T, int L, int C, int S, int Kup, int n_mel,
                        int n_layers_total, const __nv_bfloat16* Wup16, int NupN, const __nv_bfloat16* W1,
                        const __nv_bfloat16* W2, __nv_bfloat16* aup16, __nv_bfloat16* spect16, __nv_bfloat16* h16a,
-                       __nv_bfloat16* h16b, __nv_bfloat16* hlo) {
+                       __nv_bfloat16* h16b, __nv_bfloat16* hlo, bool pm, int R, const __nv_bfloat16* V) {
   if (C != WL_C || S != WL_S) fail(WG_ERR_UNSUPPORTED, "tensor path is built for C=256, S=640 (got C=%d, S=%d)", C, S);
   pl.sm_count = sm_count; pl.B = B; pl.T = T; pl.L = L; pl.C = C; pl.S = S; pl.Kup = Kup; pl.n_mel = n_mel; pl.NupN = NupN;
-  pl.tiles_per_b = (L + WL_BM - 1) / WL_BM;
-  pl.n_tiles = pl.tiles_per_b * B;
   pl.aup16 = aup16; pl.spect16 = spect16; pl.h16[0] = h16a; pl.h16[1] = h16b; pl.hlo = hlo;
-  make_map_2d(&pl.m_aup, aup16, (uint64_t)B * T, Kup, TG_BM);
-  make_map_2d(&pl.m_wup, Wup16, NupN, Kup, TG_BN);
+  pl.pm = pm;
+  pl.R = pm ? R : 1;
+  pl.Trows = pm ? T : L;
+  pl.tiles_per_row = (pl.Trows + WL_BM - 1) / WL_BM;
+  pl.n_tiles = pl.tiles_per_row * pl.R * B;
+  pl.tiles_per_b = pl.tiles_per_row;
   make_map_2d(&pl.m_w1, W1, (uint64_t)n_layers_total * 2 * C, 3 * C + S, 256);
   make_map_2d(&pl.m_w2, W2, (uint64_t)n_layers_total * C, C, 256);
-  make_map_3d(&pl.m_h16[0], h16a, B, L, C, WL_BM);
-  make_map_3d(&pl.m_h16[1], h16b, B, L, C, WL_BM);
-  make_map_3d(&pl.m_lo, hlo, B, L, C, WL_BM);
-  make_map_3d(&pl.m_spect, spect16, B, L, S, WL_BM);
+  // phase-major: (channels, frames, phases, batch); position-major: (channels, rows, batch, 1)
+  const uint64_t d3 = pm ? B : 1, d2 = pm ? (uint64_t)R : (uint64_t)B;
+  make_map_4d(&pl.m4_h[0], h16a, d3, d2, pl.Trows, C, WL_BM);
+  make_map_4d(&pl.m4_h[1], h16b, d3, d2, pl.Trows, C, WL_BM);
+  make_map_4d(&pl.m4_lo, hlo, d3, d2, pl.Trows, C, WL_BM);
+  if (pm) {
+    if (Kup % WL_BK) fail(WG_ERR_UNSUPPORTED, "mel window K (%d) must be a multiple of 64", Kup);
+    make_map_4d(&pl.m4_cond, aup16, B, 1, T, Kup, WL_BM);
+    make_map_2d(&pl.m_wc, V, (uint64_t)n_layers_total * R * 2 * C, Kup, 256);
+    pl.n_cond_kb = Kup / WL_BK; pl.wc_col0 = 0; pl.wc_rows_per_layer = R * 2 * C; pl.wc_rstride = 2 * C;
+  } else {
+    make_map_2d(&pl.m_aup, aup16, (uint64_t)B * T, Kup, TG_BM);
+    make_map_2d(&pl.m_wup, Wup16, NupN, Kup, TG_BN);
+    make_map_4d(&pl.m4_cond, spect16, 1, B, L, S, WL_BM);
+    make_map_2d(&pl.m_wc, W1, (uint64_t)n_layers_total * 2 * C, 3 * C + S, 256);
+    pl.n_cond_kb = S / WL_BK; pl.wc_col0 = 3 * C; pl.wc_rows_per_layer = 2 * C; pl.wc_rstride = 0;
+    // 3-D maps for the CTA-pair kernel
+    make_map_3d(&pl.m_h16[0], h16a, B, L, C, WL_BM);
+    make_map_3d(&pl.m_h16[1], h16b, B, L, C, WL_BM);
+    make_map_3d(&pl.m_lo, hlo, B, L, C, WL_BM);
+    make_map_3d(&pl.m_spect, spect16, B, L, S, WL_BM);
+  }
 }
 
+// A operand of the conditioning: 4-frame mel window (always), plus the polyphase upsample GEMM when the
+// position-major path needs the materialised spect.
 inline int tc_upsample(const TcPlan& pl, const float* mel, const float* bup, cudaStream_t st) {
   const size_t total = (size_t)pl.B * pl.T * pl.Kup;
   upsample_im2col_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(mel, pl.aup16, pl.B, pl.T, pl.n_mel, pl.Kup);
   WG_CK(cudaGetLastError());
+  if (pl.pm) return 1;
   const int M = pl.B * pl.T;
   dim3 grid(pl.NupN / TG_BN, (M + TG_BM - 1) / TG_BM);
   tc_gemm_kernel<__nv_bfloat16><<<grid, TG_THREADS, TG_SMEM, st>>>(pl.m_aup, pl.m_wup, bup, pl.spect16, M, pl.NupN, pl.Kup);
@@ -891,27 +977,53 @@ inline int tc_upsample(const TcPlan& pl, const float* mel, const float* bup, cud
   return 2;
 }
 
+inline void tc_fill_params(const TcPlan& pl, WnLayerParams& p, int layer, int dilation, int hcur, float* acc8,
+                           const float* b1, const float* b2, unsigned long long* timing, int flags) {
+  p.T = pl.Trows; p.R = pl.R; p.tiles_per_row = pl.tiles_per_row; p.n_tiles = pl.n_tiles;
+  p.L = pl.Trows; p.tiles_per_b = pl.tiles_per_row;
+  p.n_cond_kb = pl.n_cond_kb; p.wc_col0 = pl.wc_col0; p.wc_row0 = layer * pl.wc_rows_per_layer; p.wc_rstride = pl.wc_rstride;
+  p.layer = layer; p.dilation = dilation;
+  p.b1 = b1; p.b2 = b2; p.hi_out = pl.h16[hcur ^ 1]; p.lo = pl.hlo; p.acc8 = acc8; p.timing = timing; p.flags = flags;
+}
+
 inline int tc_wn_layer(const TcPlan& pl, int layer, int dilation, bool last, int hcur, float* acc8, const float* b1,
                        const float* b2, const float* wse_host, unsigned long long* timing, int flags, cudaStream_t st) {
   WnLayerParams p{};
-  p.L = pl.L; p.tiles_per_b = pl.tiles_per_b; p.n_tiles = pl.n_tiles; p.layer = layer; p.dilation = dilation;
-  p.b1 = b1; p.b2 = b2; p.hi_out = pl.h16[hcur ^ 1]; p.lo = pl.hlo; p.acc8 = acc8; p.timing = timing; p.flags = flags;
+  tc_fill_params(pl, p, layer, dilation, hcur, acc8, b1, b2, timing, flags);
   WnLayerConst cw;
   std::memcpy(cw.wse, wse_host, sizeof cw.wse);
   const int grid = pl.n_tiles < pl.sm_count ? pl.n_tiles : pl.sm_count;
   if (last)
-    tc_wn_layer_kernel<true><<<grid, WL_THREADS, WL_SMEM, st>>>(pl.m_h16[hcur], pl.m_h16[hcur ^ 1], pl.m_lo, pl.m_spect, pl.m_w1, pl.m_w2, p, cw);
+    tc_wn_layer_kernel<true><<<grid, WL_THREADS, WL_SMEM, st>>>(pl.m4_h[hcur], pl.m4_h[hcur ^ 1], pl.m4_lo, pl.m4_cond, pl.m_w1, pl.m_wc, pl.m_w2, p, cw);
   else
-    tc_wn_layer_kernel<false><<<grid, WL_THREADS, WL_SMEM, st>>>(pl.m_h16[hcur], pl.m_h16[hcur ^ 1], pl.m_lo, pl.m_spect, pl.m_w1, pl.m_w2, p, cw);
+    tc_wn_layer_kernel<false><<<grid, WL_THREADS, WL_SMEM, st>>>(pl.m4_h[hcur], pl.m4_h[hcur ^ 1], pl.m4_lo, pl.m4_cond, pl.m_w1, pl.m_wc, pl.m_w2, p, cw);
   WG_CK(cudaGetLastError());
   return 1;
 }
 
-// debug: h = hi + lo as float32
+// debug: h = hi + lo as float32, rows re-ordered from ((b*R + r)*T + t) to position-major (b, R*t + r)
 __global__ void hilo_to_f32_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
-                                   float* __restrict__ out, size_t n) {
+                                   float* __restrict__ out, size_t n_rows, int C, int R, int T) {
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx < n) out[idx] = __bfloat162float(hi[idx]) + __bfloat162float(lo[idx]);
+  if (idx >= n_rows * C) return;
+  const size_t m = idx / C;
+  const int c = static_cast<int>(idx - m * C);
+  const size_t per_b = static_cast<size_t>(R) * T;
+  const size_t b = m / per_b, rem = m - b * per_b;
+  const size_t r = rem / T, t = rem - r * T;
+  out[(b * per_b + t * R + r) * C + c] = __bfloat162float(hi[idx]) + __bfloat162float(lo[idx]);
+}
+
+// debug: float rows [n_rows, W] re-ordered the same way
+__global__ void unpermute_rows_kernel(const float* __restrict__ in, float* __restrict__ out, size_t n_rows, int W, int R, int T) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= n_rows * W) return;
+  const size_t m = idx / W;
+  const int c = static_cast<int>(idx - m * W);
+  const size_t per_b = static_cast<size_t>(R) * T;
+  const size_t b = m / per_b, rem = m - b * per_b;
+  const size_t r = rem / T, t = rem - r * T;
+  out[(b * per_b + t * R + r) * W + c] = in[idx];
 }
 
 inline void tc_bf16_to_f32(const __nv_bfloat16* in, float* out, size_t n, cudaStream_t st) {

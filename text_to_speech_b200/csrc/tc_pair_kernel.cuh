@@ -575,9 +575,9 @@ inline void tc_pair_prepare(TcPairMaps& pm, int n_layers_total, int C, int S, co
 inline int tc_wn_layer_pair(const TcPlan& pl, const TcPairMaps& pm, int layer, int dilation, bool last, int hcur,
                             float* acc8, const float* b1, const float* b2, const float* wse_host,
                             unsigned long long* timing, int flags, cudaStream_t st) {
+  if (pl.pm) fail(WG_ERR_UNSUPPORTED, "the CTA-pair kernel only supports the position-major layout");
   WnLayerParams p{};
-  p.L = pl.L; p.tiles_per_b = pl.tiles_per_b; p.n_tiles = pl.n_tiles; p.layer = layer; p.dilation = dilation;
-  p.b1 = b1; p.b2 = b2; p.hi_out = pl.h16[hcur ^ 1]; p.lo = pl.hlo; p.acc8 = acc8; p.timing = timing; p.flags = flags;
+  tc_fill_params(pl, p, layer, dilation, hcur, acc8, b1, b2, timing, flags);
   WnLayerConst cw;
   std::memcpy(cw.wse, wse_host, sizeof cw.wse);
   const int max_pairs = pl.sm_count / 2;

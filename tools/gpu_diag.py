@@ -73,10 +73,11 @@ def stage_bf16():
     ref = o.infer(mel, z, 0.6, taps=taps).numpy()
     eng = WaveGlowEngine(hp, w, mode="bf16")
     md, zd = torch.from_numpy(mel).cuda(), torch.from_numpy(z).cuda()
-    print("bf16: upsample + start conv")
+    print("bf16: upsample + start conv   WG_PM =", os.environ.get("WG_PM"))
     h, acc = eng.debug_prefix(md, zd, 0.6, 11, -1)
     torch.cuda.synchronize()
-    stats("spect", eng.debug_spect(B, T).cpu().numpy(), taps["spect"].reshape(-1, 640).numpy())
+    if os.environ.get("WG_PM") != "1":
+        stats("spect", eng.debug_spect(B, T).cpu().numpy(), taps["spect"].reshape(-1, 640).numpy())
     for (k, i) in [(11, 0), (11, 1), (11, 6), (11, 7), (10, 0), (10, 7), (0, 7)]:
         h, acc = eng.debug_prefix(md, zd, 0.6, k, i)
         torch.cuda.synchronize()
