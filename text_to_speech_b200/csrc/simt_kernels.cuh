@@ -291,30 +291,41 @@ flow_boundary_kernel(const __grid_constant__ BoundaryArgs a) {
   }
   if (a.Wstart == nullptr) return;
   __syncthreads();
-  // start conv of the next flow: coalesced over channels (4 per thread)
-  const int C4 = a.C >> 2;
-  for (int idx = tid; idx < FB_ROWS * C4; idx += FB_THREADS) {
-    const int r = idx / C4, c4 = (idx - r * C4) * 4;
+  // start conv of the next flow: coalesced over channels, 8 per thread (16-byte bf16 stores)
+  const int C8 = a.C >> 3;
+  for (int idx = tid; idx < FB_ROWS * C8; idx += FB_THREADS) {
+    const int r = idx / C8, c8 = (idx - r * C8) * 8;
     const int m = m0 + r;
     if (m >= a.M) break;
-    float4 v = *reinterpret_cast<const float4*>(a.bstart + c4);
+    float v[8];
+    {
+      const float4 b0 = *reinterpret_cast<const float4*>(a.bstart + c8);
+      const float4 b1 = *reinterpret_cast<const float4*>(a.bstart + c8 + 4);
+      v[0] = b0.x; v[1] = b0.y; v[2] = b0.z; v[3] = b0.w; v[4] = b1.x; v[5] = b1.y; v[6] = b1.z; v[7] = b1.w;
+    }
     for (int j = 0; j < a.n_half_next; ++j) {
       const float x = s_a0[r][j];
-      const float4 w = *reinterpret_cast<const float4*>(a.Wstart + (size_t)j * a.C + c4);
-      v.x = fmaf(x, w.x, v.x); v.y = fmaf(x, w.y, v.y); v.z = fmaf(x, w.z, v.z); v.w = fmaf(x, w.w, v.w);
+      const float4 w0 = *reinterpret_cast<const float4*>(a.Wstart + (size_t)j * a.C + c8);
+      const float4 w1 = *reinterpret_cast<const float4*>(a.Wstart + (size_t)j * a.C + c8 + 4);
+      v[0] = fmaf(x, w0.x, v[0]); v[1] = fmaf(x, w0.y, v[1]); v[2] = fmaf(x, w0.z, v[2]); v[3] = fmaf(x, w0.w, v[3]);
+      v[4] = fmaf(x, w1.x, v[4]); v[5] = fmaf(x, w1.y, v[5]); v[6] = fmaf(x, w1.z, v[6]); v[7] = fmaf(x, w1.w, v[7]);
     }
-    if (a.h32) *reinterpret_cast<float4*>(a.h32 + (size_t)m * a.C + c4) = v;
+    if (a.h32) {
+      *reinterpret_cast<float4*>(a.h32 + (size_t)m * a.C + c8) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(a.h32 + (size_t)m * a.C + c8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
     if (a.h16) {
-      __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
-      uint2 u;
-      u.x = *reinterpret_cast<uint32_t*>(&p0);
-      u.y = *reinterpret_cast<uint32_t*>(&p1);
-      *reinterpret_cast<uint2*>(a.h16 + (size_t)m * a.C + c4) = u;
-      const float2 f0 = __bfloat1622float2(p0), f1 = __bfloat1622float2(p1);
-      __nv_bfloat162 q0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y), q1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
-      u.x = *reinterpret_cast<uint32_t*>(&q0);
-      u.y = *reinterpret_cast<uint32_t*>(&q1);
-      *reinterpret_cast<uint2*>(a.hlo + (size_t)m * a.C + c4) = u;
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const __nv_bfloat162 p = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+        const float2 f = __bfloat1622float2(p);
+        const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * q] - f.x, v[2 * q + 1] - f.y);
+        hi[q] = *reinterpret_cast<const uint32_t*>(&p);
+        lo[q] = *reinterpret_cast<const uint32_t*>(&l);
+      }
+      *reinterpret_cast<uint4*>(a.h16 + (size_t)m * a.C + c8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(a.hlo + (size_t)m * a.C + c8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
   }
 }
