@@ -115,6 +115,35 @@ def test_bf16_both_row_layouts_against_oracle(lib_built, monkeypatch, pm, B, T):
     eng.close()
 
 
+@pytest.mark.parametrize("pm", ["0", "1"])
+def test_bf16_waveglow512_matches_golden(lib_built, monkeypatch, pm):
+    """WaveGlow-512 (reference default width, BASELINE.json configs[2]) on the two-kernel tcgen05 layer."""
+    monkeypatch.setenv("WG_PM", pm)
+    hp, w, f = load_golden("wg512_t16")
+    eng = _engine(hp, w)
+    out = _run(eng, f["mel"], f["z"], float(f["sigma"]))
+    ref = f["wave_reference_fp32"]
+    err, snr = np.abs(out - ref).max(), snr_db(ref, out)
+    print(f"wg512_t16 pm={pm}: bf16 max-abs {err:.3e}, SNR {snr:.1f} dB")
+    assert err <= TOL_BF16_ABS and snr >= TOL_BF16_SNR
+    eng.close()
+
+
+def test_bf16_waveglow512_multi_tile_against_oracle(lib_built):
+    hp = WaveGlowHParams(n_channels=512)
+    w = generate_weights(hp, 99, bias_std=0.05)
+    mel, z = synthetic_inputs(77, 2, 150, hp)          # phase-major: 2 tiles of 128 frames per (b, phase), ragged
+    ref = OracleWaveGlow(hp, w)(mel, z, 0.6).numpy()
+    eng = _engine(hp, w)
+    out = _run(eng, mel, z, 0.6)
+    err, snr = np.abs(out - ref).max(), snr_db(ref, out)
+    print(f"wg512 2x150: bf16 max-abs {err:.3e}, SNR {snr:.1f} dB")
+    assert err <= TOL_BF16_ABS and snr >= TOL_BF16_SNR
+    assert np.array_equal(_run(eng, mel, z, 0.6), out)                       # reproducible
+    assert np.array_equal(_run(eng, mel[1:2], z[1:2], 0.6)[0], out[1])       # utterances independent
+    eng.close()
+
+
 def test_bf16_agrees_with_fp32_engine_and_is_reproducible(lib_built):
     hp = WaveGlowHParams()
     w = generate_weights(hp, 1234)

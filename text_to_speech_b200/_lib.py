@@ -13,7 +13,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwg_b200.so")
 SOURCES = [os.path.join(_HERE, "csrc", "engine.cu")]
-HEADERS = [os.path.join(_HERE, "csrc", f) for f in ("common.cuh", "simt_kernels.cuh", "tc_kernels.cuh", "tc_pair_kernel.cuh")] + \
+HEADERS = [os.path.join(_HERE, "csrc", f) for f in ("common.cuh", "simt_kernels.cuh", "tc_kernels.cuh", "tc_pair_kernel.cuh", "tc_c512_kernels.cuh")] + \
           [os.path.join(os.path.dirname(_HERE), "include", "wg_b200.h")]
 
 WG_OK = 0

@@ -21,6 +21,7 @@
 #include "simt_kernels.cuh"
 #include "tc_kernels.cuh"
 #include "tc_pair_kernel.cuh"
+#include "tc_c512_kernels.cuh"
 
 namespace {
 
@@ -158,7 +159,7 @@ inline __nv_bfloat16 f2bf(float x) { return __float2bfloat16_rn(x); }
 
 struct Ws {  // workspace carving for one (B, T)
   size_t spect = 0, h32 = 0, acts = 0, skip = 0, acc8 = 0, audio0 = 0, audio1 = 0;
-  size_t spect16 = 0, h16a = 0, h16b = 0, hlo = 0, aup16 = 0;
+  size_t spect16 = 0, h16a = 0, h16b = 0, hlo = 0, aup16 = 0, acts16 = 0;
   size_t total = 0;
 };
 
@@ -194,6 +195,7 @@ Ws carve(const wg_engine* e, int B, int T) {
     w.h16b = take(M * e->C * 2);
     w.hlo = take(M * e->C * 2);
     w.aup16 = take((size_t)B * T * e->Kup * 2);
+    if (e->C == 512) w.acts16 = take(M * e->C * 2);   // WaveGlow-512: acts travel between the gate and residual kernels
   }
   w.total = off;
   return w;
@@ -250,6 +252,8 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
                            reinterpret_cast<__nv_bfloat16*>(base + w.h16b)};
   __nv_bfloat16* hlo = reinterpret_cast<__nv_bfloat16*>(base + w.hlo);
   __nv_bfloat16* aup16 = reinterpret_cast<__nv_bfloat16*>(base + w.aup16);
+  __nv_bfloat16* acts16 = reinterpret_cast<__nv_bfloat16*>(base + w.acts16);
+  CUtensorMap m_acts512;
   const float* zz = deterministic ? nullptr : z;
 
   TcPlan plan;
@@ -266,7 +270,8 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
   } else {
     tc_prepare(plan, e->sm_count, B, T, L, C, S, e->Kup, c.n_mel_channels, c.n_flows * c.n_layers,
                e->Wup16, R * S, e->W1, e->W2, aup16, spect16, h16[0], h16[1], hlo, pm, R, e->V);
-    if (e->use_pair && !pm) tc_pair_prepare(pmaps, c.n_flows * c.n_layers, C, S, e->W1, e->W2);
+    if (e->use_pair && !pm && C == 256) tc_pair_prepare(pmaps, c.n_flows * c.n_layers, C, S, e->W1, e->W2);
+    if (C == 512) make_map_4d(&m_acts512, acts16, pm ? B : 1, pm ? (uint64_t)R : (uint64_t)B, plan.Trows, C, WL_BM);
     e->launches += tc_upsample(plan, mel, e->bup, st);
   }
 
@@ -340,7 +345,10 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
       } else {
         prof_mark();
         if (e->profiling) e->ev_last.push_back(last ? 1 : 0);
-        if (e->use_pair && !pm)
+        if (C == 512)
+          e->launches += tc512_wn_layer(plan, m_acts512, k * c.n_layers + i, d, last, hcur, acc8, pm ? lw.b1_pm : lw.b1,
+                                        lw.b2, lw.wse_h.data(), st);
+        else if (e->use_pair && !pm)
           e->launches += tc_wn_layer_pair(plan, pmaps, k * c.n_layers + i, d, last, hcur, acc8, lw.b1, lw.b2,
                                           lw.wse_h.data(), e->timing, e->dbg_flags, st);
         else
@@ -405,9 +413,11 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
   if (c.n_flows <= 0 || c.n_layers <= 0 || c.n_layers > 12 || c.n_early_every <= 0 || c.n_early_size < 0 ||
       c.n_early_size % 2)
     fail(WG_ERR_INVALID, "bad flow/layer hparams");
-  if (c.mode == WG_MODE_BF16 && c.n_channels != 256)
-    fail(WG_ERR_UNSUPPORTED, "WG_MODE_BF16 currently requires n_channels == 256 (got %d); use WG_MODE_FP32",
+  if (c.mode == WG_MODE_BF16 && c.n_channels != 256 && c.n_channels != 512)
+    fail(WG_ERR_UNSUPPORTED, "WG_MODE_BF16 supports n_channels 256 and 512 (got %d); use WG_MODE_FP32",
          c.n_channels);
+  if (c.mode == WG_MODE_BF16 && c.n_mel_channels * c.n_group != 640)
+    fail(WG_ERR_UNSUPPORTED, "WG_MODE_BF16 requires n_mel_channels * n_group == 640 (got %d)", c.n_mel_channels * c.n_group);
   if (c.mode == WG_MODE_BF16 && (c.n_mel_channels * c.n_group) % 64)
     fail(WG_ERR_UNSUPPORTED, "WG_MODE_BF16 requires n_mel_channels*n_group %% 64 == 0");
 
@@ -657,6 +667,7 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
       if (const char* pmv = std::getenv("WG_PM")) e->pm_policy = std::atoi(pmv);
     }
     tc_pair_init();
+    tc512_init();
     if (const char* pr = std::getenv("WG_PAIR")) e->use_pair = pr[0] == '1';
     if (const char* f = std::getenv("WG_DEBUG_FLAGS")) e->dbg_flags = std::atoi(f);
     if (const char* t = std::getenv("WG_LAYER_TIMING")) {

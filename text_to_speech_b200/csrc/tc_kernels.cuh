@@ -928,7 +928,7 @@ inline void tc_prepare(TcPlan& pl, int sm_count, int B, int T, int L, int C, int
                        int n_layers_total, const __nv_bfloat16* Wup16, int NupN, const __nv_bfloat16* W1,
                        const __nv_bfloat16* W2, __nv_bfloat16* aup16, __nv_bfloat16* spect16, __nv_bfloat16* h16a,
                        __nv_bfloat16* h16b, __nv_bfloat16* hlo, bool pm, int R, const __nv_bfloat16* V) {
-  if (C != WL_C || S != WL_S) fail(WG_ERR_UNSUPPORTED, "tensor path is built for C=256, S=640 (got C=%d, S=%d)", C, S);
+  if ((C != 256 && C != 512) || S != WL_S) fail(WG_ERR_UNSUPPORTED, "tensor path is built for C in {256, 512}, S=640 (got C=%d, S=%d)", C, S);
   pl.sm_count = sm_count; pl.B = B; pl.T = T; pl.L = L; pl.C = C; pl.S = S; pl.Kup = Kup; pl.n_mel = n_mel; pl.NupN = NupN;
   pl.aup16 = aup16; pl.spect16 = spect16; pl.h16[0] = h16a; pl.h16[1] = h16b; pl.hlo = hlo;
   pl.pm = pm;

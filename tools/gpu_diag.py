@@ -110,6 +110,31 @@ def stage_accuracy():
         eng.close()
 
 
+def stage_c512():
+    hp = WaveGlowHParams(n_channels=512)
+    w = generate_weights(hp, 99, bias_std=0.05)
+    B, T = 2, 9
+    mel, z = synthetic_inputs(5, B, T, hp)
+    taps = {}
+    o = OracleWaveGlow(hp, w)
+    ref = o.infer(mel, z, 0.6, taps=taps).numpy()
+    t = time.time()
+    eng = WaveGlowEngine(hp, w, mode="bf16")
+    print(f"engine create {time.time()-t:.1f}s  WG_PM={os.environ.get('WG_PM')}")
+    md, zd = torch.from_numpy(mel).cuda(), torch.from_numpy(z).cuda()
+    for (k, i) in [(11, 0), (11, 1), (11, 7), (0, 7)]:
+        h, acc = eng.debug_prefix(md, zd, 0.6, k, i)
+        torch.cuda.synchronize()
+        nh = hp.flow_channels()[k][0]
+        ref_acc = (o.w[f"block-{k}/end_conv/bias"] + taps[f"flow{k}/layer{i}/skip"] @ o.w[f"block-{k}/end_conv/kernel"][0])
+        stats(f"h flow{k} layer{i}", h.cpu().numpy(), taps[f"flow{k}/layer{i}/audio"].reshape(-1, 512).numpy())
+        if i == 7:
+            stats(f"acc8 flow{k} layer{i}", acc.cpu().numpy()[:, :2 * nh], ref_acc.reshape(-1, 2 * nh).numpy())
+    out = eng.infer_device(md, zd, sigma=0.6)
+    torch.cuda.synchronize()
+    stats("waveform", out.cpu().numpy(), ref)
+
+
 def stage_time():
     hp = WaveGlowHParams()
     w = generate_weights(hp, 1234)
