@@ -202,3 +202,32 @@ def test_runtime_plugin_end_to_end(lib_built, tmp_path):
     want = wrapper_infer(lambda m, **kw: OracleWaveGlow(hp, w)(m, None, kw.get("sigma", 1.0), deterministic=True).numpy(),
                          long_mel, win_len=64, hop_len=-16, deterministic=True)
     assert got.shape == want.shape and np.abs(got - want).max() <= 1e-4
+
+
+def test_wg_infer_is_cuda_graph_capturable(lib_built):
+    """wg_infer does no allocation and no host synchronisation, so a caller can capture it into a CUDA graph
+    (the launch-bound single-utterance case) and replay it with new data in the same buffers."""
+    hp = WaveGlowHParams()
+    w = generate_weights(hp, 1234)
+    eng = _engine(hp, w)
+    mel, z = synthetic_inputs(41, 1, 150, hp)
+    mel2, z2 = synthetic_inputs(42, 1, 150, hp)
+    md, zd = torch.from_numpy(mel).cuda(), torch.from_numpy(z).cuda()
+    out = torch.empty(1, 150 * 256, device="cuda")
+    eager = eng.infer_device(md, zd, 0.6).clone()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        eng.infer_device(md, zd, 0.6, out=out)            # warm-up on the side stream (workspace allocation)
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        eng.infer_device(md, zd, 0.6, out=out)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, eager)
+    md.copy_(torch.from_numpy(mel2)); zd.copy_(torch.from_numpy(z2))
+    g.replay()
+    torch.cuda.synchronize()
+    ref = OracleWaveGlow(hp, w)(mel2, z2, 0.6).numpy()
+    assert np.abs(out.cpu().numpy() - ref).max() <= TOL_BF16_ABS

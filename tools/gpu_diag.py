@@ -135,6 +135,37 @@ def stage_c512():
     stats("waveform", out.cpu().numpy(), ref)
 
 
+def stage_latency():
+    """Single-utterance latency (B=1), eager launches vs a CUDA graph of the same call."""
+    hp = WaveGlowHParams()
+    w = generate_weights(hp, 1234)
+    eng = WaveGlowEngine(hp, w, mode="bf16")
+    for T in (100, 300, 860):
+        mel, z = synthetic_inputs(1, 1, T, hp)
+        md, zd = torch.from_numpy(mel).cuda(), torch.from_numpy(z).cuda()
+        out = torch.empty(1, T * 256, device="cuda")
+        for _ in range(3):
+            eng.infer_device(md, zd, 0.6, out=out)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            eng.infer_device(md, zd, 0.6, out=out)
+        e1.record(); torch.cuda.synchronize()
+        eager = e0.elapsed_time(e1) / 10
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            eng.infer_device(md, zd, 0.6, out=out)
+        g.replay(); torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            g.replay()
+        e1.record(); torch.cuda.synchronize()
+        graph = e0.elapsed_time(e1) / 10
+        print(f"latency B=1 T={T} ({T*256/22050:.1f} s of audio): eager {eager:.2f} ms, CUDA graph {graph:.2f} ms "
+              f"-> {T*256/22050/(graph*1e-3):.0f} xRT")
+
+
 def stage_time():
     hp = WaveGlowHParams()
     w = generate_weights(hp, 1234)
