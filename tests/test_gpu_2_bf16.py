@@ -174,6 +174,20 @@ def test_bf16_full_size_properties(lib_built):
     assert np.abs(full[3, :2048] - ref[0, :2048]).max() <= TOL_BF16_ABS
 
 
+def test_bf16_full_size_parity_against_fp32_engine(lib_built):
+    """The headline configuration (WaveGlow-256, 16 x 860 frames) end to end: the BF16 tcgen05 path against the
+    fp32 engine (itself pinned to the reference fp32 waveform at <= 1e-4 by test_gpu_1_fp32.py) on all
+    3.5 M samples. Bars from BASELINE.json: max-abs <= 2e-2, SNR >= 35 dB."""
+    hp = WaveGlowHParams()
+    w = generate_weights(hp, 1234)
+    mel, z = synthetic_inputs(2024, 16, 860, hp)
+    a = _run(_engine(hp, w, "bf16"), mel, z, 0.6)
+    b = _run(_engine(hp, w, "fp32"), mel, z, 0.6)
+    err, snr = np.abs(a - b).max(), snr_db(b, a)
+    print(f"K2 full size: bf16 vs fp32 engine max-abs {err:.3e}, SNR {snr:.1f} dB, |wave|max {np.abs(b).max():.2f}")
+    assert err <= TOL_BF16_ABS and snr >= TOL_BF16_SNR
+
+
 def test_runtime_plugin_end_to_end(lib_built, tmp_path):
     """The call a user of the reference makes: WaveGlow(runtime='b200', path=...)(mel, sigma=..., z=...)
     with host numpy buffers, plus the extra kwargs the reference's callers pass along."""
