@@ -3,7 +3,7 @@ boundary of yui-mhcp/text_to_speech (models/tts/waveglow.py -> architectures/wav
 from .weights import WaveGlowHParams, generate_weights, save_weights, load_weights, synthetic_inputs  # noqa: F401
 
 __all__ = ["WaveGlowHParams", "generate_weights", "save_weights", "load_weights", "synthetic_inputs",
-           "WaveGlowEngine", "B200WaveGlowRuntime", "build_runtime", "WaveGlow"]
+           "WaveGlowEngine", "B200WaveGlowRuntime", "build_runtime", "WaveGlow", "TacotronSTFT", "MelSTFT"]
 
 
 def __getattr__(name):   # lazy: importing the package must not need torch / the CUDA library
@@ -16,4 +16,7 @@ def __getattr__(name):   # lazy: importing the package must not need torch / the
     if name == "WaveGlow":
         from .waveglow import WaveGlow
         return WaveGlow
+    if name in ("TacotronSTFT", "MelSTFT"):
+        from . import stft
+        return getattr(stft, name)
     raise AttributeError(name)

@@ -12,9 +12,9 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwg_b200.so")
-SOURCES = [os.path.join(_HERE, "csrc", "engine.cu")]
+SOURCES = [os.path.join(_HERE, "csrc", "engine.cu"), os.path.join(_HERE, "csrc", "mel.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", f) for f in ("common.cuh", "simt_kernels.cuh", "tc_kernels.cuh", "tc_pair_kernel.cuh", "tc_c512_kernels.cuh")] + \
-          [os.path.join(os.path.dirname(_HERE), "include", "wg_b200.h")]
+          [os.path.join(os.path.dirname(_HERE), "include", f) for f in ("wg_b200.h", "wg_mel_b200.h")]
 
 WG_OK = 0
 WG_MODE_FP32, WG_MODE_BF16 = 0, 1
@@ -25,12 +25,21 @@ ABI_VERSION = 1
 EXPORTS = ["wg_abi_version", "wg_create", "wg_destroy", "wg_last_error", "wg_workspace_bytes", "wg_infer",
            "wg_infer_host", "wg_last_launch_count", "wg_profile_enable", "wg_profile_read", "wg_debug_read_timing", "wg_debug_infer_prefix", "wg_debug_get_spect",
            "wg_debug_gemm_bf16"]
+# ... and include/wg_mel_b200.h
+MEL_EXPORTS = ["wg_mel_create", "wg_mel_destroy", "wg_mel_last_error", "wg_mel_frames", "wg_mel_spectrogram",
+               "wg_mel_spectrogram_host"]
 
 
 class WgConfig(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in
                 ("n_mel_channels", "n_flows", "n_group", "n_early_every", "n_early_size", "n_layers",
                  "n_channels", "kernel_size", "mode")]
+
+
+class WgMelConfig(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ("sampling_rate", "n_mel_channels", "filter_length", "hop_length", "win_length")] + \
+               [("clip_val", ctypes.c_float)]
 
 
 class WgTensor(ctypes.Structure):
@@ -108,6 +117,18 @@ def load_library():
     lib.wg_debug_get_spect.argtypes = [vp, i32, i32, vp, vp, vp]
     lib.wg_debug_gemm_bf16.restype = c.c_int
     lib.wg_debug_gemm_bf16.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
+    lib.wg_mel_create.restype = c.c_int
+    lib.wg_mel_create.argtypes = [c.POINTER(WgMelConfig), f32p, f32p, i32, c.POINTER(vp)]
+    lib.wg_mel_destroy.restype = None
+    lib.wg_mel_destroy.argtypes = [vp]
+    lib.wg_mel_last_error.restype = c.c_char_p
+    lib.wg_mel_last_error.argtypes = [vp]
+    lib.wg_mel_frames.restype = c.c_int
+    lib.wg_mel_frames.argtypes = [vp, c.c_int64, c.POINTER(c.c_int64)]
+    lib.wg_mel_spectrogram.restype = c.c_int
+    lib.wg_mel_spectrogram.argtypes = [vp, vp, i32, c.c_int64, vp, vp]
+    lib.wg_mel_spectrogram_host.restype = c.c_int
+    lib.wg_mel_spectrogram_host.argtypes = [vp, f32p, i32, c.c_int64, f32p]
     if lib.wg_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libwg_b200.so ABI {lib.wg_abi_version()} != expected {ABI_VERSION}; rebuild")
     _lib = lib
