@@ -12,9 +12,10 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwg_b200.so")
-SOURCES = [os.path.join(_HERE, "csrc", "engine.cu"), os.path.join(_HERE, "csrc", "mel.cu")]
+SOURCES = [os.path.join(_HERE, "csrc", "engine.cu"), os.path.join(_HERE, "csrc", "mel.cu"),
+           os.path.join(_HERE, "csrc", "taco.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", f) for f in ("common.cuh", "simt_kernels.cuh", "tc_kernels.cuh", "tc_pair_kernel.cuh", "tc_c512_kernels.cuh")] + \
-          [os.path.join(os.path.dirname(_HERE), "include", f) for f in ("wg_b200.h", "wg_mel_b200.h")]
+          [os.path.join(os.path.dirname(_HERE), "include", f) for f in ("wg_b200.h", "wg_mel_b200.h", "wg_taco_b200.h")]
 
 WG_OK = 0
 WG_MODE_FP32, WG_MODE_BF16 = 0, 1
@@ -40,6 +41,16 @@ class WgMelConfig(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in
                 ("sampling_rate", "n_mel_channels", "filter_length", "hop_length", "win_length")] + \
                [("clip_val", ctypes.c_float)]
+
+
+TACO_EXPORTS = ["wg_taco_create", "wg_taco_destroy", "wg_taco_last_error", "wg_taco_decode", "wg_taco_set_graph_chunk"]
+
+
+class WgTacoConfig(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ("n_mel_channels", "prenet_dim", "embedding_dim", "attention_rnn_dim", "decoder_rnn_dim",
+                 "attention_dim", "attention_filters", "attention_kernel_size")] + [("prenet_drop_rate", ctypes.c_float),
+                                                                                    ("lstm_weight_dtype", ctypes.c_int32)]
 
 
 class WgTensor(ctypes.Structure):
@@ -129,6 +140,17 @@ def load_library():
     lib.wg_mel_spectrogram.argtypes = [vp, vp, i32, c.c_int64, vp, vp]
     lib.wg_mel_spectrogram_host.restype = c.c_int
     lib.wg_mel_spectrogram_host.argtypes = [vp, f32p, i32, c.c_int64, f32p]
+    lib.wg_taco_create.restype = c.c_int
+    lib.wg_taco_create.argtypes = [c.POINTER(WgTacoConfig), c.POINTER(WgTensor), i32, i32, c.POINTER(vp)]
+    lib.wg_taco_destroy.restype = None
+    lib.wg_taco_destroy.argtypes = [vp]
+    lib.wg_taco_last_error.restype = c.c_char_p
+    lib.wg_taco_last_error.argtypes = [vp]
+    lib.wg_taco_decode.restype = c.c_int
+    lib.wg_taco_decode.argtypes = [vp, vp, c.POINTER(i32), i32, i32, i32, i32, i32, c.c_uint64, vp, vp, vp, vp,
+                                   c.POINTER(i32), vp]
+    lib.wg_taco_set_graph_chunk.restype = c.c_int
+    lib.wg_taco_set_graph_chunk.argtypes = [vp, i32]
     if lib.wg_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libwg_b200.so ABI {lib.wg_abi_version()} != expected {ABI_VERSION}; rebuild")
     _lib = lib

@@ -1,0 +1,76 @@
+"""End-to-end `tts()` pipeline around the WaveGlow path (BASELINE.json configs[3]):
+token sequences -> Tacotron2 mel producer -> B200 WaveGlow runtime -> waveforms, utterance-sharded.
+
+Mirrors the data flow of the reference's `Tacotron2.infer` wrapper (`models/tts/tacotron2.py:104-241`):
+each text is synthesised to a mel trimmed to its predicted length (`outputs.mel[0, :lengths[0]]`,
+:183), vocoded (`vocoder(mels[-1], **kwargs)`, :187), and returned as `{'mel', 'audio', 'rate', 'time'}`
+(:196-203; an utterance with no frame gives `silence_time` seconds of zeros, :205-210). Where the
+reference walks the sentences one by one at batch 1, this pipeline batches them: texts are sharded over
+ranks by length (no collective, sharding.py), synthesised in batches, and the mels -- still on the
+device -- are re-bucketed by frame count for the vocoder.
+"""
+from __future__ import annotations
+
+import time
+from typing import Dict, List, Sequence
+
+import numpy as np
+
+from .sharding import assign_utterances, make_batches
+from .weights import HOP, SAMPLE_RATE
+
+PAD_MEL_VALUE = -11.0     # models/tts/waveglow.py:52-58 pads mels with this value
+
+
+def synthetic_texts(n: int, seed: int, min_len: int = 40, max_len: int = 120, vocab_size: int = 148) -> List[np.ndarray]:
+    """Seeded random token sequences (ids 1..vocab-1; 0 is the pad token)."""
+    rng = np.random.default_rng(seed)
+    return [rng.integers(1, vocab_size, size=int(rng.integers(min_len, max_len + 1))).astype(np.int64) for _ in range(n)]
+
+
+def tts(token_seqs: Sequence[np.ndarray], tacotron, vocoder, *, max_length=10.0, batch_size: int = 16,
+        vocoder_max_frames: int = 16 * 860, sigma: float = 0.6, silence_time: float = 0.15, rank: int = 0,
+        world_size: int = 1, early_stopping: bool = True, deterministic: bool = False, use_graph: bool = True,
+        pad_token: int = 0, timings: dict | None = None, decoder: str = "torch", seed: int = 0) -> Dict[int, dict]:
+    """Synthesises this rank's share of `token_seqs`; returns {utterance index: {'mel' [T,80] numpy,
+    'audio' [256 T] numpy float32, 'rate', 'time'}}. `vocoder` is a B200WaveGlowRuntime (called with
+    device tensors); `tacotron` a text_to_speech_b200.tacotron2.Tacotron2."""
+    import torch
+    lengths = [len(s) for s in token_seqs]
+    mine = assign_utterances(lengths, world_size)[rank]
+    t0 = time.perf_counter()
+    mels = {}
+    for batch in make_batches(mine, lengths, max_frames=batch_size * max(lengths), max_batch=batch_size):
+        S = batch.T
+        toks = np.full((len(batch.indices), S), pad_token, dtype=np.int64)
+        for j, i in enumerate(batch.indices):
+            toks[j, :lengths[i]] = token_seqs[i]
+        out = tacotron.infer(toks, max_length=max_length, early_stopping=early_stopping, deterministic=deterministic,
+                             use_graph=use_graph, decoder=decoder, seed=seed, return_attention=False)
+        n_frames = out.lengths.cpu().tolist()
+        for j, i in enumerate(batch.indices):
+            mels[i] = out.mel[j, :n_frames[j]]                     # tacotron2.py:183
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    results = {}
+    frames = {i: int(m.shape[0]) for i, m in mels.items()}
+    voiced = [i for i in mine if frames[i] > 0]
+    for i in mine:
+        if frames[i] == 0:                                         # tacotron2.py:205-210
+            results[i] = {"mel": np.zeros((0, 80), np.float32), "audio": np.zeros(int(silence_time * SAMPLE_RATE), np.float32),
+                          "rate": SAMPLE_RATE, "time": silence_time}
+    flens = [frames.get(i, 0) for i in range(len(token_seqs))]
+    for batch in make_batches(voiced, flens, max_frames=vocoder_max_frames):
+        x = torch.full((len(batch.indices), batch.T, 80), PAD_MEL_VALUE, dtype=torch.float32, device=mels[batch.indices[0]].device)
+        for j, i in enumerate(batch.indices):
+            x[j, :frames[i]] = mels[i]
+        wave = vocoder(x, sigma=sigma).cpu().numpy()
+        for j, i in enumerate(batch.indices):
+            audio = wave[j, :frames[i] * HOP].copy()               # models/tts/waveglow.py:82
+            results[i] = {"mel": mels[i].cpu().numpy(), "audio": audio, "rate": SAMPLE_RATE, "time": len(audio) / SAMPLE_RATE}
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    if timings is not None:
+        timings.update(synthesizer_s=t1 - t0, vocoder_s=t2 - t1, utterances=len(mine),
+                       samples=int(sum(len(r["audio"]) for r in results.values())))
+    return results
