@@ -245,3 +245,26 @@ def test_wg_infer_is_cuda_graph_capturable(lib_built):
     torch.cuda.synchronize()
     ref = OracleWaveGlow(hp, w)(mel2, z2, 0.6).numpy()
     assert np.abs(out.cpu().numpy() - ref).max() <= TOL_BF16_ABS
+
+
+def test_maximum_sizes(lib_built):
+    """Edge of the supported shape range: a 64 x 860-frame batch (4 x K2, 1.76 M rows, ~7 GB of workspace) must equal
+    the same utterances run in K2-sized batches bit for bit (32-bit row/element indexing holds), a long single
+    utterance (1 x 6000 frames = 70 s) must equal itself run inside a batch, and a shape whose element count
+    would overflow the kernels' 32-bit indexing is refused before anything is launched."""
+    hp = WaveGlowHParams()
+    w = generate_weights(hp, 1234)
+    eng = _engine(hp, w)
+    mel, z = synthetic_inputs(77, 64, 860, hp)
+    big = _run(eng, mel, z, 0.6)
+    assert big.shape == (64, 860 * 256) and np.isfinite(big).all()
+    for b0 in (0, 48):
+        assert np.array_equal(_run(eng, mel[b0:b0 + 16], z[b0:b0 + 16], 0.6), big[b0:b0 + 16])
+    del big
+    mel, z = synthetic_inputs(78, 2, 6000, hp)
+    pair = _run(eng, mel, z, 0.6)
+    assert np.array_equal(_run(eng, mel[1:2], z[1:2], 0.6)[0], pair[1])
+    with pytest.raises(RuntimeError, match="too large"):
+        eng.workspace_bytes(200, 1000)          # 6.4 M rows x 640 conditioning channels > 2^31 elements
+    with pytest.raises(RuntimeError, match="positive"):
+        eng.workspace_bytes(0, 10)

@@ -130,3 +130,24 @@ def test_global_batch_plan_is_balanced_and_tight():
         assert (max(loads) - min(loads)) / max(loads) < 0.03
         assert sharding.padding_waste([b for r in plan for b in r], lengths) < 0.02
         assert plan == sharding.plan_batches(lengths, ws, max_frames=16 * 860)   # deterministic
+
+
+def test_write_audio_matches_reference_normalisation(tmp_path):
+    """audio_processing.py:51-62 / audio_io.py:346-369: mean removed, peak scaled to 32767, int16 truncation, PCM wav."""
+    from scipy.io import wavfile
+    from text_to_speech_b200.audio_io import normalize_audio, write_audio
+    rng = np.random.default_rng(0)
+    wave = (rng.standard_normal(5000) * 0.3 + 0.05).astype(np.float32)
+    path = write_audio(str(tmp_path / "a.wav"), wave, 22050)
+    rate, pcm = wavfile.read(path)
+    assert rate == 22050 and pcm.dtype == np.int16 and pcm.shape == wave.shape
+    centred = wave - np.mean(wave)
+    want = (centred * (32767 / np.max(np.abs(centred)))).astype(np.int16)
+    assert np.array_equal(pcm, want) and np.abs(pcm).max() == 32767
+    f = normalize_audio(wave, max_val=1.0)
+    assert f.dtype == np.float32 and abs(np.abs(f).max() - 1.0) < 1e-6
+    assert np.array_equal(normalize_audio(np.zeros(10, np.float32)), np.zeros(10, np.int16))    # silent input: no division
+    raw = write_audio(str(tmp_path / "b.wav"), wave, 22050, normalize=False)
+    assert wavfile.read(raw)[1].dtype == np.float32
+    with pytest.raises(ValueError, match="Unsupported file extension"):
+        write_audio(str(tmp_path / "c.mp3"), wave, 22050)
