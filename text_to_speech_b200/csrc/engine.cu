@@ -669,7 +669,10 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
     tc_pair_init();
     tc512_init();
     if (const char* pr = std::getenv("WG_PAIR")) e->use_pair = pr[0] == '1';
-    if (const char* f = std::getenv("WG_DEBUG_FLAGS")) e->dbg_flags = std::atoi(f);
+    // A/B probes that deliberately BREAK the result to isolate a cost (profiles/r01_probes.md): honoured only when
+    // the caller also sets WG_ALLOW_PROBES=1, so a stray variable can never corrupt a production run.
+    if (const char* f = std::getenv("WG_DEBUG_FLAGS"))
+      if (const char* ok = std::getenv("WG_ALLOW_PROBES")) e->dbg_flags = ok[0] == '1' ? std::atoi(f) : 0;
     if (const char* t = std::getenv("WG_LAYER_TIMING")) {
       if (t[0] == '1') {
         CK(cudaMalloc(&e->timing, 128 * sizeof(unsigned long long)));

@@ -759,7 +759,7 @@ void enqueue_frames(wg_taco_engine* e, int B, int S, int frames, cudaStream_t st
   const size_t xa_gs = static_cast<size_t>(2) * d.KA * kRows, xd_gs = static_cast<size_t>(2) * d.KD * kRows;
   const size_t xo_gs = static_cast<size_t>(d.KO) * kRows;
   const bool pdl = e->use_pdl;
-  const int pdl_instr = std::getenv("WG_TACO_PDL_INSTR") ? std::atoi(std::getenv("WG_TACO_PDL_INSTR")) : (pdl ? 1 : 0);
+  const int pdl_instr = pdl ? 1 : 0;
   auto dense = [&](const float* Wp, const float* bp, const float* X, size_t x_gs, int K, int n_cols, int step) {
     DenseArgs a{};
     a.io = e->io; a.Wp = Wp; a.bp = bp; a.X = X; a.x_gs = x_gs; a.K = K; a.n_cols = n_cols; a.step = step;
