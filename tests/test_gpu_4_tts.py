@@ -1,6 +1,6 @@
 """GPU: the tts() pipeline (Tacotron2 producer -> B200 WaveGlow runtime) and the CUDA-graph decode loop.
-The producer is torch library code with unpinned parity (see text_to_speech_b200/tacotron2.py); what is
-checked here is that the pipeline delivers exactly what the vocoder produces for the producer's mels."""
+Parity of the decoder kernels: against the reference-source fixture (last test) and the torch restatement; the
+encoder/postnet are torch library code with unpinned parity (see text_to_speech_b200/tacotron2.py)."""
 import os
 
 import numpy as np
@@ -206,3 +206,25 @@ def test_b200_decoder_bf16_lstm_weights_equal_fp32_math_on_rounded_weights(model
     dev = float((got.mel - full.mel).abs().max())
     print(f"\nbf16-stored LSTM weights vs fp32 weights: max |mel diff| over {T} frames = {dev:.3e}")
     assert dev <= 5e-2
+
+
+def test_b200_decoder_against_reference_source_fixture(lib_built):
+    """csrc/taco.cu against what the reference's OWN Tacotron2Decoder.infer source produced (fixture generated over
+    the Keras shim, oracle/gen_golden_taco.py): three utterances the reference decoded one by one, run here as one
+    padded batch."""
+    from test_oracle_taco import load_taco_golden, padded_batch
+    from text_to_speech_b200.tacotron2 import Tacotron2
+    hp, w, mems, frames, f = load_taco_golden("taco_decoder_nvidia")
+    model = Tacotron2(hp, w, device="cuda")
+    memory, mask = padded_batch(mems, torch.float32)
+    out, stops, attn, lengths = model.decode_b200(memory.cuda(), mask.cuda(), frames, early_stopping=False, deterministic=True)
+    assert lengths.tolist() == [frames] * len(mems)
+    worst = 0.0
+    for i, m in enumerate(mems):
+        e_out = np.abs(out[i].cpu().numpy() - f[f"u{i}_decoder_output_fp64"]).max()
+        e_stop = np.abs(stops[i].cpu().numpy() - f[f"u{i}_stop_tokens_fp64"]).max()
+        e_att = np.abs(attn[i, :, :len(m)].cpu().numpy() - f[f"u{i}_attention_weights_fp64"]).max()
+        worst = max(worst, e_out, e_stop, e_att)
+        assert float(attn[i, :, len(m):].abs().max()) == 0.0 if len(m) < attn.shape[2] else True
+    print(f"\nCUDA decoder vs reference-source fixture (float64), {frames} frames: max abs error {worst:.2e}")
+    assert worst <= 1e-5

@@ -1,6 +1,6 @@
-"""CPU: internal consistency of the Tacotron2 mel producer (the CALLER of the path; torch library ops,
-parity with the reference UNPINNED -- see the header of text_to_speech_b200/tacotron2.py) and of the
-tts() pipeline's host logic."""
+"""CPU: internal consistency of the Tacotron2 mel producer (the CALLER of the path; the decoder is pinned to the
+reference source in tests/test_oracle_taco.py, encoder/postnet are not -- see the header of
+text_to_speech_b200/tacotron2.py) and of the tts() pipeline's host logic."""
 import numpy as np
 import pytest
 import torch

@@ -1,14 +1,18 @@
 """The CALLER of the WaveGlow path: a Tacotron2 mel producer for the end-to-end `tts()` workload
 (BASELINE.json configs[3]).
 
-STATUS -- read before citing a number from this file: this is NOT one of the B200 kernels and NOT
-part of the drop-in boundary. It is a restatement of the reference's Tacotron2 inference
-(`architectures/tacotron2_arch.py:609-749, 866-925`; attention `architectures/layers/
-location_sensitive_attention.py:96-186`) in plain torch ops (cuDNN/cuBLAS underneath), written so
-that the vocoder stage can be measured in the pipeline it lives in. The reference model is built
-with the functional Keras API plus custom layers and cannot be executed in this environment (no
-keras), so this file's parity is UNPINNED: tests cover its internal consistency (float64 twin,
-batch/padding invariance, stop/length logic), not agreement with the reference's numbers.
+STATUS -- read before citing a number from this file: this is NOT part of the vocoder's drop-in
+boundary. It is a restatement of the reference's Tacotron2 inference (`architectures/tacotron2_arch.py
+:609-749, 866-925`; attention `architectures/layers/location_sensitive_attention.py:96-186`) in plain torch
+ops (cuDNN/cuBLAS underneath), written so that the vocoder stage can be measured in the pipeline it lives
+in, plus the host side of the CUDA decoder loop (`decode_b200` -> csrc/taco.cu). Parity:
+  * DECODER (prenet, attention LSTM, location sensitive attention, decoder LSTM, projection, stop gate, the
+    finished/lengths bookkeeping): pinned to the reference's own source, executed unmodified over the Keras
+    shim (oracle/run_reference_taco.py) -- `decode` reproduces it to 2e-16 in float64 (tests/test_oracle_taco.py,
+    fixtures tests/golden/taco_decoder_*.npz);
+  * ENCODER and POSTNET: the reference builds them with its generic `simple_cnn` factory on the functional
+    Keras API, which the shim does not cover -- UNPINNED; tests cover internal consistency only (float64
+    twin, padding invariance).
 
 What is restated (inference only, single speaker):
   encoder   embedding(148, 512, pad 0) -> 3 x [conv k5 'same' -> batch-norm -> relu] -> BiLSTM(256+256),
