@@ -8,7 +8,7 @@ ops (cuDNN/cuBLAS underneath), written so that the vocoder stage can be measured
 in, plus the host side of the CUDA decoder loop (`decode_b200` -> csrc/taco.cu). Parity:
   * DECODER (prenet, attention LSTM, location sensitive attention, decoder LSTM, projection, stop gate, the
     finished/lengths bookkeeping): pinned to the reference's own source, executed unmodified over the Keras
-    shim (oracle/run_reference_taco.py) -- `decode` reproduces it to 2e-16 in float64 (tests/test_oracle_taco.py,
+    shim (run_reference_taco in the test oracle) -- `decode` reproduces it to 2e-16 in float64 (tests/test_oracle_taco.py,
     fixtures tests/golden/taco_decoder_*.npz);
   * ENCODER and POSTNET: the reference builds them with its generic `simple_cnn` factory on the functional
     Keras API, which the shim does not cover -- UNPINNED; tests cover internal consistency only (float64
