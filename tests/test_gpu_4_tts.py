@@ -102,7 +102,7 @@ def _ragged_tokens(n, seed, lo, hi):
     return toks
 
 
-@pytest.mark.parametrize("B,lo,hi,T", [(3, 12, 20, 70), (17, 5, 9, 23), (1, 1, 1, 9), (16, 40, 40, 64)])
+@pytest.mark.parametrize("B,lo,hi,T", [(3, 12, 20, 70), (17, 5, 9, 23), (1, 1, 1, 9), (16, 40, 40, 64), (33, 150, 300, 10)])
 def test_b200_decoder_matches_torch_restatement(models, B, lo, hi, T):
     taco = models[0]
     toks = _ragged_tokens(B, 100 + B, lo, hi)
