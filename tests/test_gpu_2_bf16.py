@@ -268,3 +268,39 @@ def test_maximum_sizes(lib_built):
         eng.workspace_bytes(200, 1000)          # 6.4 M rows x 640 conditioning channels > 2^31 elements
     with pytest.raises(RuntimeError, match="positive"):
         eng.workspace_bytes(0, 10)
+
+
+def test_concurrent_wg_infer_on_two_streams(lib_built):
+    """include/wg_b200.h: a handle is immutable after wg_create, so concurrent wg_infer calls on different streams with
+    different workspaces are safe. Two host threads drive the same handle through the raw C ABI; each result must be
+    bit-identical to the serial run."""
+    import threading
+    hp = WaveGlowHParams()
+    w = generate_weights(hp, 1234)
+    eng = _engine(hp, w)
+    lib, h = eng._lib, eng._h
+    jobs = []
+    for seed, (B, T) in enumerate([(3, 120), (2, 333)]):
+        mel, z = synthetic_inputs(500 + seed, B, T, hp)
+        serial = _run(eng, mel, z, 0.6)
+        ws = torch.empty(eng.workspace_bytes(B, T) + 1024, dtype=torch.uint8, device="cuda")
+        ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
+        jobs.append(dict(B=B, T=T, serial=serial, mel=torch.from_numpy(mel).cuda(), z=torch.from_numpy(z).cuda(),
+                         out=torch.zeros(B, T * 256, device="cuda"), ws=ws, ws_ptr=ws_ptr,
+                         ws_bytes=eng.workspace_bytes(B, T), stream=torch.cuda.Stream(), rc=[]))
+    torch.cuda.synchronize()
+
+    def worker(j):
+        for _ in range(5):
+            j["rc"].append(lib.wg_infer(h, j["mel"].data_ptr(), j["z"].data_ptr(), 0.6, 0, j["B"], j["T"],
+                                        j["out"].data_ptr(), j["ws_ptr"], j["ws_bytes"], j["stream"].cuda_stream))
+
+    threads = [threading.Thread(target=worker, args=(j,)) for j in jobs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    torch.cuda.synchronize()
+    for j in jobs:
+        assert j["rc"] == [0] * 5
+        assert np.array_equal(j["out"].cpu().numpy(), j["serial"])
