@@ -151,3 +151,40 @@ def test_write_audio_matches_reference_normalisation(tmp_path):
     assert wavfile.read(raw)[1].dtype == np.float32
     with pytest.raises(ValueError, match="Unsupported file extension"):
         write_audio(str(tmp_path / "c.mp3"), wave, 22050)
+
+
+REF_RUNTIME = "/root/reference/utils/keras/runtimes/runtime.py"
+
+
+@pytest.mark.skipif(not __import__("os").path.isfile(REF_RUNTIME), reason="reference tree not mounted")
+def test_runtime_mirror_is_interchangeable_with_the_reference_abc():
+    """Loads the reference's REAL Runtime ABC (a stand-alone file) and checks (a) the mirror exposes the same public
+    surface with the same signatures and (b) B200WaveGlowRuntime's methods satisfy the real ABC, i.e. the class
+    INTEGRATION.md registers under `_runtimes['b200']` can inherit from the reference's base unchanged."""
+    import importlib.util
+    import inspect
+    from text_to_speech_b200.runtime import B200WaveGlowRuntime
+    spec = importlib.util.spec_from_file_location("_ref_runtime", REF_RUNTIME)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    Ref = mod.Runtime
+    public = [n for n in vars(Ref) if not n.startswith("_") or n in ("__init__", "__call__", "__repr__")]
+    for name in public:
+        assert hasattr(Runtime, name), f"mirror lacks {name}"
+        if callable(getattr(Ref, name)):
+            assert str(inspect.signature(getattr(Ref, name))) == str(inspect.signature(getattr(Runtime, name))), name
+    assert Ref.__abstractmethods__ == Runtime.__abstractmethods__ == frozenset({"__call__", "load_engine"})
+    for name in ("build_from", "from_tensorflow", "from_torch", "from_onnx"):
+        assert isinstance(inspect.getattr_static(Ref, name), classmethod) and isinstance(inspect.getattr_static(Runtime, name), classmethod)
+
+    class OnRealBase(Ref):                       # what a maintainer would write inside the reference tree
+        __call__ = B200WaveGlowRuntime.__call__
+        load_engine = staticmethod(B200WaveGlowRuntime.load_engine)
+
+    fake_engine = object()
+    rt = OnRealBase("weights.npz", engine=fake_engine)
+    assert rt.engine is fake_engine and rt.path == "weights.npz" and repr(rt) == "<OnRealBase path=weights.npz>"
+    with pytest.raises(NotImplementedError, match="cannot be initialized from `ONNX`"):
+        OnRealBase.from_onnx("m.onnx", "weights.npz")
+    with pytest.raises(NotImplementedError, match="cannot be initialized from `ONNX`"):
+        B200WaveGlowRuntime.from_onnx("m.onnx", "weights.npz")

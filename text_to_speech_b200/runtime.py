@@ -48,6 +48,35 @@ class Runtime(metaclass=ABCMeta):
     def load_engine(path, **kwargs):
         """ Loads the custom runtime engine """
 
+    # Optional builders of the reference ABC (runtime.py:44-81). A WaveGlow engine is built from a weight file, not
+    # traced from a framework function, so they refuse with the reference's own messages.
+    @classmethod
+    def build_from(cls, function, path, overwrite=False, **kwargs):
+        import os
+        if os.path.exists(path) and not overwrite:
+            return cls(path, **kwargs)
+        if isinstance(function, str):
+            if function.endswith('.onnx'):
+                return cls.from_onnx(function, path, **kwargs)
+            elif function.endswith('.pth'):
+                return cls.from_torch(function, path, **kwargs)
+            elif os.path.isdir(path):
+                return cls.from_tensorflow(function, path, **kwargs)
+            raise NotImplementedError('Invalid path : {}'.format(path))
+        raise NotImplementedError()
+
+    @classmethod
+    def from_tensorflow(cls, function, path, **kwargs):
+        raise NotImplementedError('{} cannot be initialized from `tf.function`'.format(cls.__name__))
+
+    @classmethod
+    def from_torch(cls, function, path, **kwargs):
+        raise NotImplementedError('{} cannot be initialized from `torch.compile`'.format(cls.__name__))
+
+    @classmethod
+    def from_onnx(cls, onnx_path, path, **kwargs):
+        raise NotImplementedError('{} cannot be initialized from `ONNX`'.format(cls.__name__))
+
 
 class B200WaveGlowRuntime(Runtime):
     """WaveGlow vocoder runtime on one B200.
