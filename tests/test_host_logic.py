@@ -188,3 +188,45 @@ def test_runtime_mirror_is_interchangeable_with_the_reference_abc():
         OnRealBase.from_onnx("m.onnx", "weights.npz")
     with pytest.raises(NotImplementedError, match="cannot be initialized from `ONNX`"):
         B200WaveGlowRuntime.from_onnx("m.onnx", "weights.npz")
+
+
+def _ref_wrapper_available():
+    from oracle.run_reference_wrapper import wrapper_reference_available
+    return wrapper_reference_available()
+
+
+@pytest.mark.skipif(not _ref_wrapper_available(), reason="reference tree not mounted")
+@pytest.mark.parametrize("T", [37, 200, 333])
+@pytest.mark.parametrize("kw", [dict(), dict(win_len=128), dict(win_len=64, hop_len=-16), dict(win_len=128, batch=True),
+                                dict(win_len=0.5), dict(win_len=3.0, use_slice=True), dict(win_len=512),
+                                dict(win_len=512, force_pad=True), dict(win_len=100, hop_len=0.5, max_win_len=80),
+                                dict(win_len=96, hop_len=-32, batch=True)])
+def test_wrapper_matches_the_reference_wrapper_source(T, kw):
+    """models/tts/waveglow.py executed unmodified (oracle/run_reference_wrapper.py) against our wrapper, with the same
+    stand-in vocoder behind both: every windowing / padding / stitching branch must give the same samples."""
+    from oracle.run_reference_wrapper import reference_get_steps, reference_wrapper_infer
+    rng = np.random.default_rng(T)
+    mel = rng.normal(size=(1, T, 80)).astype(np.float32)
+    try:
+        want = reference_wrapper_infer(_FakeRuntime(), mel, **kw)
+    except Exception as e:      # the reference's own quirks (float slice bounds with use_slice=True) are part of the contract
+        with pytest.raises(type(e)):
+            _wrapper_with_fake()(mel, **kw)
+        return
+    got = np.asarray(_wrapper_with_fake()(mel, **kw))
+    assert got.shape == want.shape and np.array_equal(got, want)
+    assert np.array_equal(wrapper_infer(_FakeRuntime(), mel, **kw), want)          # and the oracle restatement
+    for args in ((T, 64, 48), (T, 128, 64), (1000, 256, 192)):
+        if args[0] > args[1]:
+            assert list(reference_get_steps(*args)) == list(_get_steps(*args)) == list(get_steps(*args))
+
+
+@pytest.mark.skipif(not _ref_wrapper_available(), reason="reference tree not mounted")
+def test_wrapper_2d_input_and_batch_branch_match_the_reference_source():
+    from oracle.run_reference_wrapper import reference_wrapper_infer
+    rng = np.random.default_rng(2)
+    mel2 = rng.normal(size=(50, 80)).astype(np.float32)
+    assert np.array_equal(np.asarray(_wrapper_with_fake()(mel2)), reference_wrapper_infer(_FakeRuntime(), mel2))
+    melb = rng.normal(size=(3, 300, 80)).astype(np.float32)
+    assert np.array_equal(np.asarray(_wrapper_with_fake()(melb, win_len=128)),
+                          reference_wrapper_infer(_FakeRuntime(), melb, win_len=128))
