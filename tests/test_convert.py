@@ -46,3 +46,42 @@ def test_torch_layout_tensors_compute_the_same_function():
     assert torch.allclose(y_t.permute(0, 2, 1), y_k, atol=1e-5)
     out = OracleWaveGlow(hp, w2)(mel, z, 0.6).numpy()
     assert np.isfinite(out).all() and out.shape == (1, 5 * 256)
+
+
+REF_CONVERTER = "/root/reference/models/weights_converter.py"
+
+
+@pytest.mark.skipif(not __import__("os").path.isfile(REF_CONVERTER), reason="reference tree not mounted")
+def test_layout_rule_is_the_reference_transpose_weights():
+    """The reference converts torch tensors to Keras layouts with `transpose_weights` (models/weights_converter.py:252-271,
+    a stand-alone numpy function): every conv kernel `from_nvidia_state_dict` emits must be exactly what that REAL
+    function returns for the NVIDIA tensor (conditioning convs: for the per-layer slice)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ref_weights_converter", REF_CONVERTER)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    hp = WaveGlowHParams(n_flows=4, n_early_every=2, n_layers=3, n_channels=16)
+    w = generate_weights(hp, 9, bias_std=0.1)
+    for fused in (False, True):
+        sd = to_nvidia_state_dict(hp, w, fused_cond=fused)
+        _, got = from_nvidia_state_dict(sd, n_early_every=2, n_early_size=2)
+        checked = 0
+        pairs = [("upsample.weight", "upsample/kernel")]
+        for k in range(hp.n_flows):
+            pairs += [(f"WN.{k}.start.weight", f"block-{k}/start_conv/kernel"), (f"WN.{k}.end.weight", f"block-{k}/end_conv/kernel")]
+            for i in range(hp.n_layers):
+                pairs += [(f"WN.{k}.in_layers.{i}.weight", f"block-{k}/in_conv-{i}/kernel"),
+                          (f"WN.{k}.res_skip_layers.{i}.weight", f"block-{k}/res_skip_conv-{i}/kernel")]
+                if not fused:
+                    pairs.append((f"WN.{k}.cond_layers.{i}.weight", f"block-{k}/cond_layer-{i}/kernel"))
+        for src, dst in pairs:
+            if src in sd and dst in got:
+                assert np.array_equal(ref.transpose_weights(np.asarray(sd[src])), got[dst]), (src, dst)
+                checked += 1
+        assert checked >= (2 + 2 * hp.n_layers) * hp.n_flows
+        if fused:       # one 640 -> 2C*n_layers conv per flow, sliced per layer after the reference's transpose
+            C2 = 2 * hp.n_channels
+            for k in range(hp.n_flows):
+                full = ref.transpose_weights(np.asarray(sd[f"WN.{k}.cond_layer.weight"]))
+                for i in range(hp.n_layers):
+                    assert np.array_equal(full[..., i * C2:(i + 1) * C2], got[f"block-{k}/cond_layer-{i}/kernel"])
