@@ -230,3 +230,52 @@ def test_wrapper_2d_input_and_batch_branch_match_the_reference_source():
     melb = rng.normal(size=(3, 300, 80)).astype(np.float32)
     assert np.array_equal(np.asarray(_wrapper_with_fake()(melb, win_len=128)),
                           reference_wrapper_infer(_FakeRuntime(), melb, win_len=128))
+
+
+REF_AUDIO_PROC = "/root/reference/utils/audio/audio_processing.py"
+
+
+@pytest.mark.skipif(not __import__("os").path.isfile(REF_AUDIO_PROC), reason="reference tree not mounted")
+def test_normalize_audio_equals_the_reference_function():
+    """utils/audio/audio_processing.py::normalize_audio executed from the reference file (its unrelated imports --
+    librosa.util, loggers.timer, the dispatch wrapper -- replaced by inert stand-ins) against audio_io.normalize_audio."""
+    import importlib.util
+    import sys
+    import types
+    from text_to_speech_b200.audio_io import normalize_audio
+    saved = {k: sys.modules.get(k) for k in ("librosa", "librosa.util", "loggers", "_ref_audio", "_ref_audio.wrappers")}
+    try:
+        librosa = types.ModuleType("librosa")
+        librosa.util = types.ModuleType("librosa.util")
+        loggers = types.ModuleType("loggers")
+        loggers.timer = lambda fn=None, **kw: fn if callable(fn) else (lambda f: f)
+        pkg = types.ModuleType("_ref_audio")
+        pkg.__path__ = []
+        wrappers = types.ModuleType("_ref_audio.wrappers")
+
+        def dispatch_wrapper(*a, **k):
+            def deco(fn):
+                fn.dispatch = lambda *aa, **kk: (aa[0] if aa and callable(aa[0]) else (lambda f: f))
+                return fn
+            return deco
+        wrappers.dispatch_wrapper = dispatch_wrapper
+        sub = types.ModuleType("_ref_audio.audio")
+        sub.__path__ = []
+        sys.modules.update({"librosa": librosa, "librosa.util": librosa.util, "loggers": loggers, "_ref_audio": pkg,
+                            "_ref_audio.wrappers": wrappers, "_ref_audio.audio": sub})
+        spec = importlib.util.spec_from_file_location("_ref_audio.audio.audio_processing", REF_AUDIO_PROC)
+        ref = importlib.util.module_from_spec(spec)
+        sys.modules["_ref_audio.audio.audio_processing"] = ref
+        spec.loader.exec_module(ref)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    rng = np.random.default_rng(4)
+    for wave in (rng.standard_normal(4000).astype(np.float32) * 0.2 + 0.03, np.zeros(100, np.float32),
+                 (rng.standard_normal(777) * 3).astype(np.float32), rng.standard_normal(50)):
+        for kw in (dict(), dict(max_val=1.0), dict(max_val=20000)):
+            a, b = normalize_audio(wave, **kw), ref.normalize_audio(wave, **kw)
+            assert a.dtype == b.dtype and np.array_equal(a, b)
