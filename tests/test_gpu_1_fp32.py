@@ -103,3 +103,44 @@ def test_host_entry_point_and_errors(lib_built):
         import ctypes
         rc = eng._lib.wg_infer(eng._h, 1, 1, 1.0, 0, 1, 1, 1, 0, 0, 0)
         eng._check(rc, "wg_infer")
+
+
+def test_every_argument_error_is_reported_before_any_launch(lib_built):
+    """The wg_status / message of each refusal (wg_b200.h), through the raw C ABI; none of them may launch a kernel."""
+    from text_to_speech_b200.engine import WaveGlowEngine, WaveGlowError
+    hp = WaveGlowHParams(n_channels=32)
+    w = generate_weights(hp, 35)
+    eng = _engine(hp, w)
+    lib, h = eng._lib, eng._h
+    mel, z = synthetic_inputs(8, 1, 4, hp)
+    mel_d, z_d = torch.from_numpy(mel).cuda(), torch.from_numpy(z).cuda()
+    out = torch.zeros(1, 4 * 256, device="cuda")
+    need = eng.workspace_bytes(1, 4)
+    ws = torch.empty(need + 2048, dtype=torch.uint8, device="cuda")
+    base = (ws.data_ptr() + 1023) // 1024 * 1024
+    _run(eng, mel, z, 0.6)
+    launches = eng.last_launch_count
+
+    def call(mel_p=mel_d.data_ptr(), z_p=z_d.data_ptr(), det=0, B=1, T=4, out_p=out.data_ptr(), ws_p=base, ws_n=need):
+        rc = lib.wg_infer(h, mel_p, z_p, 0.6, det, B, T, out_p, ws_p, ws_n, 0)
+        return rc, lib.wg_last_error(h).decode()
+
+    assert call()[0] == 0
+    for kwargs, code, text in [(dict(mel_p=0), -1, "NULL"), (dict(out_p=0), -1, "NULL"), (dict(z_p=0), -1, "z must be given"),
+                               (dict(B=0), -1, "positive"), (dict(T=-3), -1, "positive"),
+                               (dict(ws_n=need - 1), -4, "too small"), (dict(ws_p=base + 8), -4, "aligned"),
+                               (dict(B=4096, T=4096), -1, "too large")]:
+        rc, msg = call(**kwargs)
+        assert rc == code and text in msg, (kwargs, rc, msg)
+    assert call(z_p=0, det=1)[0] == 0                        # z may be NULL when deterministic
+    torch.cuda.synchronize()
+    assert eng.last_launch_count == launches                 # the failed calls launched nothing; the good ones the same count
+    # create-time refusals
+    bad = dict(w)
+    bad["invertible_conv-0/conv/kernel"] = np.zeros_like(w["invertible_conv-0/conv/kernel"])
+    with pytest.raises(WaveGlowError, match="singular"):
+        WaveGlowEngine(hp, bad, mode="fp32", device=0)
+    with pytest.raises(WaveGlowError, match="n_channels 256 and 512"):
+        WaveGlowEngine(hp, w, mode="bf16", device=0)
+    with pytest.raises(WaveGlowError, match="out of range"):
+        WaveGlowEngine(hp, w, mode="fp32", device=99)
