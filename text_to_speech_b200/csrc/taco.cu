@@ -2,11 +2,12 @@
 //
 // One decoder frame (reference architectures/tacotron2_arch.py:422-486, :640-691) is EIGHT kernels,
 // captured `graph_chunk` frames at a time into a CUDA graph:
-//   dense16<32,LSTM>    attention LSTM: gates = [prenet, context, h_a] . W (K = 1792) + LSTMCell update
+//   lstm_mma_kernel     attention LSTM: gates = [prenet, context, h_a] . W (K = 1792) + LSTMCell update
+//                       (split-bf16 mma.sync tensor-core path; dense16<32,LSTM> is the fp32 FFMA alternative)
 //   dense16<8,QUERY>    query projection of the new h_a (1024 -> 128)
 //   energy_kernel       location sensitive attention, 16 text positions per CTA: location conv + dense, energies
 //   context_kernel      masked softmax, attention state update, context (4 CTAs per batch row)
-//   dense16<32,LSTM>    decoder LSTM: gates = [h_a, context, h_d] . W (K = 2560)
+//   lstm_mma_kernel     decoder LSTM: gates = [h_a, context, h_d] . W (K = 2560)
 //   dense16<8,FRAME>    [h_d, context] -> frame + stop probability, finished/length bookkeeping
 //   dense16<8,PRENET>x2 prenet (dense-relu-dropout) of the new frame for the next step
 // The dense kernels are weight-streaming: 18 M fp32 parameters (72 MB) are read once per frame through a
@@ -276,6 +277,135 @@ __global__ void __launch_bounds__(kDenseThreads) dense16_kernel(DenseArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// lstm_mma_kernel: the LSTM gate GEMM on the (legacy-interface) tensor cores. The batch group is exactly one
+// mma.sync M = 16 tile, so tcgen05 (M >= 64) would idle three quarters of the array; m16n8k16 BF16 fits.
+// fp32 accuracy is kept by SPLITTING both operands into bf16 hi + lo (x = hi + lo to 2^-17) and issuing three
+// products per tile (hi.hi + hi.lo + lo.hi, fp32 accumulate; the dropped lo.lo term is 2^-16 relative): the
+// weights are pre-split and pre-swizzled into mma B-fragment order at create time (same bytes as fp32), the
+// state is split on the fly. Each of the 16 warps owns 16 k-rows of a 256-row chunk and streams exactly those
+// through a 3-stage cp.async ring (no block barrier in the loop); partial tiles meet in shared memory.
+constexpr int kMmaChunk = 256;
+constexpr int kMmaStages = 3;
+constexpr int kXPitch = 20;     // floats per k-row of the staged state: 16 rows + 4 pad -> conflict-free A-fragment loads
+constexpr size_t kMmaSmem = kMmaStages * (16 * 2048 + kMmaChunk * kXPitch * sizeof(float)) + sizeof(float) * (16 * kRows * 32 + 32 * kRows);
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void split_bf16(float x0, float x1, unsigned& hi, unsigned& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);      // .x (low half) = x0: the smaller k index
+  const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - __bfloat162float(h.x), x1 - __bfloat162float(h.y));
+  hi = *reinterpret_cast<const unsigned*>(&h);
+  lo = *reinterpret_cast<const unsigned*>(&l);
+}
+
+__global__ void __launch_bounds__(kDenseThreads) lstm_mma_kernel(DenseArgs a) {
+  if (a.pdl) pdl_trigger();
+  extern __shared__ __align__(16) unsigned char smraw[];
+  unsigned char* ws = smraw;                                                      // stages x 16 warps x 2 KB
+  float* xs = reinterpret_cast<float*>(ws + kMmaStages * 16 * 2048);              // stages x 256 x 20
+  float* red = xs + kMmaStages * kMmaChunk * kXPitch;                             // 16 x 16 x 32
+  float* zs = red + 16 * kRows * 32;                                              // 32 x 16
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tg = lane & 3;
+  const int cta = blockIdx.x, grp = blockIdx.y;
+  const int n_chunks = (a.K + kMmaChunk - 1) / kMmaChunk, n_kb = n_chunks * 16;
+  const unsigned char* Wg = reinterpret_cast<const unsigned char*>(a.Wp) + static_cast<size_t>(cta) * n_kb * 2048;
+  const float* Xg = a.X + grp * a.x_gs;
+
+  auto issue_w = [&](int c) {
+    if (c < n_chunks) {
+      const unsigned char* src = Wg + static_cast<size_t>(c * 16 + warp) * 2048;
+      unsigned char* dst = ws + ((c % kMmaStages) * 16 + warp) * 2048;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) cp_async16(dst + (lane + 32 * u) * 16, src + (lane + 32 * u) * 16, 16);
+    }
+  };
+  auto issue_x = [&](int c) {
+    if (c < n_chunks) {
+      const int k0 = c * kMmaChunk + warp * 16;
+      float* dst = xs + ((c % kMmaStages) * kMmaChunk + warp * 16) * kXPitch;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int unit = lane + 32 * u, row = unit >> 2, part = unit & 3;
+        const bool ok = k0 + row < a.K;
+        cp_async16(dst + row * kXPitch + part * 4, ok ? Xg + static_cast<size_t>(k0 + row) * kRows + part * 4 : Xg, ok ? 16 : 0);
+      }
+    }
+    cp_async_commit();
+  };
+
+#pragma unroll
+  for (int c = 0; c < kMmaStages - 1; ++c) issue_w(c);
+  if (a.pdl) pdl_wait();
+  const TacoIo& io = *a.io;
+  if (io.t_base + a.step >= io.max_len) {
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    return;
+  }
+#pragma unroll
+  for (int c = 0; c < kMmaStages - 1; ++c) issue_x(c);
+
+  float acc[4][4];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[nt][i] = 0.0f;
+  for (int c = 0; c < n_chunks; ++c) {
+    cp_async_wait<kMmaStages - 2>();
+    __syncwarp();
+    const float* xw = xs + ((c % kMmaStages) * kMmaChunk + warp * 16) * kXPitch;
+    const uint2* wf = reinterpret_cast<const uint2*>(ws + ((c % kMmaStages) * 16 + warp) * 2048);
+    unsigned ahi[4], alo[4];
+    // A fragment (16 batch rows x 16 k): a0 = (row g, k 2tg..), a1 = (row g+8, same k), a2 / a3 = k + 8
+    split_bf16(xw[(2 * tg) * kXPitch + g], xw[(2 * tg + 1) * kXPitch + g], ahi[0], alo[0]);
+    split_bf16(xw[(2 * tg) * kXPitch + g + 8], xw[(2 * tg + 1) * kXPitch + g + 8], ahi[1], alo[1]);
+    split_bf16(xw[(2 * tg + 8) * kXPitch + g], xw[(2 * tg + 9) * kXPitch + g], ahi[2], alo[2]);
+    split_bf16(xw[(2 * tg + 8) * kXPitch + g + 8], xw[(2 * tg + 9) * kXPitch + g + 8], ahi[3], alo[3]);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const uint2 bh = wf[nt * 32 + lane], bl = wf[(4 + nt) * 32 + lane];
+      mma_bf16_16816(acc[nt], ahi, bh.x, bh.y);
+      mma_bf16_16816(acc[nt], ahi, bl.x, bl.y);
+      mma_bf16_16816(acc[nt], alo, bh.x, bh.y);
+    }
+    __syncwarp();
+    issue_w(c + kMmaStages - 1);
+    issue_x(c + kMmaStages - 1);
+  }
+  // C fragment: c0,c1 = (row g, cols 2tg, 2tg+1), c2,c3 = (row g+8, same cols) of n-tile nt (= LSTM gate nt)
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    float* r = red + (warp * kRows + g) * 32 + nt * 8 + 2 * tg;
+    *reinterpret_cast<float2*>(r) = make_float2(acc[nt][0], acc[nt][1]);
+    *reinterpret_cast<float2*>(r + 8 * 32) = make_float2(acc[nt][2], acc[nt][3]);
+  }
+  __syncthreads();
+  {
+    const int col = tid & 31, row = tid >> 5;
+    float z = a.bp[cta * 32 + col];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) z += red[(q * kRows + row) * 32 + col];
+    zs[col * kRows + row] = z;
+  }
+  __syncthreads();
+  if (tid < kUnitsPerCta * kRows) {
+    const int du = tid >> 4, b = tid & 15;
+    const float zi = zs[du * kRows + b], zf = zs[(8 + du) * kRows + b], zc = zs[(16 + du) * kRows + b], zo = zs[(24 + du) * kRows + b];
+    const int u = cta * kUnitsPerCta + du;
+    float* cp = a.c + grp * a.c_gs + u * kRows + b;
+    const float c_new = sigmoidf_(zf) * *cp + sigmoidf_(zi) * tanhf(zc);
+    const float h = sigmoidf_(zo) * tanhf(c_new);
+    *cp = c_new;
+    a.o1[grp * a.o1_gs + u * kRows + b] = h;
+    if (a.o2) a.o2[grp * a.o2_gs + u * kRows + b] = h;
+    if (a.o3) a.o3[grp * a.o3_gs + u * kRows + b] = h;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Location sensitive attention (location_sensitive_attention.py:104-186) in two kernels so that one batch
 // row is spread over several SMs: energy_kernel computes the raw energies of 16 text positions per CTA (one
 // warp per position: location conv, location dense with float4 weights per lane, tanh, dot with v);
@@ -484,6 +614,7 @@ struct wg_taco_engine {
   int device = 0;
   int graph_chunk = 32;
   bool lstm_bf16 = false;  // LSTM weights stored as bf16 (wg_taco_config.lstm_weight_dtype == 1)
+  int lstm_mode = 0;       // wg_taco_config.lstm_weight_dtype
   bool use_pdl = false;    // WG_TACO_PDL=1: programmatic dependent launch along the frame chain (measured 6 % SLOWER
                            // than plain stream order on the 8-kernel frame, so it is off by default; kept as an A/B switch)
   // weights
@@ -575,7 +706,7 @@ const wg_tensor& find(const wg_tensor* ts, int n, const char* name, std::initial
 }
 
 // [K_in, 4U] kernel + [U, 4U] recurrent kernel -> per-CTA packed [U/8][K][32], bias -> [U/8][32]
-void pack_lstm(const wg_tensor* ts, int n, const std::string& prefix, int n_in, int U, bool bf16, float** Wp, float** bp) {
+void pack_lstm(const wg_tensor* ts, int n, const std::string& prefix, int n_in, int U, int mode, float** Wp, float** bp) {
   const wg_tensor& k = find(ts, n, (prefix + "/kernel").c_str(), {n_in, 4 * U});
   const wg_tensor& r = find(ts, n, (prefix + "/recurrent_kernel").c_str(), {U, 4 * U});
   const wg_tensor& b = find(ts, n, (prefix + "/bias").c_str(), {4 * U});
@@ -592,7 +723,39 @@ void pack_lstm(const wg_tensor* ts, int n, const std::string& prefix, int n_in, 
           w[(static_cast<size_t>(c) * K + kk) * 32 + j] = val;
         }
       }
-  if (bf16) {
+  if (mode == 2) {
+    // split-bf16 mma B fragments: [cta][k16 block][hi | lo][n-tile = gate][lane][4 bf16], K padded to 256 with zeros
+    auto to_bf16 = [](float x) {
+      uint32_t u;
+      std::memcpy(&u, &x, 4);
+      return static_cast<uint16_t>((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+    };
+    auto from_bf16 = [](uint16_t h) {
+      uint32_t u = static_cast<uint32_t>(h) << 16;
+      float x;
+      std::memcpy(&x, &u, 4);
+      return x;
+    };
+    const int n_kb = (K + 255) / 256 * 16;
+    std::vector<uint16_t> frag(static_cast<size_t>(n_cta) * n_kb * 1024, 0);
+    for (int c = 0; c < n_cta; ++c)
+      for (int kb = 0; kb < n_kb; ++kb)
+        for (int nt = 0; nt < 4; ++nt)
+          for (int lane = 0; lane < 32; ++lane) {
+            const int gq = lane >> 2, tq = lane & 3, j = nt * 8 + gq;
+            const int ks[4] = {kb * 16 + 2 * tq, kb * 16 + 2 * tq + 1, kb * 16 + 2 * tq + 8, kb * 16 + 2 * tq + 9};
+            for (int e = 0; e < 4; ++e) {
+              const float val = ks[e] < K ? w[(static_cast<size_t>(c) * K + ks[e]) * 32 + j] : 0.0f;
+              const uint16_t hi = to_bf16(val), lo = to_bf16(val - from_bf16(hi));
+              const size_t base = (static_cast<size_t>(c) * n_kb + kb) * 1024;
+              frag[base + (static_cast<size_t>(nt) * 32 + lane) * 4 + e] = hi;
+              frag[base + 512 + (static_cast<size_t>(nt) * 32 + lane) * 4 + e] = lo;
+            }
+          }
+    std::vector<float> as_words(frag.size() / 2);
+    std::memcpy(as_words.data(), frag.data(), frag.size() * 2);
+    *Wp = upload(as_words);
+  } else if (mode == 1) {
     // round to nearest even into bf16, two per 32-bit word (the kernel reads them back with shifts)
     std::vector<float> packed(w.size() / 2);
     for (size_t i = 0; i < w.size(); i += 2) {
@@ -650,11 +813,13 @@ void build_taco(wg_taco_engine* e, const wg_taco_config* cfg, const wg_tensor* t
   d.KA = kP + d.E + d.A; d.KD = d.A + d.E + d.D; d.KO = d.D + d.E;
   d.drop_rate = c.prenet_drop_rate;
 
-  if (c.lstm_weight_dtype != 0 && c.lstm_weight_dtype != 1)
-    fail(WG_ERR_INVALID, "wg_taco_create: lstm_weight_dtype %d (0 = fp32, 1 = bf16)", c.lstm_weight_dtype);
+  if (c.lstm_weight_dtype < 0 || c.lstm_weight_dtype > 2)
+    fail(WG_ERR_INVALID, "wg_taco_create: lstm_weight_dtype %d (0 = fp32, 1 = bf16, 2 = split-bf16 mma)", c.lstm_weight_dtype);
+  e->lstm_mode = c.lstm_weight_dtype;
   e->lstm_bf16 = c.lstm_weight_dtype == 1;
-  pack_lstm(ts, n, "decoder/attention_rnn", kP + d.E, d.A, e->lstm_bf16, &e->WpA, &e->bpA);
-  pack_lstm(ts, n, "decoder/decoder_rnn/cell_0", d.A + d.E, d.D, e->lstm_bf16, &e->WpD, &e->bpD);
+  pack_lstm(ts, n, "decoder/attention_rnn", kP + d.E, d.A, e->lstm_mode, &e->WpA, &e->bpA);
+  pack_lstm(ts, n, "decoder/decoder_rnn/cell_0", d.A + d.E, d.D, e->lstm_mode, &e->WpD, &e->bpD);
+  CK(cudaFuncSetAttribute(lstm_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMmaSmem)));
   auto plain = [&](const char* name, std::initializer_list<int64_t> shape) {
     const wg_tensor& t = find(ts, n, name, shape);
     size_t numel = 1;
@@ -778,7 +943,9 @@ void enqueue_frames(wg_taco_engine* e, int B, int S, int frames, cudaStream_t st
     la.c = e->ca; la.c_gs = static_cast<size_t>(d.A) * kRows;
     la.o1 = XAq + static_cast<size_t>(kP + d.E) * kRows; la.o1_gs = xa_gs;
     la.o2 = XDp; la.o2_gs = xd_gs;
-    if (e->lstm_bf16)
+    if (e->lstm_mode == 2)
+      launch_chain(lstm_mma_kernel, dim3(d.A / kUnitsPerCta, G), kDenseThreads, kMmaSmem, st, la, pdl);
+    else if (e->lstm_bf16)
       launch_chain(dense16_kernel<32, EPI_LSTM, __nv_bfloat16>, dim3(d.A / kUnitsPerCta, G), kDenseThreads,
                    dense_smem<32, __nv_bfloat16>(), st, la, pdl);
     else
@@ -800,7 +967,9 @@ void enqueue_frames(wg_taco_engine* e, int B, int S, int frames, cudaStream_t st
     ld.c = e->cd; ld.c_gs = static_cast<size_t>(d.D) * kRows;
     ld.o1 = XDq + static_cast<size_t>(d.A + d.E) * kRows; ld.o1_gs = xd_gs;
     ld.o2 = e->XO; ld.o2_gs = xo_gs;
-    if (e->lstm_bf16)
+    if (e->lstm_mode == 2)
+      launch_chain(lstm_mma_kernel, dim3(d.D / kUnitsPerCta, G), kDenseThreads, kMmaSmem, st, ld, pdl);
+    else if (e->lstm_bf16)
       launch_chain(dense16_kernel<32, EPI_LSTM, __nv_bfloat16>, dim3(d.D / kUnitsPerCta, G), kDenseThreads,
                    dense_smem<32, __nv_bfloat16>(), st, ld, pdl);
     else

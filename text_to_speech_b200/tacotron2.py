@@ -128,9 +128,9 @@ class Tacotron2:
     """`Tacotron2(hp, weights, device, dtype).infer(tokens, max_length=..., early_stopping=...)` -- the
     argument names and the returned namedtuple follow `architectures.Tacotron2.infer` (:866-925)."""
 
-    def __init__(self, hp: Tacotron2HParams, weights: dict, device="cuda", dtype=torch.float32, b200_lstm_weights="fp32"):
-        if b200_lstm_weights not in ("fp32", "bf16"):
-            raise ValueError("b200_lstm_weights must be 'fp32' or 'bf16'")
+    def __init__(self, hp: Tacotron2HParams, weights: dict, device="cuda", dtype=torch.float32, b200_lstm_weights="split_bf16"):
+        if b200_lstm_weights not in ("fp32", "bf16", "split_bf16"):
+            raise ValueError("b200_lstm_weights must be 'fp32', 'bf16' or 'split_bf16'")
         self.hp, self.device, self.dtype, self.b200_lstm_weights = hp, torch.device(device), dtype, b200_lstm_weights
         t = lambda k: torch.as_tensor(np.asarray(weights[k]), dtype=dtype, device=self.device)  # noqa: E731
         self.emb = t("encoder/embeddings")
@@ -190,7 +190,7 @@ class Tacotron2:
             cfg = _lib.WgTacoConfig(hp.n_mel_channels, hp.prenet_sizes[-1], hp.embedding_dim, hp.attention_rnn_dim,
                                     hp.decoder_rnn_dim, hp.attention_dim, hp.attention_filters,
                                     hp.attention_kernel_size, hp.prenet_drop_rate,
-                                    1 if self.b200_lstm_weights == "bf16" else 0)
+                                    {"fp32": 0, "bf16": 1, "split_bf16": 2}[self.b200_lstm_weights])
             if tuple(hp.prenet_sizes) != (hp.prenet_sizes[-1],) * 2:
                 raise RuntimeError("decoder='b200' supports a two-layer prenet of equal widths")
             names = sorted(self._decoder_weights)

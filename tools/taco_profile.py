@@ -12,7 +12,7 @@ from text_to_speech_b200.tts import synthetic_texts
 hp = Tacotron2HParams()
 w = generate_tacotron2_weights(hp, 77)
 w["decoder/gate_output/bias"][:] = -10.0
-m = Tacotron2(hp, w, device="cuda", b200_lstm_weights=os.environ.get("TACO_LSTM", "fp32"))
+m = Tacotron2(hp, w, device="cuda", b200_lstm_weights=os.environ.get("TACO_LSTM", "split_bf16"))
 toks = np.stack(synthetic_texts(16, 99, 86, 86))
 frames = int(os.environ.get("TACO_FRAMES", "64"))
 chunk = int(os.environ.get("TACO_CHUNK", "0"))
