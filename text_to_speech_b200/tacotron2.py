@@ -248,22 +248,24 @@ class Tacotron2:
         x = self.emb[tokens] * mask[..., None]
         x = x.transpose(1, 2)
         m = mask[:, None, :]
-        for w, b in self.enc_convs:
-            x = F.relu(F.conv1d(x * m, w, b, padding=w.shape[-1] // 2))
-        x = (x * m).transpose(1, 2)
-        lengths = mask.sum(1).cpu()
-        packed = torch.nn.utils.rnn.pack_padded_sequence(x, lengths, batch_first=True, enforce_sorted=False)
-        out, _ = self.bilstm(packed)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):    # cuDNN would otherwise run fp32 convs / LSTMs in TF32
+            for w, b in self.enc_convs:
+                x = F.relu(F.conv1d(x * m, w, b, padding=w.shape[-1] // 2))
+            x = (x * m).transpose(1, 2)
+            lengths = mask.sum(1).cpu()
+            packed = torch.nn.utils.rnn.pack_padded_sequence(x, lengths, batch_first=True, enforce_sorted=False)
+            out, _ = self.bilstm(packed)
         out, _ = torch.nn.utils.rnn.pad_packed_sequence(out, batch_first=True, total_length=tokens.shape[1])
         return out * mask[..., None], mask
 
     def postnet(self, decoder_output: torch.Tensor, mask: torch.Tensor):
         x = (decoder_output * mask[..., None]).transpose(1, 2)
         m = mask[:, None, :]
-        for i, (w, b) in enumerate(self.post_convs):
-            x = F.conv1d(x * m, w, b, padding=w.shape[-1] // 2)
-            if i + 1 < len(self.post_convs):
-                x = torch.tanh(x)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            for i, (w, b) in enumerate(self.post_convs):
+                x = F.conv1d(x * m, w, b, padding=w.shape[-1] // 2)
+                if i + 1 < len(self.post_convs):
+                    x = torch.tanh(x)
         return (x * m).transpose(1, 2)
 
     # ---------------------------------------------------------------- decoder
