@@ -64,10 +64,18 @@ def tts(token_seqs: Sequence[np.ndarray], tacotron, vocoder, *, max_length=10.0,
         x = torch.full((len(batch.indices), batch.T, 80), PAD_MEL_VALUE, dtype=torch.float32, device=mels[batch.indices[0]].device)
         for j, i in enumerate(batch.indices):
             x[j, :frames[i]] = mels[i]
-        wave = vocoder(x, sigma=sigma).cpu().numpy()
+        wave_d = vocoder(x, sigma=sigma)
+        # waveforms and mels leave the device through pinned staging (one asynchronous copy each, one sync)
+        wave_h = torch.empty(wave_d.shape, dtype=torch.float32, pin_memory=True)
+        mel_h = torch.empty(x.shape, dtype=torch.float32, pin_memory=True)
+        wave_h.copy_(wave_d, non_blocking=True)
+        mel_h.copy_(x, non_blocking=True)
+        torch.cuda.current_stream(x.device).synchronize()
+        wave, mel_np = wave_h.numpy(), mel_h.numpy()
         for j, i in enumerate(batch.indices):
             audio = wave[j, :frames[i] * HOP].copy()               # models/tts/waveglow.py:82
-            results[i] = {"mel": mels[i].cpu().numpy(), "audio": audio, "rate": SAMPLE_RATE, "time": len(audio) / SAMPLE_RATE}
+            results[i] = {"mel": mel_np[j, :frames[i]].copy(), "audio": audio, "rate": SAMPLE_RATE,
+                          "time": len(audio) / SAMPLE_RATE}
     torch.cuda.synchronize()
     t2 = time.perf_counter()
     if timings is not None:
