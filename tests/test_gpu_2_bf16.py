@@ -115,6 +115,46 @@ def test_bf16_both_row_layouts_against_oracle(lib_built, monkeypatch, pm, B, T):
     eng.close()
 
 
+@pytest.mark.parametrize("B,T", [(2, 5), (1, 130), (3, 200)])
+def test_bf16_start_fold_against_oracle_and_unfolded_path(lib_built, monkeypatch, B, T):
+    """Phase-major path with the start conv folded into each flow's first WN layer (WG_FOLD0=1, default): h0 is never
+    materialised; layer 0 reads the audio rows through a0_build_kernel. Must meet the BF16 bar, agree with the
+    unfolded path (WG_FOLD0=0) far inside it, and give the right residual stream right after layer 0 (edges included:
+    the tap rows l-1 / l+1 outside the utterance are the reference's zero padding of h0, bias and all)."""
+    monkeypatch.setenv("WG_PM", "1")
+    hp = WaveGlowHParams()
+    w = generate_weights(hp, 1234, bias_std=0.05)
+    mel, z = synthetic_inputs(900 + B * 10 + T, B, T, hp)
+    taps = {}
+    ref = OracleWaveGlow(hp, w).infer(mel, z, 0.6, taps=taps).numpy()
+    mel_d, z_d = torch.from_numpy(mel).cuda(), torch.from_numpy(z).cuda()
+    outs, h0s = {}, {}
+    for fold in ("1", "0"):
+        monkeypatch.setenv("WG_FOLD0", fold)
+        eng = _engine(hp, w)
+        outs[fold] = _run(eng, mel, z, 0.6)
+        launches = eng.last_launch_count
+        for (k, i) in [(11, 0), (5, 0), (0, 0), (0, 1)]:
+            h, _ = eng.debug_prefix(mel_d, z_d, 0.6, k, i)
+            torch.cuda.synchronize()
+            h0s[fold, k, i] = h.cpu().numpy()
+        eng.close()
+        err, snr = np.abs(outs[fold] - ref).max(), snr_db(ref, outs[fold])
+        print(f"WG_FOLD0={fold} B={B} T={T}: max-abs {err:.3e} SNR {snr:.1f} dB, {launches} launches")
+        assert err <= TOL_BF16_ABS and snr >= TOL_BF16_SNR
+    assert np.abs(outs["1"] - outs["0"]).max() <= TOL_BF16_ABS
+    for (k, i) in [(11, 0), (5, 0), (0, 0), (0, 1)]:
+        ref_h = taps[f"flow{k}/layer{i}/audio"].reshape(-1, hp.n_channels).numpy()
+        scale = max(1.0, np.abs(ref_h).max())
+        e1, e0 = np.abs(h0s["1", k, i] - ref_h).max(), np.abs(h0s["0", k, i] - ref_h).max()
+        print(f"flow {k} layer {i}: h err folded {e1:.3e} / unfolded {e0:.3e} (|h| {scale:.2f})")
+        assert e1 <= 5e-2 * scale and e0 <= 5e-2 * scale
+        # first and last position of every utterance: the zero-padded taps
+        L = T * 32
+        edge = np.concatenate([np.arange(B) * L, np.arange(B) * L + L - 1])
+        assert np.abs(h0s["1", k, i][edge] - ref_h[edge]).max() <= 5e-2 * scale
+
+
 @pytest.mark.parametrize("pm", ["0", "1"])
 def test_bf16_waveglow512_matches_golden(lib_built, monkeypatch, pm):
     """WaveGlow-512 (reference default width, BASELINE.json configs[2]) on the two-kernel tcgen05 layer."""

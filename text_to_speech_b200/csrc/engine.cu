@@ -74,6 +74,10 @@ struct wg_engine {
   __nv_bfloat16* W1 = nullptr;     // [n_flows*n_layers*2C, 3C+S]
   __nv_bfloat16* W2 = nullptr;     // [n_flows*n_layers*C, C]
   __nv_bfloat16* V = nullptr;      // [n_flows*n_layers*R*2C, Kup]: (Wup_r @ Wcond) per layer and upsample phase
+  // start-conv fold (phase-major bf16 path, C = 256): layer 0 of a flow consumes the audio rows directly
+  __nv_bfloat16* W0 = nullptr;     // [n_flows*2C, 64]: per tap [Wstart@Win_tap hi | same | lo | bstart@Win_tap hi | lo | 0 0], chunk-packed rows
+  __nv_bfloat16* H0 = nullptr;     // [n_flows*C, 64]: columns 48..63 = [Wstart hi | same | lo | bstart hi | lo | 0 0]
+  bool fold0 = true;               // WG_FOLD0=0 keeps the materialised start conv (A/B and debugging)
   int pm_policy = -1;               // WG_PM: -1 auto (by tile efficiency), 0 never, 1 always
   int Kup = 0;
   std::vector<void*> allocs;
@@ -159,7 +163,7 @@ inline __nv_bfloat16 f2bf(float x) { return __float2bfloat16_rn(x); }
 
 struct Ws {  // workspace carving for one (B, T)
   size_t spect = 0, h32 = 0, acts = 0, skip = 0, acc8 = 0, audio0 = 0, audio1 = 0;
-  size_t spect16 = 0, h16a = 0, h16b = 0, hlo = 0, aup16 = 0, acts16 = 0;
+  size_t spect16 = 0, h16a = 0, h16b = 0, hlo = 0, aup16 = 0, acts16 = 0, a0 = 0;
   size_t total = 0;
 };
 
@@ -196,6 +200,7 @@ Ws carve(const wg_engine* e, int B, int T) {
     w.hlo = take(M * e->C * 2);
     w.aup16 = take((size_t)B * T * e->Kup * 2);
     if (e->C == 512) w.acts16 = take(M * e->C * 2);   // WaveGlow-512: acts travel between the gate and residual kernels
+    if (e->W0 && use_pm(e, T)) w.a0 = take(M * 64 * 2);   // start fold: A operand of each flow's first layer
   }
   w.total = off;
   return w;
@@ -253,6 +258,9 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
   __nv_bfloat16* hlo = reinterpret_cast<__nv_bfloat16*>(base + w.hlo);
   __nv_bfloat16* aup16 = reinterpret_cast<__nv_bfloat16*>(base + w.aup16);
   __nv_bfloat16* acts16 = reinterpret_cast<__nv_bfloat16*>(base + w.acts16);
+  __nv_bfloat16* a0 = reinterpret_cast<__nv_bfloat16*>(base + w.a0);
+  // start fold: off for a debug prefix that wants h right after the start conv (it would not exist)
+  const bool fold0 = bf16 && pm && e->W0 && e->fold0 && !(stop_flow >= 0 && stop_layer == -1);
   CUtensorMap m_acts512;
   const float* zz = deterministic ? nullptr : z;
 
@@ -269,7 +277,8 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
     launch_gemm<EPI_STORE>(e, g, st);
   } else {
     tc_prepare(plan, e->sm_count, B, T, L, C, S, e->Kup, c.n_mel_channels, c.n_flows * c.n_layers,
-               e->Wup16, R * S, e->W1, e->W2, aup16, spect16, h16[0], h16[1], hlo, pm, R, e->V);
+               e->Wup16, R * S, e->W1, e->W2, aup16, spect16, h16[0], h16[1], hlo, pm, R, e->V,
+               fold0 ? a0 : nullptr, e->W0, e->H0, c.n_flows);
     if (e->use_pair && !pm && C == 256) tc_pair_prepare(pmaps, c.n_flows * c.n_layers, C, S, e->W1, e->W2);
     if (C == 512) make_map_4d(&m_acts512, acts16, pm ? B : 1, pm ? (uint64_t)R : (uint64_t)B, plan.Trows, C, WL_BM);
     e->launches += tc_upsample(plan, mel, e->bup, st);
@@ -283,12 +292,18 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
     a.R = geomR; a.T = geomT;
     a.first = 1; a.z = zz; a.n_group = c.n_group; a.z_off = 0; a.n_inject = e->flows[F - 1].n_rem;
     a.sigma = sigma; a.audio_out = audio[cur]; a.M = M; a.C = C;
-    a.Wstart = e->flows[F - 1].Wstart; a.bstart = e->flows[F - 1].bstart;
+    a.Wstart = fold0 ? nullptr : e->flows[F - 1].Wstart; a.bstart = e->flows[F - 1].bstart;
     a.n_half_next = e->flows[F - 1].n_half; a.h32 = h32; a.h16 = bf16 ? h16[hcur] : nullptr; a.hlo = bf16 ? hlo : nullptr;
     if (bf16) { a.acc8_rearm = acc8; std::memcpy(a.acc8_init, e->flows[F - 1].bse8, sizeof a.acc8_init); }
     launch_boundary(e, a, st);
     z_off = a.n_inject;
   }
+  auto launch_a0 = [&](const float* audio_rows, int n_half) {
+    a0_build_kernel<<<(unsigned)(((size_t)M * 4 + 255) / 256), 256, 0, st>>>(audio_rows, a0, M, geomR, geomT, n_half);
+    CK(cudaGetLastError());
+    e->launches++;
+  };
+  if (fold0) launch_a0(audio[cur], e->flows[F - 1].n_half);
 
   auto prof_mark = [&](void) {
     if (!e->profiling) return;
@@ -353,7 +368,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
                                           lw.wse_h.data(), e->timing, e->dbg_flags, st);
         else
           e->launches += tc_wn_layer(plan, k * c.n_layers + i, d, last, hcur, acc8, pm ? lw.b1_pm : lw.b1, lw.b2,
-                                     lw.wse_h.data(), e->timing, e->dbg_flags, st);
+                                     lw.wse_h.data(), e->timing, e->dbg_flags, st, fold0 && i == 0);
         prof_mark();
         if (!last) hcur ^= 1;
       }
@@ -383,7 +398,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
     if (early) z_off += c.n_early_size;
     if (k > 0) {
       a.audio_out = audio[cur ^ 1];
-      a.Wstart = e->flows[k - 1].Wstart; a.bstart = e->flows[k - 1].bstart;
+      a.Wstart = fold0 ? nullptr : e->flows[k - 1].Wstart; a.bstart = e->flows[k - 1].bstart;
       a.n_half_next = e->flows[k - 1].n_half; a.h32 = h32;
       hcur = 0;
       a.h16 = bf16 ? h16[hcur] : nullptr; a.hlo = bf16 ? hlo : nullptr;
@@ -395,6 +410,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
     }
     launch_boundary(e, a, st);
     cur ^= 1;
+    if (fold0 && k > 0) launch_a0(audio[cur], e->flows[k - 1].n_half);
   }
 }
 
@@ -509,10 +525,15 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
   // ---- flows / layers ------------------------------------------------------------------------
   e->layers.resize((size_t)F * NL);
   const int K1 = 3 * C + S;
-  std::vector<__nv_bfloat16> w1all, w2all;
+  std::vector<__nv_bfloat16> w1all, w2all, w0all, h0all;
+  const bool build_fold0 = c.mode == WG_MODE_BF16 && C == 256 && NL > 1;
   if (c.mode == WG_MODE_BF16) {
     w1all.assign((size_t)F * NL * 2 * C * K1, f2bf(0.f));
     w2all.assign((size_t)F * NL * C * C, f2bf(0.f));
+    if (build_fold0) {
+      w0all.assign((size_t)F * 2 * C * 64, f2bf(0.f));
+      h0all.assign((size_t)F * C * 64, f2bf(0.f));
+    }
   }
   for (int k = 0; k < F; ++k) {
     FlowW& fw = e->flows[k];
@@ -586,6 +607,45 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
           b1[pcol] = inb.data[col] + cb.data[col];
           for (int kk = 0; kk < K1; ++kk) w1[(size_t)pcol * K1 + kk] = f2bf(wsrc(kk, col));
         }
+        if (build_fold0 && i == 0) {
+          // start fold (a0_build_kernel): 16 K columns per tap = [G hi (4) | G hi (4) | G lo (4) | g hi | g lo | 0 0] with
+          // G = Wstart @ Win[tap] ([nh, 2C]) and g = bstart @ Win[tap], folded in double and split into bf16 hi + lo;
+          // H0 carries [Wstart; bstart] the same way in columns 48..63 (the residual operand h0 itself).
+          auto split = [](double v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+            hi = f2bf((float)v);
+            lo = f2bf((float)(v - (double)__bfloat162float(hi)));
+          };
+          __nv_bfloat16* w0 = w0all.data() + (size_t)k * 2 * C * 64;
+          for (int pcol = 0; pcol < 2 * C; ++pcol) {
+            const int chunk = pcol >> 8, wi = pcol & 255;
+            const int col = wi < 128 ? 128 * chunk + wi : C + 128 * chunk + (wi - 128);
+            for (int tap = 0; tap < 3; ++tap) {
+              __nv_bfloat16* dst = w0 + (size_t)pcol * 64 + tap * 16;
+              for (int j = 0; j <= nh; ++j) {       // j == nh: the bias row
+                double acc = 0.0;
+                for (int ci = 0; ci < C; ++ci) {
+                  const double left = j < nh ? (double)sk.data[(size_t)j * C + ci] : (double)sb.data[ci];
+                  acc += left * (double)inw.data[((size_t)tap * C + ci) * 2 * C + col];
+                }
+                __nv_bfloat16 hi, lo;
+                split(acc, hi, lo);
+                if (j < nh) { dst[j] = hi; dst[4 + j] = hi; dst[8 + j] = lo; }
+                else { dst[12] = hi; dst[13] = lo; }
+              }
+            }
+          }
+          __nv_bfloat16* h0 = h0all.data() + (size_t)k * C * 64;
+          for (int n = 0; n < C; ++n) {
+            __nv_bfloat16* dst = h0 + (size_t)n * 64 + 48;
+            for (int j = 0; j <= nh; ++j) {
+              const double v = j < nh ? (double)sk.data[(size_t)j * C + n] : (double)sb.data[n];
+              __nv_bfloat16 hi, lo;
+              split(v, hi, lo);
+              if (j < nh) { dst[j] = hi; dst[4 + j] = hi; dst[8 + j] = lo; }
+              else { dst[12] = hi; dst[13] = lo; }
+            }
+          }
+        }
         {   // phase-major path: fp32 cond weights in packed column order + bias with the upsample bias folded in
           std::vector<float> wc((size_t)S * 2 * C), b1pm((size_t)2 * C);
           for (int pcol = 0; pcol < 2 * C; ++pcol) {
@@ -634,6 +694,11 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
   if (c.mode == WG_MODE_BF16) {
     e->W1 = upload(e, w1all);
     e->W2 = upload(e, w2all);
+    if (build_fold0) {
+      e->W0 = upload(e, w0all);
+      e->H0 = upload(e, h0all);
+      if (const char* f0 = std::getenv("WG_FOLD0")) e->fold0 = f0[0] != '0';
+    }
     tc_init();
     {   // V[(layer*R + r)*2C + n][k] = sum_s Wup_r[k][s] * Wcond_layer[s][n]   (k < 4*n_mel, padded to Kup)
       const int Kw = (UPSAMPLE_K / HOP) * NM;       // 320

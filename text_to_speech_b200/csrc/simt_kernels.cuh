@@ -330,4 +330,52 @@ flow_boundary_kernel(const __grid_constant__ BoundaryArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Start-conv fold (bf16 phase-major path): the A operand of the FIRST WN layer of a flow.
+//
+// h0 = start(audio_0) is a rank-n_half (<= 4) function of the audio rows, so layer 0's dilated conv
+// (dilation 1) and its residual do not need h0 in HBM at all:
+//   conv[l]  = sum_tap h0[l+tap-1] @ Win[tap] = sum_tap [a(l+tap-1), 1] @ [Wstart @ Win[tap]; bstart @ Win[tap]]
+//   resid[l] = h0[l]                           =         [a(l), 1]       @ [Wstart; bstart]
+// with a zero row (including the ones column) for positions outside the utterance == the reference's
+// zero 'same' padding of h0 (waveglow_arch.py:108, :113-118). Row m of `a0` [M, 64] bf16 holds four
+// 16-column groups -- taps l-1, l, l+1 and the residual operand l -- each
+//   [a_hi(4) | a_lo(4) | a_hi(4) | 1 | 1 | 0 | 0],   a = a_hi + a_lo (bf16 split of the fp32 audio),
+// to be multiplied with [G_hi; G_hi; G_lo; g_hi; g_lo] (three-product split, fp32-grade accuracy).
+// One thread per (row, group); rows follow the internal (b, r, t) order, position l = R*t + r.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+a0_build_kernel(const float* __restrict__ audio, __nv_bfloat16* __restrict__ a0, int M, int R, int T, int n_half) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * 4) return;
+  const int m = idx >> 2, g = idx & 3;
+  const int per_b = R * T;
+  const int b = m / per_b, rem = m - b * per_b;
+  const int r = rem / T, t = rem - r * T;
+  const int l = t * R + r + (g < 3 ? g - 1 : 0);
+  uint32_t w[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) w[j] = 0u;
+  if (l >= 0 && l < per_b) {
+    const int ts = l / R, rs = l - ts * R;
+    const size_t src = static_cast<size_t>(b) * per_b + static_cast<size_t>(rs) * T + ts;
+    const float4 v4 = *reinterpret_cast<const float4*>(audio + src * 8);
+    float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j >= n_half) v[j] = 0.f;
+    const __nv_bfloat162 h01 = __floats2bfloat162_rn(v[0], v[1]), h23 = __floats2bfloat162_rn(v[2], v[3]);
+    const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+    const __nv_bfloat162 l01 = __floats2bfloat162_rn(v[0] - f01.x, v[1] - f01.y);
+    const __nv_bfloat162 l23 = __floats2bfloat162_rn(v[2] - f23.x, v[3] - f23.y);
+    w[0] = *reinterpret_cast<const uint32_t*>(&h01); w[1] = *reinterpret_cast<const uint32_t*>(&h23);
+    w[2] = *reinterpret_cast<const uint32_t*>(&l01); w[3] = *reinterpret_cast<const uint32_t*>(&l23);
+    w[4] = w[0]; w[5] = w[1];
+    w[6] = 0x3F803F80u;   // two bf16 ones
+  }
+  uint4* dst = reinterpret_cast<uint4*>(a0 + static_cast<size_t>(m) * 64 + g * 16);
+  dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+  dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
 }  // namespace wg

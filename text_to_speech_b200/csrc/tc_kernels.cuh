@@ -341,6 +341,7 @@ struct WnLayerParams {
   int wc_row0;          // first N row of this layer's conditioning weights inside map_wc
   int wc_rstride;       // extra N rows per phase (0 or 512)
   int layer;      // row block in the stacked W1 / W2 matrices
+  int flow;       // row block in the stacked start-fold matrices W0 / H0 (FIRST variant)
   int dilation;
   const float* b1;   // [512] chunk-packed
   const float* b2;   // [256]
@@ -413,13 +414,19 @@ __device__ __forceinline__ void gate_step(const uint32_t (&t)[16], const uint32_
   }
 }
 
-template <bool LAST>
+// FIRST (layer 0 of a flow, phase-major only): the start conv is folded into the layer (simt_kernels.cuh,
+// a0_build_kernel). The 12 conv K-blocks become ONE K-block  a0[128 x 64] @ W0[64 x 512]  (three K = 16 MMAs,
+// one per tap) and the residual operand comes from the same tile,  a0 @ H0[64 x 256]  (one K = 16 MMA), instead
+// of eight identity MMAs on (hi, lo): h0 never exists in HBM.
+template <bool LAST, bool FIRST = false>
 __global__ void __launch_bounds__(WL_THREADS, 1)
 tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_ho,
                    const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_cond, const __grid_constant__ CUtensorMap map_w1,
                    const __grid_constant__ CUtensorMap map_wc,
-                   const __grid_constant__ CUtensorMap map_w2, const WnLayerParams p,
+                   const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_a0,
+                   const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_h0, const WnLayerParams p,
                    const __grid_constant__ WnLayerConst cw) {
+  static_assert(!(LAST && FIRST), "the start fold needs a residual layer");
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
   float* s_b1 = reinterpret_cast<float*>(smem + WL_OFF_B1);
@@ -448,6 +455,11 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
     prefetch_tmap(&map_wc);
     prefetch_tmap(&map_w1);
     prefetch_tmap(&map_w2);
+    if (FIRST) {
+      prefetch_tmap(&map_a0);
+      prefetch_tmap(&map_w0);
+      prefetch_tmap(&map_h0);
+    }
     for (int s = 0; s < WL_STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -467,6 +479,8 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
   for (int i = threadIdx.x; i < 2 * WL_C; i += WL_THREADS) s_b1[i] = p.b1[i];
   if (!LAST) {
     for (int i = threadIdx.x; i < WL_C; i += WL_THREADS) s_b2[i] = p.b2[i];
+  }
+  if (!LAST && !FIRST) {
     // identity B tile: element (n, k) of a [64 x 64] K-major SWIZZLE_128B tile sits at byte
     // n*128 + (((k>>3) ^ (n&7)) << 4) + (k&7)*2
     uint32_t* i64w = reinterpret_cast<uint32_t*>(smem + WL_OFF_I64);
@@ -487,7 +501,8 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
   const bool timing = p.timing != nullptr;
   const bool pm = p.R > 1;   // phase-major: maps are (channels, frames, phases, batch); else (channels, rows, batch, 1)
-  const int kb1 = WL_KB_CONV + p.n_cond_kb;   // K-blocks of GEMM1 per chunk: 22 (spect) or 17 (mel window)
+  constexpr int KB_CONV = FIRST ? 1 : WL_KB_CONV;   // conv K-blocks of GEMM1: 12, or the single start-fold block
+  const int kb1 = KB_CONV + p.n_cond_kb;   // K-blocks of GEMM1 per chunk: 22 (spect), 17 (mel window), 6 (FIRST)
   // tile -> (utterance b, phase r, first row t0 of the 128-row tile inside the (b, r) row block)
   auto tile_coords = [&](int tile, int& b, int& r, int& t0) {
     const int tt = tile % p.tiles_per_row, br = tile / p.tiles_per_row;
@@ -521,7 +536,10 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
             const uint32_t s = acquire((skip_a ? 0 : WL_A_BYTES) + (skip_b ? 0 : WL_B_BYTES));
             const uint32_t a_dst = smem_base + s * WL_STAGE_BYTES;
             if (elect_one()) {
-              if (kb < WL_KB_CONV) {
+              if (FIRST && kb == 0) {
+                if (!skip_a) tma_load_4d(a_dst, &map_a0, full_bar(s), 0, t0, pm ? r : b, pm ? b : 0);
+                if (!skip_b) tma_load_2d(a_dst + WL_A_BYTES, &map_w0, full_bar(s), 0, p.flow * 2 * WL_C + q * 256);
+              } else if (kb < KB_CONV) {
                 // tap shifted by sh positions: phase (r+sh) mod R, frames moved by floor((r+sh)/R)
                 const int tap = kb >> 2, cblk = kb & 3;
                 const int rs = r + (tap - 1) * p.dilation;
@@ -529,7 +547,7 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
                 if (!skip_a) tma_load_4d(a_dst, &map_h, full_bar(s), cblk * WL_BK, t0 + carry, pm ? rs - carry * p.R : b, pm ? b : 0);
                 if (!skip_b) tma_load_2d(a_dst + WL_A_BYTES, &map_w1, full_bar(s), kb * WL_BK, p.layer * 2 * WL_C + q * 256);
               } else {
-                const int kc = kb - WL_KB_CONV;
+                const int kc = kb - KB_CONV;
                 if (!skip_a) tma_load_4d(a_dst, &map_cond, full_bar(s), kc * WL_BK, t0, pm ? 0 : b, pm ? b : 0);
                 if (!skip_b) tma_load_2d(a_dst + WL_A_BYTES, &map_wc, full_bar(s), p.wc_col0 + kc * WL_BK,
                                          p.wc_row0 + r * p.wc_rstride + q * 256);
@@ -538,7 +556,22 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
             __syncwarp();
           }
         }
-        if (!LAST) {
+        if (FIRST) {
+          // consumption order of the MMA warp: a0 / H0 (residual operand) | W2 blocks 0..3 (A = acts in smem)
+          for (int step = 0; step < 5; ++step, ++it) {
+            const uint32_t s = acquire(step == 0 ? WL_STAGE_BYTES : WL_B_BYTES);
+            const uint32_t dst = smem_base + s * WL_STAGE_BYTES;
+            if (elect_one()) {
+              if (step == 0) {
+                tma_load_4d(dst, &map_a0, full_bar(s), 0, t0, pm ? r : b, pm ? b : 0);
+                tma_load_2d(dst + WL_A_BYTES, &map_h0, full_bar(s), 0, p.flow * WL_C);
+              } else {
+                tma_load_2d(dst + WL_A_BYTES, &map_w2, full_bar(s), (step - 1) * WL_BK, p.layer * WL_C);
+              }
+            }
+            __syncwarp();
+          }
+        } else if (!LAST) {
           // consumption order of the MMA warp: W2/hi blocks 0,1 | lo blocks 0..3 | W2/hi blocks 2,3
           for (int step = 0; step < 6; ++step, ++it) {
             if (step == 2 || step == 3) {
@@ -605,15 +638,40 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
             const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + WL_A_BYTES);
             if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < WL_BK / 16; ++k)
+              for (int k = 0; k < WL_BK / 16; ++k) {
+                if (FIRST && kb == 0 && k == 3) break;   // columns 48..63 of a0 are the residual operand (GEMM2)
                 umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+              }
               tc_commit(empty_bar(it % WL_STAGES));
               if (kb == kb1 - 1) tc_commit(dfull_bar(q));
             }
             __syncwarp();
           }
         }
-        if (!LAST) {
+        if (FIRST) {
+          const uint32_t d_tmem = tmem_base + 256u * par;
+          wait_epi(actsa_bar, n & 1u);   // acts blocks 0,1 written, D1a (this region) read out
+          for (int step = 0; step < 5; ++step, ++it) {
+            if (step == 3) wait_epi(acts2_bar, n & 1u);  // acts block 2 written
+            if (step == 4) wait_epi(acts_bar, n & 1u);   // acts block 3 written, D1b read out
+            const uint32_t st_addr = wait_full();
+            if (elect_one()) {
+              if (step == 0) {
+                // h0 = [a(l), 1] @ [Wstart; bstart]: K columns 48..63 of the a0 tile against H0
+                umma_bf16(d_tmem, umma_desc_sw128(st_addr) + 6, umma_desc_sw128(st_addr + WL_A_BYTES) + 6, idesc, 0u);
+              } else {
+                const int kb = step - 1;
+                const uint64_t adesc = umma_desc_sw128(smem_base + WL_OFF_ACTS + kb * WL_A_BYTES);
+                const uint64_t bdesc = umma_desc_sw128(st_addr + WL_A_BYTES);
+#pragma unroll
+                for (int k = 0; k < WL_BK / 16; ++k) umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+              }
+              tc_commit(empty_bar(it % WL_STAGES));
+              if (step == 4) tc_commit(dfull_bar(2));
+            }
+            __syncwarp();
+          }
+        } else if (!LAST) {
           const uint32_t d_tmem = tmem_base + 256u * par;
           wait_epi(actsa_bar, n & 1u);   // acts blocks 0,1 written, D1a (this region) read out
           for (int step = 0; step < 6; ++step, ++it) {
@@ -865,6 +923,7 @@ inline void tc_init() {
   WG_CK(cudaFuncSetAttribute(tc_gemm_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
   WG_CK(cudaFuncSetAttribute(tc_wn_layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WL_SMEM));
   WG_CK(cudaFuncSetAttribute(tc_wn_layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WL_SMEM));
+  WG_CK(cudaFuncSetAttribute(tc_wn_layer_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WL_SMEM));
 }
 
 // bf16 tensor map, innermost dim contiguous, SWIZZLE_128B, box inner = 64 elements (128 B).
@@ -915,6 +974,10 @@ struct TcPlan {
   CUtensorMap m_aup, m_wup, m_w1, m_w2, m_h16[2], m_lo, m_spect;
   // (phase, frame) geometry of the single-CTA layer kernel: 4-D maps (channels, rows, phases, batch)
   CUtensorMap m4_h[2], m4_lo, m4_cond, m_wc;
+  // start-conv fold (FIRST layer variant, phase-major only): a0 [M, 64], W0 [n_flows*2C, 64], H0 [n_flows*C, 64]
+  CUtensorMap m4_a0{}, m_w0{}, m_h0{};
+  bool fold0 = false;
+  int n_layers = 0;
   bool pm = false;           // phase-major layout (R = 32) with the rank-320 conditioning
   int R = 1, Trows = 0, tiles_per_row = 0;
   int n_cond_kb = 0, wc_col0 = 0, wc_rows_per_layer = 0, wc_rstride = 0;
@@ -927,7 +990,9 @@ struct TcPlan {
 inline void tc_prepare(TcPlan& pl, int sm_count, int B, int T, int L, int C, int S, int Kup, int n_mel,
                        int n_layers_total, const __nv_bfloat16* Wup16, int NupN, const __nv_bfloat16* W1,
                        const __nv_bfloat16* W2, __nv_bfloat16* aup16, __nv_bfloat16* spect16, __nv_bfloat16* h16a,
-                       __nv_bfloat16* h16b, __nv_bfloat16* hlo, bool pm, int R, const __nv_bfloat16* V) {
+                       __nv_bfloat16* h16b, __nv_bfloat16* hlo, bool pm, int R, const __nv_bfloat16* V,
+                       __nv_bfloat16* a0 = nullptr, const __nv_bfloat16* W0 = nullptr, const __nv_bfloat16* H0 = nullptr,
+                       int n_flows = 0) {
   if ((C != 256 && C != 512) || S != WL_S) fail(WG_ERR_UNSUPPORTED, "tensor path is built for C in {256, 512}, S=640 (got C=%d, S=%d)", C, S);
   pl.sm_count = sm_count; pl.B = B; pl.T = T; pl.L = L; pl.C = C; pl.S = S; pl.Kup = Kup; pl.n_mel = n_mel; pl.NupN = NupN;
   pl.aup16 = aup16; pl.spect16 = spect16; pl.h16[0] = h16a; pl.h16[1] = h16b; pl.hlo = hlo;
@@ -949,6 +1014,13 @@ inline void tc_prepare(TcPlan& pl, int sm_count, int B, int T, int L, int C, int
     make_map_4d(&pl.m4_cond, aup16, B, 1, T, Kup, WL_BM);
     make_map_2d(&pl.m_wc, V, (uint64_t)n_layers_total * R * 2 * C, Kup, 256);
     pl.n_cond_kb = Kup / WL_BK; pl.wc_col0 = 0; pl.wc_rows_per_layer = R * 2 * C; pl.wc_rstride = 2 * C;
+    pl.fold0 = a0 && W0 && H0 && n_flows > 0 && C == WL_C;
+    if (pl.fold0) {
+      pl.n_layers = n_layers_total / n_flows;
+      make_map_4d(&pl.m4_a0, a0, B, R, T, WL_BK, WL_BM);
+      make_map_2d(&pl.m_w0, W0, (uint64_t)n_flows * 2 * C, WL_BK, 256);
+      make_map_2d(&pl.m_h0, H0, (uint64_t)n_flows * C, WL_BK, 256);
+    }
   } else {
     make_map_2d(&pl.m_aup, aup16, (uint64_t)B * T, Kup, TG_BM);
     make_map_2d(&pl.m_wup, Wup16, NupN, Kup, TG_BN);
@@ -983,20 +1055,25 @@ inline void tc_fill_params(const TcPlan& pl, WnLayerParams& p, int layer, int di
   p.L = pl.Trows; p.tiles_per_b = pl.tiles_per_row;
   p.n_cond_kb = pl.n_cond_kb; p.wc_col0 = pl.wc_col0; p.wc_row0 = layer * pl.wc_rows_per_layer; p.wc_rstride = pl.wc_rstride;
   p.layer = layer; p.dilation = dilation;
+  p.flow = pl.n_layers > 0 ? layer / pl.n_layers : 0;
   p.b1 = b1; p.b2 = b2; p.hi_out = pl.h16[hcur ^ 1]; p.lo = pl.hlo; p.acc8 = acc8; p.timing = timing; p.flags = flags;
 }
 
 inline int tc_wn_layer(const TcPlan& pl, int layer, int dilation, bool last, int hcur, float* acc8, const float* b1,
-                       const float* b2, const float* wse_host, unsigned long long* timing, int flags, cudaStream_t st) {
+                       const float* b2, const float* wse_host, unsigned long long* timing, int flags, cudaStream_t st,
+                       bool first = false) {
   WnLayerParams p{};
   tc_fill_params(pl, p, layer, dilation, hcur, acc8, b1, b2, timing, flags);
   WnLayerConst cw;
   std::memcpy(cw.wse, wse_host, sizeof cw.wse);
   const int grid = pl.n_tiles < pl.sm_count ? pl.n_tiles : pl.sm_count;
+  if (first && (!pl.fold0 || last || dilation != 1)) fail(WG_ERR_INVALID, "start fold requested for a layer it does not apply to");
   if (last)
-    tc_wn_layer_kernel<true><<<grid, WL_THREADS, WL_SMEM, st>>>(pl.m4_h[hcur], pl.m4_h[hcur ^ 1], pl.m4_lo, pl.m4_cond, pl.m_w1, pl.m_wc, pl.m_w2, p, cw);
+    tc_wn_layer_kernel<true><<<grid, WL_THREADS, WL_SMEM, st>>>(pl.m4_h[hcur], pl.m4_h[hcur ^ 1], pl.m4_lo, pl.m4_cond, pl.m_w1, pl.m_wc, pl.m_w2, pl.m4_a0, pl.m_w0, pl.m_h0, p, cw);
+  else if (first)
+    tc_wn_layer_kernel<false, true><<<grid, WL_THREADS, WL_SMEM, st>>>(pl.m4_h[hcur], pl.m4_h[hcur ^ 1], pl.m4_lo, pl.m4_cond, pl.m_w1, pl.m_wc, pl.m_w2, pl.m4_a0, pl.m_w0, pl.m_h0, p, cw);
   else
-    tc_wn_layer_kernel<false><<<grid, WL_THREADS, WL_SMEM, st>>>(pl.m4_h[hcur], pl.m4_h[hcur ^ 1], pl.m4_lo, pl.m4_cond, pl.m_w1, pl.m_wc, pl.m_w2, p, cw);
+    tc_wn_layer_kernel<false><<<grid, WL_THREADS, WL_SMEM, st>>>(pl.m4_h[hcur], pl.m4_h[hcur ^ 1], pl.m4_lo, pl.m4_cond, pl.m_w1, pl.m_wc, pl.m_w2, pl.m4_a0, pl.m_w0, pl.m_h0, p, cw);
   WG_CK(cudaGetLastError());
   return 1;
 }
