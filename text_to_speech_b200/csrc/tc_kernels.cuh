@@ -19,6 +19,7 @@
 #include <stdint.h>
 
 #include <cstring>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -414,6 +415,67 @@ __device__ __forceinline__ void gate_step(const uint32_t (&t)[16], const uint32_
   }
 }
 
+// Packed-math (f32x2: FADD2 / FMUL2 / FFMA2, sm_100) versions used by the single-CTA kernel. Two adjacent gate
+// channels travel as one float2 through bias add, gate and fold; the fold keeps EVEN and ODD channels in the two
+// lanes of eight float2 accumulators (summed once per tile), so no operand has to be duplicated:
+//   o8p[c] += (a_j, a_j+1) * (wse[j][c], wse[j+1][c])      wse2 = [channel pair][8] float2 (host-permuted)
+template <bool LAST>
+__device__ __forceinline__ void gate_step2(const uint32_t (&t)[16], const uint32_t (&g)[16], const float* bT,
+                                           const float2* wse2, uint8_t* kblk, int st, int row, float2 (&o8p)[8]) {
+  const float* bG = bT + 128;
+  const float2 half2 = make_float2(0.5f, 0.5f);
+  uint32_t pk[8];
+#pragma unroll
+  for (int j4 = 0; j4 < 4; ++j4) {
+    const float4 bt4 = *reinterpret_cast<const float4*>(bT + 4 * j4);
+    const float4 bg4 = *reinterpret_cast<const float4*>(bG + 4 * j4);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j2 = 2 * j4 + h;   // channel pair (2 j2, 2 j2 + 1)
+      const float2 xt = __fadd2_rn(make_float2(__uint_as_float(t[2 * j2]), __uint_as_float(t[2 * j2 + 1])),
+                                   h == 0 ? make_float2(bt4.x, bt4.y) : make_float2(bt4.z, bt4.w));
+      const float2 xg = __fmul2_rn(__fadd2_rn(make_float2(__uint_as_float(g[2 * j2]), __uint_as_float(g[2 * j2 + 1])),
+                                              h == 0 ? make_float2(bg4.x, bg4.y) : make_float2(bg4.z, bg4.w)), half2);
+      const float2 th = make_float2(tanh_fast(xt.x), tanh_fast(xt.y));
+      const float2 sg = __ffma2_rn(make_float2(tanh_fast(xg.x), tanh_fast(xg.y)), half2, half2);
+      const float2 a = __fmul2_rn(th, sg);
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const float4 w = *reinterpret_cast<const float4*>(wse2 + j2 * 8 + 2 * c4);   // (w[j][2c4], w[j+1][2c4], w[j][2c4+1], w[j+1][2c4+1])
+        o8p[2 * c4] = __ffma2_rn(a, make_float2(w.x, w.y), o8p[2 * c4]);
+        o8p[2 * c4 + 1] = __ffma2_rn(a, make_float2(w.z, w.w), o8p[2 * c4 + 1]);
+      }
+      pk[j2] = pack_bf16x2(a.x, a.y);
+    }
+  }
+  if (!LAST) {
+    *reinterpret_cast<uint4*>(kblk + (((st * 2) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    *reinterpret_cast<uint4*>(kblk + (((st * 2 + 1) ^ (row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  }
+}
+
+// Residual epilogue, packed: PASS 0 stages hi = bf16(v) only, PASS 1 recomputes it and stages lo = bf16(v - hi).
+template <int PASS>
+__device__ __forceinline__ void resid_step2(const uint32_t (&r)[16], const float* bb, uint8_t* stg, int gi, int row) {
+  uint32_t w[8];
+#pragma unroll
+  for (int j2 = 0; j2 < 8; ++j2) {
+    const float2 v = __fadd2_rn(make_float2(__uint_as_float(r[2 * j2]), __uint_as_float(r[2 * j2 + 1])),
+                                *reinterpret_cast<const float2*>(bb + 2 * j2));
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v.x, v.y);
+    if (PASS == 0) {
+      w[j2] = *reinterpret_cast<const uint32_t*>(&h2);
+    } else {
+      const float2 d = __ffma2_rn(__bfloat1622float2(h2), make_float2(-1.f, -1.f), v);   // exact: v - hi
+      w[j2] = pack_bf16x2(d.x, d.y);
+    }
+  }
+  uint8_t* dst = stg + (gi >> 2) * (128 * 64 * 2);
+  const int c0 = (gi & 3) * 2;
+  *reinterpret_cast<uint4*>(dst + ((c0 ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+  *reinterpret_cast<uint4*>(dst + (((c0 + 1) ^ (row & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
 // FIRST (layer 0 of a flow, phase-major only): the start conv is folded into the layer (simt_kernels.cuh,
 // a0_build_kernel). The 12 conv K-blocks become ONE K-block  a0[128 x 64] @ W0[64 x 512]  (three K = 16 MMAs,
 // one per tap) and the residual operand comes from the same tile,  a0 @ H0[64 x 256]  (one K = 16 MMA), instead
@@ -732,9 +794,9 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
       const uint32_t ph = n & 1u;
       const bool valid = (t0 + row) < p.T;
       const size_t m = (static_cast<size_t>(b) * p.R + r) * p.T + t0 + row;
-      float o8[8];
+      float2 o8p[8];   // (even-channel, odd-channel) partial sums of the eight fold columns
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o8[j] = 0.f;
+      for (int j = 0; j < 8; ++j) o8p[j] = make_float2(0.f, 0.f);
 
       // ---- gate epilogue: chunk q holds gate channels [128 q, 128 q + 128) ---------------------
       // (loops deliberately NOT fully unrolled: the kernel must stay inside the instruction cache)
@@ -759,17 +821,17 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
           uint8_t* kblk = acts + (q * 2 + blk) * WL_A_BYTES + row * 128;   // K-block (64 channels) row
           const int ch0 = blk * 64 + hf * 32;                                // first channel inside the chunk
           const float* bT0 = s_b1 + q * 256 + ch0;
-          const float* wse0 = cw.wse + (q * 128 + ch0) * 8;
+          const float2* wse0 = reinterpret_cast<const float2*>(cw.wse) + (q * 128 + ch0) * 4;   // [channel pair][8]
           tmem_ld_wait();
           tmem_ld16(taddr + blk * 64 + 16, t1r);
           tmem_ld16(taddr + 128 + blk * 64 + 16, g1r);
-          gate_step<LAST>(t0r, g0r, bT0, wse0, kblk, hf * 2, row, o8);
+          gate_step2<LAST>(t0r, g0r, bT0, wse0, kblk, hf * 2, row, o8p);
           tmem_ld_wait();
           if (blk == 0) {
             tmem_ld16(taddr + 64, t0r);
             tmem_ld16(taddr + 128 + 64, g0r);
           }
-          gate_step<LAST>(t1r, g1r, bT0 + 16, wse0 + 128, kblk, hf * 2 + 1, row, o8);
+          gate_step2<LAST>(t1r, g1r, bT0 + 16, wse0 + 64, kblk, hf * 2 + 1, row, o8p);
           if (!LAST && q == 1 && blk == 0) {
             fence_proxy_async_smem();
             mbar_arrive(acts2_bar);
@@ -784,7 +846,10 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
         }
         if (tmr) t_e1 += clock64() - tw1;
       }
-      // fold accumulator: the two column halves of a row are combined in a fixed order (bit-reproducible)
+      // fold accumulator: even + odd channels, then the two column halves of a row, in a fixed order (bit-reproducible)
+      float o8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o8[j] = o8p[j].x + o8p[j].y;
       if (hf == 1) {
         *reinterpret_cast<float4*>(s_o8 + row * 8) = make_float4(o8[0], o8[1], o8[2], o8[3]);
         *reinterpret_cast<float4*>(s_o8 + row * 8 + 4) = make_float4(o8[4], o8[5], o8[6], o8[7]);
@@ -814,8 +879,8 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
         uint8_t* stg = acts + (hf * 2) * WL_A_BYTES + row * 128;      // this half's two 64-column blocks
         const uint32_t stg_addr = smem_base + WL_OFF_ACTS + (hf * 2) * WL_A_BYTES;
         const bool issuer = (we == hf * 4) && lane == 0;
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
+        auto resid_pass = [&](auto pass_tag) {
+          constexpr int pass = decltype(pass_tag)::value;
           if (pass == 1) {
             if (issuer) bulk_wait_read0();   // the hi store has finished reading the staging tile
             if (hf == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
@@ -827,14 +892,14 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
           for (int gp = 0; gp < 4; ++gp) {          // two groups of 16 columns per iteration
             tmem_ld_wait();
             tmem_ld16(taddr + (2 * gp + 1) * 16, r1);
-            resid_step(r0, s_b2 + hf * 128 + (2 * gp) * 16, stg, 2 * gp, row, pass);
+            resid_step2<pass>(r0, s_b2 + hf * 128 + (2 * gp) * 16, stg, 2 * gp, row);
             tmem_ld_wait();
             if (gp < 3) tmem_ld16(taddr + (2 * gp + 2) * 16, r0);
             else if (pass == 1) {
               tc_fence_before();
               mbar_arrive(epi2_bar);   // all TMEM reads of this tile are done
             }
-            resid_step(r1, s_b2 + hf * 128 + (2 * gp + 1) * 16, stg, 2 * gp + 1, row, pass);
+            resid_step2<pass>(r1, s_b2 + hf * 128 + (2 * gp + 1) * 16, stg, 2 * gp + 1, row);
           }
           fence_proxy_async_smem();
           if (hf == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
@@ -845,7 +910,9 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
             tma_store_4d(om, stg_addr + WL_A_BYTES, (hf * 2 + 1) * WL_BK, t0, pm ? r : b, pm ? b : 0);
             bulk_commit();
           }
-        }
+        };
+        resid_pass(std::integral_constant<int, 0>{});
+        resid_pass(std::integral_constant<int, 1>{});
         if (issuer) bulk_wait_read0();   // staging tile may be overwritten by the next gate epilogue
         if (tmr) t_e2 += clock64() - tw1;
       }
@@ -1064,8 +1131,9 @@ inline int tc_wn_layer(const TcPlan& pl, int layer, int dilation, bool last, int
                        bool first = false) {
   WnLayerParams p{};
   tc_fill_params(pl, p, layer, dilation, hcur, acc8, b1, b2, timing, flags);
-  WnLayerConst cw;
-  std::memcpy(cw.wse, wse_host, sizeof cw.wse);
+  WnLayerConst cw;   // packed-fold layout of the single-CTA kernel: [channel pair][column][even, odd]
+  for (int ch = 0; ch < WL_C; ++ch)
+    for (int cc = 0; cc < 8; ++cc) cw.wse[((ch >> 1) * 8 + cc) * 2 + (ch & 1)] = wse_host[ch * 8 + cc];
   const int grid = pl.n_tiles < pl.sm_count ? pl.n_tiles : pl.sm_count;
   if (first && (!pl.fold0 || last || dilation != 1)) fail(WG_ERR_INVALID, "start fold requested for a layer it does not apply to");
   if (last)
