@@ -115,14 +115,14 @@ def test_bf16_both_row_layouts_against_oracle(lib_built, monkeypatch, pm, B, T):
     eng.close()
 
 
-@pytest.mark.parametrize("B,T", [(2, 5), (1, 130), (3, 200)])
-def test_bf16_start_fold_against_oracle_and_unfolded_path(lib_built, monkeypatch, B, T):
+@pytest.mark.parametrize("C,B,T", [(256, 2, 5), (256, 1, 130), (256, 3, 200), (512, 2, 5), (512, 1, 140)])
+def test_bf16_start_fold_against_oracle_and_unfolded_path(lib_built, monkeypatch, C, B, T):
     """Phase-major path with the start conv folded into each flow's first WN layer (WG_FOLD0=1, default): h0 is never
     materialised; layer 0 reads the audio rows through a0_build_kernel. Must meet the BF16 bar, agree with the
     unfolded path (WG_FOLD0=0) far inside it, and give the right residual stream right after layer 0 (edges included:
     the tap rows l-1 / l+1 outside the utterance are the reference's zero padding of h0, bias and all)."""
     monkeypatch.setenv("WG_PM", "1")
-    hp = WaveGlowHParams()
+    hp = WaveGlowHParams(n_channels=C)
     w = generate_weights(hp, 1234, bias_std=0.05)
     mel, z = synthetic_inputs(900 + B * 10 + T, B, T, hp)
     taps = {}
@@ -140,7 +140,7 @@ def test_bf16_start_fold_against_oracle_and_unfolded_path(lib_built, monkeypatch
             h0s[fold, k, i] = h.cpu().numpy()
         eng.close()
         err, snr = np.abs(outs[fold] - ref).max(), snr_db(ref, outs[fold])
-        print(f"WG_FOLD0={fold} B={B} T={T}: max-abs {err:.3e} SNR {snr:.1f} dB, {launches} launches")
+        print(f"WG_FOLD0={fold} C={C} B={B} T={T}: max-abs {err:.3e} SNR {snr:.1f} dB, {launches} launches")
         assert err <= TOL_BF16_ABS and snr >= TOL_BF16_SNR
     assert np.abs(outs["1"] - outs["0"]).max() <= TOL_BF16_ABS
     for (k, i) in [(11, 0), (5, 0), (0, 0), (0, 1)]:

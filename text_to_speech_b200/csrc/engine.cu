@@ -74,7 +74,7 @@ struct wg_engine {
   __nv_bfloat16* W1 = nullptr;     // [n_flows*n_layers*2C, 3C+S]
   __nv_bfloat16* W2 = nullptr;     // [n_flows*n_layers*C, C]
   __nv_bfloat16* V = nullptr;      // [n_flows*n_layers*R*2C, Kup]: (Wup_r @ Wcond) per layer and upsample phase
-  // start-conv fold (phase-major bf16 path, C = 256): layer 0 of a flow consumes the audio rows directly
+  // start-conv fold (phase-major bf16 path): layer 0 of a flow consumes the audio rows directly
   __nv_bfloat16* W0 = nullptr;     // [n_flows*2C, 64]: per tap [Wstart@Win_tap hi | same | lo | bstart@Win_tap hi | lo | 0 0], chunk-packed rows
   __nv_bfloat16* H0 = nullptr;     // [n_flows*C, 64]: columns 48..63 = [Wstart hi | same | lo | bstart hi | lo | 0 0]
   bool fold0 = true;               // WG_FOLD0=0 keeps the materialised start conv (A/B and debugging)
@@ -362,7 +362,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
         if (e->profiling) e->ev_last.push_back(last ? 1 : 0);
         if (C == 512)
           e->launches += tc512_wn_layer(plan, m_acts512, k * c.n_layers + i, d, last, hcur, acc8, pm ? lw.b1_pm : lw.b1,
-                                        lw.b2, lw.wse_h.data(), st);
+                                        lw.b2, lw.wse_h.data(), st, fold0 && i == 0);
         else if (e->use_pair && !pm)
           e->launches += tc_wn_layer_pair(plan, pmaps, k * c.n_layers + i, d, last, hcur, acc8, lw.b1, lw.b2,
                                           lw.wse_h.data(), e->timing, e->dbg_flags, st);
@@ -526,7 +526,7 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
   e->layers.resize((size_t)F * NL);
   const int K1 = 3 * C + S;
   std::vector<__nv_bfloat16> w1all, w2all, w0all, h0all;
-  const bool build_fold0 = c.mode == WG_MODE_BF16 && C == 256 && NL > 1;
+  const bool build_fold0 = c.mode == WG_MODE_BF16 && NL > 1;
   if (c.mode == WG_MODE_BF16) {
     w1all.assign((size_t)F * NL * 2 * C * K1, f2bf(0.f));
     w2all.assign((size_t)F * NL * C * C, f2bf(0.f));

@@ -27,18 +27,21 @@ constexpr int W5_SMEM = W5_OFF_BARS + W5_NBARS * 8 + 16;
 static_assert(W5_SMEM <= 232448, "shared memory budget");
 
 struct Wn512Const {        // kernel-parameter bank
-  float wse[W5_C * 8];     // Wskip @ Wend, [512][8]
+  float wse[W5_C * 8];     // Wskip @ Wend, [256 channel pairs][8][even, odd]
 };
 
 // ------------------------------------------------------------------------------------------------
 // Gate kernel: chunk q of tile n is accumulated into TMEM region (q & 1); the epilogue drains a region while
 // the MMA fills the other one. Region x is filled for the f-th time after its (f-1)-th drain.
 // ------------------------------------------------------------------------------------------------
-template <bool LAST>
+// FIRST (layer 0 of a flow, phase-major): start-conv fold as in tc_wn_layer_kernel -- the 24 conv K-blocks are one
+// block a0[128 x 64] @ W0[64 x 1024] (three K = 16 MMAs per chunk).
+template <bool LAST, bool FIRST = false>
 __global__ void __launch_bounds__(WL_THREADS, 1)
 tc512_gate_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_cond,
                   const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_wc,
-                  const __grid_constant__ CUtensorMap map_acts, const WnLayerParams p,
+                  const __grid_constant__ CUtensorMap map_acts, const __grid_constant__ CUtensorMap map_a0,
+                  const __grid_constant__ CUtensorMap map_w0, const WnLayerParams p,
                   const __grid_constant__ Wn512Const cw) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
@@ -80,7 +83,8 @@ tc512_gate_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const bool pm = p.R > 1;
-  const int kb1 = W5_KB_CONV + p.n_cond_kb;
+  constexpr int KB_CONV = FIRST ? 1 : W5_KB_CONV;
+  const int kb1 = KB_CONV + p.n_cond_kb;
   auto tile_coords = [&](int tile, int& b, int& r, int& t0) {
     const int tt = tile % p.tiles_per_row, br = tile / p.tiles_per_row;
     r = br % p.R;
@@ -101,14 +105,17 @@ tc512_gate_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
           if (elect_one()) {
             mbar_expect_tx(full_bar(s), WL_STAGE_BYTES);
             const uint32_t a_dst = smem_base + s * WL_STAGE_BYTES;
-            if (kb < W5_KB_CONV) {
+            if (FIRST && kb == 0) {
+              tma_load_4d(a_dst, &map_a0, full_bar(s), 0, t0, pm ? r : b, pm ? b : 0);
+              tma_load_2d(a_dst + WL_A_BYTES, &map_w0, full_bar(s), 0, p.flow * 2 * W5_C + q * 256);
+            } else if (kb < KB_CONV) {
               const int tap = kb >> 3, cblk = kb & 7;
               const int rs = r + (tap - 1) * p.dilation;
               const int carry = (rs >= 0) ? rs / p.R : -((-rs + p.R - 1) / p.R);
               tma_load_4d(a_dst, &map_h, full_bar(s), cblk * WL_BK, t0 + carry, pm ? rs - carry * p.R : b, pm ? b : 0);
               tma_load_2d(a_dst + WL_A_BYTES, &map_w1, full_bar(s), kb * WL_BK, p.layer * 2 * W5_C + q * 256);
             } else {
-              const int kc = kb - W5_KB_CONV;
+              const int kc = kb - KB_CONV;
               tma_load_4d(a_dst, &map_cond, full_bar(s), kc * WL_BK, t0, pm ? 0 : b, pm ? b : 0);
               tma_load_2d(a_dst + WL_A_BYTES, &map_wc, full_bar(s), p.wc_col0 + kc * WL_BK,
                           p.wc_row0 + r * p.wc_rstride + q * 256);
@@ -138,8 +145,10 @@ tc512_gate_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
           const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + WL_A_BYTES);
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < WL_BK / 16; ++k)
+            for (int k = 0; k < WL_BK / 16; ++k) {
+              if (FIRST && kb == 0 && k == 3) break;   // columns 48..63 of a0: the residual operand (tc512_res_kernel)
               umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+            }
             tc_commit(empty_bar(s));
             if (kb == kb1 - 1) tc_commit(dfull_bar(x));
           }
@@ -162,9 +171,9 @@ tc512_gate_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
       tile_coords(tile, b, r, t0);
       const bool valid = (t0 + row) < p.T;
       const size_t m = (static_cast<size_t>(b) * p.R + r) * p.T + t0 + row;
-      float o8[8];
+      float2 o8p[8];   // (even-channel, odd-channel) partial sums of the fold columns (gate_step2)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o8[j] = 0.f;
+      for (int j = 0; j < 8; ++j) o8p[j] = make_float2(0.f, 0.f);
 #pragma unroll 1
       for (int q = 0; q < 4; ++q, ++fills) {
         const uint32_t x = fills & 1u, f = fills >> 1;
@@ -186,17 +195,17 @@ tc512_gate_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
           uint8_t* kblk = stg + blk * WL_A_BYTES + row * 128;
           const int ch0 = blk * 64 + hf * 32;
           const float* bT0 = s_b1 + q * 256 + ch0;
-          const float* wse0 = cw.wse + (q * 128 + ch0) * 8;
+          const float2* wse0 = reinterpret_cast<const float2*>(cw.wse) + (q * 128 + ch0) * 4;   // [channel pair][8]
           tmem_ld_wait();
           tmem_ld16(taddr + blk * 64 + 16, t1r);
           tmem_ld16(taddr + 128 + blk * 64 + 16, g1r);
-          gate_step<LAST>(t0r, g0r, bT0, wse0, kblk, hf * 2, row, o8);
+          gate_step2<LAST>(t0r, g0r, bT0, wse0, kblk, hf * 2, row, o8p);
           tmem_ld_wait();
           if (blk == 0) {
             tmem_ld16(taddr + 64, t0r);
             tmem_ld16(taddr + 128 + 64, g0r);
           }
-          gate_step<LAST>(t1r, g1r, bT0 + 16, wse0 + 128, kblk, hf * 2 + 1, row, o8);
+          gate_step2<LAST>(t1r, g1r, bT0 + 16, wse0 + 64, kblk, hf * 2 + 1, row, o8p);
         }
         tc_fence_before();
         mbar_arrive(drained_bar(x));
@@ -212,6 +221,9 @@ tc512_gate_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
         }
       }
       // fold accumulator (fixed combination order -> bit-reproducible)
+      float o8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o8[j] = o8p[j].x + o8p[j].y;
       if (hf == 1) {
         *reinterpret_cast<float4*>(s_o8 + row * 8) = make_float4(o8[0], o8[1], o8[2], o8[3]);
         *reinterpret_cast<float4*>(s_o8 + row * 8 + 4) = make_float4(o8[4], o8[5], o8[6], o8[7]);
@@ -243,10 +255,14 @@ tc512_gate_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
 // Stages per chunk: 8 x [acts block kb | W2 rows of the chunk, K-block kb], then 2 x [hi blocks] and 2 x [lo blocks]
 // of the chunk's four 64-channel blocks (identity adds).
 // ------------------------------------------------------------------------------------------------
+// FIRST: the residual operand h0 = [a(l), 1] @ [Wstart; bstart] comes from the a0 tile (one K = 16 MMA per chunk)
+// instead of four identity stages on (hi, lo).
+template <bool FIRST = false>
 __global__ void __launch_bounds__(WL_THREADS, 1)
 tc512_res_kernel(const __grid_constant__ CUtensorMap map_acts, const __grid_constant__ CUtensorMap map_h,
                  const __grid_constant__ CUtensorMap map_ho, const __grid_constant__ CUtensorMap map_lo,
-                 const __grid_constant__ CUtensorMap map_w2, const WnLayerParams p) {
+                 const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_a0,
+                 const __grid_constant__ CUtensorMap map_h0, const WnLayerParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
   float* s_b2 = reinterpret_cast<float*>(smem + W5_OFF_B);
@@ -306,6 +322,7 @@ tc512_res_kernel(const __grid_constant__ CUtensorMap map_acts, const __grid_cons
     t0 = tt * WL_BM;
   };
   constexpr int KB2 = W5_C / WL_BK;   // 8
+  constexpr int NSTEP = FIRST ? KB2 + 1 : KB2 + 4;
 
   if (warp == 0) {
     uint32_t it = 0;
@@ -314,12 +331,16 @@ tc512_res_kernel(const __grid_constant__ CUtensorMap map_acts, const __grid_cons
       tile_coords(tile, b, r, t0);
       const int c2 = pm ? r : b, c3 = pm ? b : 0;
       for (int nn = 0; nn < 2; ++nn) {
-        for (int step = 0; step < KB2 + 4; ++step, ++it) {
+        for (int step = 0; step < NSTEP; ++step, ++it) {
           const int s = it % W5_STAGES;
           mbar_wait(empty_bar(s), ((it / W5_STAGES) & 1) ^ 1);
           if (elect_one()) {
             const uint32_t dst = smem_base + s * WL_STAGE_BYTES;
-            if (step < KB2) {
+            if (FIRST && step == KB2) {
+              mbar_expect_tx(full_bar(s), WL_STAGE_BYTES);
+              tma_load_4d(dst, &map_a0, full_bar(s), 0, t0, c2, c3);
+              tma_load_2d(dst + WL_A_BYTES, &map_h0, full_bar(s), 0, p.flow * W5_C + nn * 256);
+            } else if (step < KB2) {
               mbar_expect_tx(full_bar(s), WL_STAGE_BYTES);
               tma_load_4d(dst, &map_acts, full_bar(s), step * WL_BK, t0, c2, c3);
               tma_load_2d(dst + WL_A_BYTES, &map_w2, full_bar(s), step * WL_BK, p.layer * W5_C + nn * 256);
@@ -349,13 +370,15 @@ tc512_res_kernel(const __grid_constant__ CUtensorMap map_acts, const __grid_cons
           tc_fence_after();
         }
         const uint32_t d_tmem = tmem_base + 256u * nn;
-        for (int step = 0; step < KB2 + 4; ++step, ++it) {
+        for (int step = 0; step < NSTEP; ++step, ++it) {
           const int s = it % W5_STAGES;
           mbar_wait(full_bar(s), (it / W5_STAGES) & 1);
           tc_fence_after();
           const uint32_t st_addr = smem_base + s * WL_STAGE_BYTES;
           if (elect_one()) {
-            if (step < KB2) {
+            if (FIRST && step == KB2) {
+              umma_bf16(d_tmem, umma_desc_sw128(st_addr) + 6, umma_desc_sw128(st_addr + WL_A_BYTES) + 6, idesc, 1u);
+            } else if (step < KB2) {
               const uint64_t adesc = umma_desc_sw128(st_addr), bdesc = umma_desc_sw128(st_addr + WL_A_BYTES);
 #pragma unroll
               for (int k = 0; k < WL_BK / 16; ++k)
@@ -372,7 +395,7 @@ tc512_res_kernel(const __grid_constant__ CUtensorMap map_acts, const __grid_cons
               }
             }
             tc_commit(empty_bar(s));
-            if (step == KB2 + 3) tc_commit(dfull_bar(nn));
+            if (step == NSTEP - 1) tc_commit(dfull_bar(nn));
           }
           __syncwarp();
         }
@@ -443,25 +466,37 @@ tc512_res_kernel(const __grid_constant__ CUtensorMap map_acts, const __grid_cons
 inline void tc512_init() {
   WG_CK(cudaFuncSetAttribute(tc512_gate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, W5_SMEM));
   WG_CK(cudaFuncSetAttribute(tc512_gate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, W5_SMEM));
-  WG_CK(cudaFuncSetAttribute(tc512_res_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W5_SMEM));
+  WG_CK(cudaFuncSetAttribute(tc512_gate_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, W5_SMEM));
+  WG_CK(cudaFuncSetAttribute(tc512_res_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, W5_SMEM));
+  WG_CK(cudaFuncSetAttribute(tc512_res_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, W5_SMEM));
 }
 
 // one WN layer of WaveGlow-512: gate kernel, then (unless it is the last layer of the flow) the residual kernel
 inline int tc512_wn_layer(const TcPlan& pl, const CUtensorMap& m_acts, int layer, int dilation, bool last, int hcur,
-                          float* acc8, const float* b1, const float* b2, const float* wse_host, cudaStream_t st) {
+                          float* acc8, const float* b1, const float* b2, const float* wse_host, cudaStream_t st,
+                          bool first = false) {
   WnLayerParams p{};
   tc_fill_params(pl, p, layer, dilation, hcur, acc8, b1, b2, nullptr, 0);
   Wn512Const cw;
-  std::memcpy(cw.wse, wse_host, sizeof cw.wse);
+  for (int ch = 0; ch < W5_C; ++ch)   // packed-fold layout: [channel pair][column][even, odd]
+    for (int cc = 0; cc < 8; ++cc) cw.wse[((ch >> 1) * 8 + cc) * 2 + (ch & 1)] = wse_host[ch * 8 + cc];
   const int grid = pl.n_tiles < pl.sm_count ? pl.n_tiles : pl.sm_count;
+  if (first && (!pl.fold0 || last || dilation != 1)) fail(WG_ERR_INVALID, "start fold requested for a layer it does not apply to");
   if (last) {
-    tc512_gate_kernel<true><<<grid, WL_THREADS, W5_SMEM, st>>>(pl.m4_h[hcur], pl.m4_cond, pl.m_w1, pl.m_wc, m_acts, p, cw);
+    tc512_gate_kernel<true><<<grid, WL_THREADS, W5_SMEM, st>>>(pl.m4_h[hcur], pl.m4_cond, pl.m_w1, pl.m_wc, m_acts, pl.m4_a0, pl.m_w0, p, cw);
     WG_CK(cudaGetLastError());
     return 1;
   }
-  tc512_gate_kernel<false><<<grid, WL_THREADS, W5_SMEM, st>>>(pl.m4_h[hcur], pl.m4_cond, pl.m_w1, pl.m_wc, m_acts, p, cw);
+  if (first) {
+    tc512_gate_kernel<false, true><<<grid, WL_THREADS, W5_SMEM, st>>>(pl.m4_h[hcur], pl.m4_cond, pl.m_w1, pl.m_wc, m_acts, pl.m4_a0, pl.m_w0, p, cw);
+    WG_CK(cudaGetLastError());
+    tc512_res_kernel<true><<<grid, WL_THREADS, W5_SMEM, st>>>(m_acts, pl.m4_h[hcur], pl.m4_h[hcur ^ 1], pl.m4_lo, pl.m_w2, pl.m4_a0, pl.m_h0, p);
+    WG_CK(cudaGetLastError());
+    return 2;
+  }
+  tc512_gate_kernel<false><<<grid, WL_THREADS, W5_SMEM, st>>>(pl.m4_h[hcur], pl.m4_cond, pl.m_w1, pl.m_wc, m_acts, pl.m4_a0, pl.m_w0, p, cw);
   WG_CK(cudaGetLastError());
-  tc512_res_kernel<<<grid, WL_THREADS, W5_SMEM, st>>>(m_acts, pl.m4_h[hcur], pl.m4_h[hcur ^ 1], pl.m4_lo, pl.m_w2, p);
+  tc512_res_kernel<false><<<grid, WL_THREADS, W5_SMEM, st>>>(m_acts, pl.m4_h[hcur], pl.m4_h[hcur ^ 1], pl.m4_lo, pl.m_w2, pl.m4_a0, pl.m_h0, p);
   WG_CK(cudaGetLastError());
   return 2;
 }

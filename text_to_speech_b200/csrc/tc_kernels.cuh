@@ -1081,7 +1081,7 @@ inline void tc_prepare(TcPlan& pl, int sm_count, int B, int T, int L, int C, int
     make_map_4d(&pl.m4_cond, aup16, B, 1, T, Kup, WL_BM);
     make_map_2d(&pl.m_wc, V, (uint64_t)n_layers_total * R * 2 * C, Kup, 256);
     pl.n_cond_kb = Kup / WL_BK; pl.wc_col0 = 0; pl.wc_rows_per_layer = R * 2 * C; pl.wc_rstride = 2 * C;
-    pl.fold0 = a0 && W0 && H0 && n_flows > 0 && C == WL_C;
+    pl.fold0 = a0 && W0 && H0 && n_flows > 0;
     if (pl.fold0) {
       pl.n_layers = n_layers_total / n_flows;
       make_map_4d(&pl.m4_a0, a0, B, R, T, WL_BK, WL_BM);
