@@ -105,10 +105,11 @@ int wg_last_launch_count(wg_handle h);
 
 /* ---- test / profiling hooks (used by tests/ and bench.py only) ------------------------------ */
 
-/* Per-kernel device timing: when enabled, wg_infer brackets every WN-layer launch (the dominant
- * kernel: tc_wn_layer_kernel in BF16 mode, the in-conv+gate GEMM in FP32 mode) with CUDA events on
- * the caller's stream. wg_profile_read synchronises those events and returns the summed duration
- * (ms) and the number of launches recorded since the last read. */
+/* Per-kernel device timing of the dominant kernel with CUDA events on the caller's stream: in BF16 mode
+ * one event pair per flow around its n_layers back-to-back WN-layer launches (tc_wn_layer_kernel /
+ * tc512_*; nothing else is launched inside the bracket), in FP32 mode one pair per in-conv+gate GEMM.
+ * wg_profile_read synchronises those events and returns the summed duration (ms) and the number of
+ * layer launches it covers since the last read. */
 int wg_profile_enable(wg_handle h, int32_t enable);
 int wg_profile_read(wg_handle h, double* layer_ms_sum, int32_t* layer_launches);
 

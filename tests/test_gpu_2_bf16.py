@@ -344,3 +344,26 @@ def test_concurrent_wg_infer_on_two_streams(lib_built):
     for j in jobs:
         assert j["rc"] == [0] * 5
         assert np.array_equal(j["out"].cpu().numpy(), j["serial"])
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_profile_hooks_count_every_layer_launch(lib_built, mode):
+    """wg_profile_enable / wg_profile_read (bench.py's roofline timing): one infer = n_flows * n_layers layer launches,
+    a positive device time, and the counters re-arm after a read."""
+    hp = WaveGlowHParams()
+    eng = _engine(hp, generate_weights(hp, 1234), mode=mode)
+    mel, z = synthetic_inputs(3, 2, 9, hp)
+    md, zd = torch.from_numpy(mel).cuda(), torch.from_numpy(z).cuda()
+    eng.infer_device(md, zd, 0.6)
+    eng.profile_enable(True)
+    for _ in range(2):
+        eng.infer_device(md, zd, 0.6)
+    ms, n = eng.profile_read()
+    assert n == 2 * hp.n_flows * hp.n_layers and ms > 0.0
+    eng.infer_device(md, zd, 0.6)
+    ms1, n1 = eng.profile_read()
+    assert n1 == hp.n_flows * hp.n_layers and 0.0 < ms1 < ms
+    eng.profile_enable(False)
+    eng.infer_device(md, zd, 0.6)
+    assert eng.profile_read()[1] == 0
+    eng.close()

@@ -96,7 +96,7 @@ struct wg_engine {
   int dbg_flags = 0;                      // WG_DEBUG_FLAGS (see WnLayerParams::flags)
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;   // pairs: [2i] start, [2i+1] stop
-  std::vector<char> ev_last;          // per pair: 1 = last layer of a flow
+  std::vector<int> ev_count;          // per pair: layer launches bracketed by it
   size_t ev_used = 0;
 };
 
@@ -347,6 +347,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
         g.W = lw.Wcat; g.bias = lw.bcat; g.M = M; g.N = 2 * C; g.L = L;
         g.out0 = acts; g.ld0 = C;
         prof_mark();
+        if (e->profiling) e->ev_count.push_back(1);
         launch_gemm<EPI_GATE>(e, g, st);
         prof_mark();
         // res/skip 1x1 + residual add + skip accumulation (:129-139)
@@ -358,8 +359,13 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
         r.res_cols = last ? 0 : C; r.skip_init = (i == 0);
         launch_gemm<EPI_RES_SKIP>(e, r, st);
       } else {
-        prof_mark();
-        if (e->profiling) e->ev_last.push_back(last ? 1 : 0);
+        // bf16: ONE event pair per flow around its n_layers back-to-back layer launches (an event pair per launch
+        // costs ~3 % of the step it is meant to measure)
+        if (i == 0) {
+          prof_mark();
+          if (e->profiling) e->ev_count.push_back(0);
+        }
+        if (e->profiling) e->ev_count.back() += 1;
         if (C == 512)
           e->launches += tc512_wn_layer(plan, m_acts512, k * c.n_layers + i, d, last, hcur, acc8, pm ? lw.b1_pm : lw.b1,
                                         lw.b2, lw.wse_h.data(), st, fold0 && i == 0);
@@ -369,7 +375,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
         else
           e->launches += tc_wn_layer(plan, k * c.n_layers + i, d, last, hcur, acc8, pm ? lw.b1_pm : lw.b1, lw.b2,
                                      lw.wse_h.data(), e->timing, e->dbg_flags, st, fold0 && i == 0);
-        prof_mark();
+        if (last || (k == stop_flow && i == stop_layer)) prof_mark();
         if (!last) hcur ^= 1;
       }
       if (k == stop_flow && i == stop_layer) {
@@ -885,7 +891,7 @@ int wg_profile_enable(wg_handle h, int32_t enable) {
   if (!h) return WG_ERR_INVALID;
   h->profiling = enable != 0;
   h->ev_used = 0;
-  h->ev_last.clear();
+  h->ev_count.clear();
   return WG_OK;
 }
 
@@ -900,19 +906,11 @@ int wg_profile_read(wg_handle h, double* layer_ms_sum, int32_t* layer_launches) 
       sum += ms;
     }
     *layer_ms_sum = sum;
-    *layer_launches = (int32_t)(h->ev_used / 2);
-    if (std::getenv("WG_PROFILE_SPLIT")) {   // development aid: last-layer launches vs the others
-      double s_last = 0, s_other = 0; int n_last = 0, n_other = 0;
-      for (size_t i = 0; i + 1 < h->ev_used && i / 2 < h->ev_last.size(); i += 2) {
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, h->ev_pool[i], h->ev_pool[i + 1]);
-        if (h->ev_last[i / 2]) { s_last += ms; ++n_last; } else { s_other += ms; ++n_other; }
-      }
-      fprintf(stderr, "wg profile split: last-layer launches %d avg %.1f us | other layers %d avg %.1f us\n", n_last,
-              n_last ? 1e3 * s_last / n_last : 0.0, n_other, n_other ? 1e3 * s_other / n_other : 0.0);
-    }
+    int n = 0;
+    for (size_t i = 0; i < h->ev_used / 2 && i < h->ev_count.size(); ++i) n += h->ev_count[i];
+    *layer_launches = n;
     h->ev_used = 0;
-    h->ev_last.clear();
+    h->ev_count.clear();
   });
 }
 

@@ -178,8 +178,6 @@ def stage_time():
         for _ in range(2):
             eng.infer_device(md, zd, 0.6, out=out)
         torch.cuda.synchronize()
-        if os.environ.get("WG_PROFILE_SPLIT"):
-            eng.profile_enable(True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         n = 3
@@ -188,8 +186,6 @@ def stage_time():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / n
-        if os.environ.get("WG_PROFILE_SPLIT"):
-            eng.profile_read()
         flop = 20308852.0 * B * T * 256
         print(f"time {mode} B={B} T={T}: {ms:.2f} ms/infer, {B*T*256/ms*1e3/1e6:.2f} Msamples/s, {flop/ms/1e9:.1f} TFLOP/s algorithmic")
         if mode == "bf16" and os.environ.get("WG_LAYER_TIMING") == "1":
