@@ -167,18 +167,28 @@ struct Ws {  // workspace carving for one (B, T)
   size_t total = 0;
 };
 
-// phase-major layout pays when 128-frame tiles are reasonably full
-bool use_pm(const wg_engine* e, int T) {
+// rows between two utterances inside a phase block: >= max dilation / R frames, all zero (RowGeom)
+int pm_gap(const wg_engine* e) { return ((1 << (e->cfg.n_layers - 1)) + e->R - 1) / e->R; }
+
+// Row layout of the bf16 path, chosen per call by a wave count: phase-major tiles cost 17 + 17 + 6 K-blocks (rank-320
+// conditioning, no spect) but come in multiples of R = 32 per 128 frames of the joint sequence; position-major tiles cost
+// 22 + 22 + 6 and need the materialised spect. They only differ in speed -- both meet the same parity bar -- and only
+// small inputs (a few hundred tiles) ever pick position-major. WG_PM=0/1 forces one.
+bool use_pm(const wg_engine* e, int B, int T) {
   if (e->cfg.mode != WG_MODE_BF16 || !e->V) return false;
   if (e->pm_policy == 0) return false;
   if (e->pm_policy == 1) return true;
-  const int tiles = (T + 127) / 128;
-  return T * 10 >= tiles * 128 * 7;
+  const long sm = e->sm_count > 0 ? e->sm_count : 148;
+  const long tiles_pm = (long)e->R * (((long)B * (T + pm_gap(e)) + 127) / 128);
+  const long tiles_pos = (long)B * (((long)T * e->R + 127) / 128);
+  const long cost_pm = ((tiles_pm + sm - 1) / sm) * 40, cost_pos = ((tiles_pos + sm - 1) / sm) * 50 + 2;
+  return cost_pm <= cost_pos;
 }
 
 Ws carve(const wg_engine* e, int B, int T) {
   Ws w;
-  const size_t M = (size_t)B * T * e->R;
+  const bool pm = use_pm(e, B, T);
+  const size_t M = pm ? (size_t)B * (T + pm_gap(e)) * e->R : (size_t)B * T * e->R;   // internal rows (gap rows included)
   size_t off = 0;
   auto take = [&](size_t bytes) {
     size_t o = off;
@@ -194,13 +204,13 @@ Ws carve(const wg_engine* e, int B, int T) {
     w.acts = take(M * e->C * 4);
     w.skip = take(M * e->C * 4);
   } else {
-    if (!use_pm(e, T)) w.spect16 = take(M * e->S * 2);
+    if (!pm) w.spect16 = take(M * e->S * 2);
     w.h16a = take(M * e->C * 2);
     w.h16b = take(M * e->C * 2);
     w.hlo = take(M * e->C * 2);
-    w.aup16 = take((size_t)B * T * e->Kup * 2);
+    w.aup16 = take((pm ? (size_t)B * (T + pm_gap(e)) : (size_t)B * T) * e->Kup * 2);
     if (e->C == 512) w.acts16 = take(M * e->C * 2);   // WaveGlow-512: acts travel between the gate and residual kernels
-    if (e->W0 && use_pm(e, T)) w.a0 = take(M * 64 * 2);   // start fold: A operand of each flow's first layer
+    if (e->W0 && pm) w.a0 = take(M * 64 * 2);   // start fold: A operand of each flow's first layer
   }
   w.total = off;
   return w;
@@ -208,7 +218,7 @@ Ws carve(const wg_engine* e, int B, int T) {
 
 void check_shape(const wg_engine* e, int B, int T) {
   if (B <= 0 || T <= 0) fail(WG_ERR_INVALID, "B and T must be positive (got B=%d, T=%d)", B, T);
-  const double M = (double)B * T * e->R;
+  const double M = (double)B * (T + (e->cfg.mode == WG_MODE_BF16 ? pm_gap(e) : 0)) * e->R;   // internal rows, gap rows included
   if (M * std::max(e->S, e->C) > 2.0e9) fail(WG_ERR_INVALID, "B*T too large (B=%d, T=%d)", B, T);
 }
 
@@ -244,8 +254,10 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
   const wg_config& c = e->cfg;
   const int C = e->C, S = e->S, R = e->R, L = T * R, M = B * L;
   const bool bf16 = c.mode == WG_MODE_BF16;
-  const bool pm = use_pm(e, T);
-  const int geomR = pm ? R : 1, geomT = pm ? T : L;
+  const bool pm = use_pm(e, B, T);
+  // internal row geometry of the bf16 buffers (fp32 mode: position-major)
+  const RowGeom geo = pm ? RowGeom{R, T, T + pm_gap(e), B} : RowGeom{1, L, L, B};
+  const int Mi = geo.rows();   // internal rows (== M unless phase-major: gap rows)
   float* h32 = bf16 ? nullptr : reinterpret_cast<float*>(base + w.h32);
   float* acc8 = reinterpret_cast<float*>(base + w.acc8);
   float* audio[2] = {reinterpret_cast<float*>(base + w.audio0), reinterpret_cast<float*>(base + w.audio1)};
@@ -278,9 +290,9 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
   } else {
     tc_prepare(plan, e->sm_count, B, T, L, C, S, e->Kup, c.n_mel_channels, c.n_flows * c.n_layers,
                e->Wup16, R * S, e->W1, e->W2, aup16, spect16, h16[0], h16[1], hlo, pm, R, e->V,
-               fold0 ? a0 : nullptr, e->W0, e->H0, c.n_flows);
+               fold0 ? a0 : nullptr, e->W0, e->H0, c.n_flows, pm ? pm_gap(e) : 0);
     if (e->use_pair && !pm && C == 256) tc_pair_prepare(pmaps, c.n_flows * c.n_layers, C, S, e->W1, e->W2);
-    if (C == 512) make_map_4d(&m_acts512, acts16, pm ? B : 1, pm ? (uint64_t)R : (uint64_t)B, plan.Trows, C, WL_BM);
+    if (C == 512) make_map_4d(&m_acts512, acts16, 1, pm ? (uint64_t)R : (uint64_t)B, plan.Trows, C, WL_BM);
     e->launches += tc_upsample(plan, mel, e->bup, st);
   }
 
@@ -289,9 +301,9 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
   int cur = 0, z_off = 0, hcur = 0;
   {
     BoundaryArgs a{};
-    a.R = geomR; a.T = geomT;
+    a.R = geo.R; a.T = geo.T; a.Tp = geo.Tp; a.B = geo.B;
     a.first = 1; a.z = zz; a.n_group = c.n_group; a.z_off = 0; a.n_inject = e->flows[F - 1].n_rem;
-    a.sigma = sigma; a.audio_out = audio[cur]; a.M = M; a.C = C;
+    a.sigma = sigma; a.audio_out = audio[cur]; a.M = Mi; a.C = C;
     a.Wstart = fold0 ? nullptr : e->flows[F - 1].Wstart; a.bstart = e->flows[F - 1].bstart;
     a.n_half_next = e->flows[F - 1].n_half; a.h32 = h32; a.h16 = bf16 ? h16[hcur] : nullptr; a.hlo = bf16 ? hlo : nullptr;
     if (bf16) { a.acc8_rearm = acc8; std::memcpy(a.acc8_init, e->flows[F - 1].bse8, sizeof a.acc8_init); }
@@ -299,7 +311,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
     z_off = a.n_inject;
   }
   auto launch_a0 = [&](const float* audio_rows, int n_half) {
-    a0_build_kernel<<<(unsigned)(((size_t)M * 4 + 255) / 256), 256, 0, st>>>(audio_rows, a0, M, geomR, geomT, n_half);
+    a0_build_kernel<<<(unsigned)(((size_t)Mi * 4 + 255) / 256), 256, 0, st>>>(audio_rows, a0, geo, n_half);
     CK(cudaGetLastError());
     e->launches++;
   };
@@ -318,13 +330,13 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
   auto dump = [&](void) {
     if (h_out && !bf16) CK(cudaMemcpyAsync(h_out, h32, (size_t)M * C * 4, cudaMemcpyDeviceToDevice, st));
     if (h_out && bf16) {
-      const size_t n = (size_t)M * C;
-      hilo_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h16[hcur], hlo, h_out, (size_t)M, C, geomR, geomT);
+      const size_t n = (size_t)Mi * C;
+      hilo_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h16[hcur], hlo, h_out, geo, C);
       CK(cudaGetLastError());
     }
     if (acc_out) {
-      const size_t n = (size_t)M * 8;
-      unpermute_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc8, acc_out, (size_t)M, 8, geomR, geomT);
+      const size_t n = (size_t)Mi * 8;
+      unpermute_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc8, acc_out, geo, 8);
       CK(cudaGetLastError());
     }
   };
@@ -394,9 +406,9 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
     }
     // coupling inverse + W^-1 + early re-injection + next start conv (:278-304)
     BoundaryArgs a{};
-    a.R = geomR; a.T = geomT;
+    a.R = geo.R; a.T = geo.T; a.Tp = geo.Tp; a.B = geo.B;
     a.first = 0; a.acc8 = acc8; a.audio_in = audio[cur]; a.z = zz; a.n_group = c.n_group;
-    a.sigma = sigma; a.c_in = 2 * fw.n_half; a.M = M; a.C = C;
+    a.sigma = sigma; a.c_in = 2 * fw.n_half; a.M = Mi; a.C = C;
     std::memcpy(a.winv, fw.winv, sizeof a.winv);
     const bool early = (k % c.n_early_every == 0) && k > 0;
     a.n_inject = early ? c.n_early_size : 0;
@@ -941,7 +953,7 @@ int wg_debug_get_spect(wg_handle h, int32_t B, int32_t T, const void* workspace,
   return guarded(h, [&] {
     check_shape(h, B, T);
     if (!workspace || !spect_out) fail(WG_ERR_INVALID, "NULL argument");
-    if (use_pm(h, T)) fail(WG_ERR_UNSUPPORTED, "the phase-major path does not materialise spect (set WG_PM=0 to inspect it)");
+    if (use_pm(h, B, T)) fail(WG_ERR_UNSUPPORTED, "the phase-major path does not materialise spect (set WG_PM=0 to inspect it)");
     const Ws w = carve(h, B, T);
     const size_t n = (size_t)B * T * h->R * h->S;
     cudaStream_t st = static_cast<cudaStream_t>(stream);

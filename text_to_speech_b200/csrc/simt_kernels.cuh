@@ -200,6 +200,29 @@ end_conv_kernel(const float* __restrict__ skip, const float* __restrict__ Wend /
 // `first` replaces the three first steps by audio = sigma * z[:, :n_rem] (waveglow_arch.py:264-275).
 // The last flow writes the [M, 8] audio straight into the output waveform ([B, 8 L], :306).
 // ------------------------------------------------------------------------------------------------
+// Internal row order of the bf16-path buffers. R = 1: position-major (Tp = T = L, row = b*L + l). R = 32: phase-major
+// with all utterances of a phase in ONE row sequence, Tp = T + gap rows apart: row = (r*B + b)*Tp + t. The gap rows
+// (t >= T) are kept ZERO, so a dilated-conv tap that runs off an utterance reads the reference's zero 'same' padding
+// (gap >= max dilation / R frames) and 128-row tiles may span utterances (no ragged last tile per utterance).
+struct RowGeom {
+  int R, T, Tp, B;
+  __host__ __device__ int rows() const { return R * B * Tp; }
+  // internal row -> (b, r, t); returns false for a gap row
+  __device__ bool decode(int m, int& b, int& r, int& t) const {
+    const int per_r = B * Tp;
+    r = m / per_r;
+    const int rem = m - r * per_r;
+    b = rem / Tp;
+    t = rem - b * Tp;
+    return t < T;
+  }
+  __device__ size_t internal(int b, int l) const {   // position l = R*t + r of utterance b
+    const int t = l / R, r = l - t * R;
+    return (static_cast<size_t>(r) * B + b) * Tp + t;
+  }
+  __device__ size_t position_major(int b, int r, int t) const { return static_cast<size_t>(b) * R * T + static_cast<size_t>(t) * R + r; }
+};
+
 struct BoundaryArgs {
   const float* acc8;      // [M,8]: cols [0,n_half) = b, [n_half, 2 n_half) = log s   (null when first)
   const float* audio_in;  // [M,8] (c_in channels used)
@@ -225,9 +248,10 @@ struct BoundaryArgs {
   // this flow's value has been consumed
   float* acc8_rearm;      // [M,8] or null
   float acc8_init[8];
-  // Row geometry of the internal buffers: position l = R*t + r of utterance b lives at row (b*R + r)*T + t
-  // (R = 1: position-major). z and the final waveform are always position-major.
-  int R, T;
+  // Row geometry of the internal buffers (RowGeom below): position l = R*t + r of utterance b lives at row
+  // (r*B + b)*Tp + t; rows with t >= T are zero gap rows. z and the final waveform are always position-major.
+  // M counts INTERNAL rows (R*B*Tp).
+  int R, T, Tp, B;
   int final_out;          // audio_out is the caller's waveform buffer (position-major)
 };
 
@@ -236,18 +260,22 @@ constexpr int FB_ROWS = 64, FB_THREADS = 256;
 __global__ void __launch_bounds__(FB_THREADS)
 flow_boundary_kernel(const __grid_constant__ BoundaryArgs a) {
   __shared__ float s_a0[FB_ROWS][4];
+  __shared__ int s_gap[FB_ROWS];
   const int m0 = blockIdx.x * FB_ROWS;
   const int tid = threadIdx.x;
+  const RowGeom geo{a.R, a.T, a.Tp, a.B};
   if (tid < FB_ROWS) {
     const int m = m0 + tid;
-    if (m < a.M) {
-      size_t prow = m;   // position-major row of this internal row
-      if (a.R > 1) {
-        const int per_b = a.R * a.T;
-        const int b = m / per_b, rem = m - b * per_b;
-        const int r = rem / a.T, t = rem - r * a.T;
-        prow = static_cast<size_t>(b) * per_b + static_cast<size_t>(t) * a.R + r;
+    s_gap[tid] = 0;
+    int gb, gr, gt;
+    if (m < a.M && !geo.decode(m, gb, gr, gt)) {
+      s_gap[tid] = 1;       // gap row: stays zero in every buffer (the start conv below writes h = 0, no bias)
+      if (!a.final_out) {   // (the caller's waveform buffer has no gap rows)
+        *reinterpret_cast<float4*>(a.audio_out + (size_t)m * 8) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(a.audio_out + (size_t)m * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
+    } else if (m < a.M) {
+      const size_t prow = geo.position_major(gb, gr, gt);   // position-major row of this internal row
       float x[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) x[j] = 0.f;
@@ -303,7 +331,11 @@ flow_boundary_kernel(const __grid_constant__ BoundaryArgs a) {
       const float4 b1 = *reinterpret_cast<const float4*>(a.bstart + c8 + 4);
       v[0] = b0.x; v[1] = b0.y; v[2] = b0.z; v[3] = b0.w; v[4] = b1.x; v[5] = b1.y; v[6] = b1.z; v[7] = b1.w;
     }
-    for (int j = 0; j < a.n_half_next; ++j) {
+    if (s_gap[r]) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    }
+    for (int j = 0; j < (s_gap[r] ? 0 : a.n_half_next); ++j) {
       const float x = s_a0[r][j];
       const float4 w0 = *reinterpret_cast<const float4*>(a.Wstart + (size_t)j * a.C + c8);
       const float4 w1 = *reinterpret_cast<const float4*>(a.Wstart + (size_t)j * a.C + c8 + 4);
@@ -342,23 +374,21 @@ flow_boundary_kernel(const __grid_constant__ BoundaryArgs a) {
 // 16-column groups -- taps l-1, l, l+1 and the residual operand l -- each
 //   [a_hi(4) | a_lo(4) | a_hi(4) | 1 | 1 | 0 | 0],   a = a_hi + a_lo (bf16 split of the fp32 audio),
 // to be multiplied with [G_hi; G_hi; G_lo; g_hi; g_lo] (three-product split, fp32-grade accuracy).
-// One thread per (row, group); rows follow the internal (b, r, t) order, position l = R*t + r.
+// One thread per (row, group); rows follow the internal order (RowGeom); gap rows are all zero.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-a0_build_kernel(const float* __restrict__ audio, __nv_bfloat16* __restrict__ a0, int M, int R, int T, int n_half) {
+a0_build_kernel(const float* __restrict__ audio, __nv_bfloat16* __restrict__ a0, const RowGeom geo, int n_half) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= M * 4) return;
+  if (idx >= geo.rows() * 4) return;
   const int m = idx >> 2, g = idx & 3;
-  const int per_b = R * T;
-  const int b = m / per_b, rem = m - b * per_b;
-  const int r = rem / T, t = rem - r * T;
-  const int l = t * R + r + (g < 3 ? g - 1 : 0);
+  int b, r, t;
+  const bool valid = geo.decode(m, b, r, t);
+  const int l = t * geo.R + r + (g < 3 ? g - 1 : 0);
   uint32_t w[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) w[j] = 0u;
-  if (l >= 0 && l < per_b) {
-    const int ts = l / R, rs = l - ts * R;
-    const size_t src = static_cast<size_t>(b) * per_b + static_cast<size_t>(rs) * T + ts;
+  if (valid && l >= 0 && l < geo.R * geo.T) {
+    const size_t src = geo.internal(b, l);
     const float4 v4 = *reinterpret_cast<const float4*>(audio + src * 8);
     float v[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll

@@ -169,7 +169,7 @@ tc512_gate_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       int b, r, t0;
       tile_coords(tile, b, r, t0);
-      const bool valid = (t0 + row) < p.T;
+      const bool valid = (t0 + row) < p.T && (p.Tp == 0 || (t0 + row) % p.Tp < p.Tv);
       const size_t m = (static_cast<size_t>(b) * p.R + r) * p.T + t0 + row;
       float2 o8p[8];   // (even-channel, odd-channel) partial sums of the fold columns (gate_step2)
 #pragma unroll
@@ -415,6 +415,7 @@ tc512_res_kernel(const __grid_constant__ CUtensorMap map_acts, const __grid_cons
       int b, r, t0;
       tile_coords(tile, b, r, t0);
       const int c2 = pm ? r : b, c3 = pm ? b : 0;
+      const bool valid = (t0 + row) < p.T && (p.Tp == 0 || (t0 + row) % p.Tp < p.Tv);   // gap rows are stored as zeros
 #pragma unroll 1
       for (int nn = 0; nn < 2; ++nn) {
         mbar_wait(dfull_bar(nn), n & 1u);
@@ -432,14 +433,14 @@ tc512_res_kernel(const __grid_constant__ CUtensorMap map_acts, const __grid_cons
           for (int gp = 0; gp < 4; ++gp) {
             tmem_ld_wait();
             tmem_ld16(taddr + (2 * gp + 1) * 16, r1);
-            resid_step(r0, s_b2 + nn * 256 + hf * 128 + (2 * gp) * 16, stg, 2 * gp, row, pass);
+            resid_step(r0, s_b2 + nn * 256 + hf * 128 + (2 * gp) * 16, stg, 2 * gp, row, pass, valid);
             tmem_ld_wait();
             if (gp < 3) tmem_ld16(taddr + (2 * gp + 2) * 16, r0);
             else if (pass == 1) {
               tc_fence_before();
               mbar_arrive(drained_bar(nn));
             }
-            resid_step(r1, s_b2 + nn * 256 + hf * 128 + (2 * gp + 1) * 16, stg, 2 * gp + 1, row, pass);
+            resid_step(r1, s_b2 + nn * 256 + hf * 128 + (2 * gp + 1) * 16, stg, 2 * gp + 1, row, pass, valid);
           }
           fence_proxy_async_smem();
           if (hf == 0) asm volatile("bar.sync 3, 128;" ::: "memory");

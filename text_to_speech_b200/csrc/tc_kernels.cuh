@@ -22,6 +22,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "simt_kernels.cuh"
 
 namespace wg {
 
@@ -341,6 +342,7 @@ struct WnLayerParams {
   int wc_col0;          // first K column of the conditioning weights inside map_wc
   int wc_row0;          // first N row of this layer's conditioning weights inside map_wc
   int wc_rstride;       // extra N rows per phase (0 or 512)
+  int Tp, Tv;     // gap layout (phase-major): row t of a phase block is valid iff (t % Tp) < Tv; Tp = 0: every row < T is valid
   int layer;      // row block in the stacked W1 / W2 matrices
   int flow;       // row block in the stacked start-fold matrices W0 / H0 (FIRST variant)
   int dilation;
@@ -361,10 +363,14 @@ struct WnLayerConst {   // kernel-parameter (constant bank) copy: every read is 
 // Residual epilogue for 16 columns of one row: v = accumulator + bias; pass 0 stages hi = bf16(v), pass 1
 // stages lo = bf16(v - hi) into the SWIZZLE_128B staging tile.
 __device__ __forceinline__ void resid_step(const uint32_t (&r)[16], const float* bb, uint8_t* stg, int gi, int row,
-                                           int pass) {
+                                           int pass, bool valid = true) {
   uint32_t w[8];
 #pragma unroll
   for (int j2 = 0; j2 < 8; ++j2) {
+    if (!valid) {      // gap row between two utterances: h stays exactly zero
+      w[j2] = 0u;
+      continue;
+    }
     const float2 b2v = *reinterpret_cast<const float2*>(bb + 2 * j2);
     const float v0 = __uint_as_float(r[2 * j2]) + b2v.x;
     const float v1 = __uint_as_float(r[2 * j2 + 1]) + b2v.y;
@@ -456,10 +462,14 @@ __device__ __forceinline__ void gate_step2(const uint32_t (&t)[16], const uint32
 
 // Residual epilogue, packed: PASS 0 stages hi = bf16(v) only, PASS 1 recomputes it and stages lo = bf16(v - hi).
 template <int PASS>
-__device__ __forceinline__ void resid_step2(const uint32_t (&r)[16], const float* bb, uint8_t* stg, int gi, int row) {
+__device__ __forceinline__ void resid_step2(const uint32_t (&r)[16], const float* bb, uint8_t* stg, int gi, int row, bool valid) {
   uint32_t w[8];
 #pragma unroll
   for (int j2 = 0; j2 < 8; ++j2) {
+    if (!valid) {      // gap row between two utterances: h stays exactly zero (the next layer's zero padding)
+      w[j2] = 0u;
+      continue;
+    }
     const float2 v = __fadd2_rn(make_float2(__uint_as_float(r[2 * j2]), __uint_as_float(r[2 * j2 + 1])),
                                 *reinterpret_cast<const float2*>(bb + 2 * j2));
     const __nv_bfloat162 h2 = __floats2bfloat162_rn(v.x, v.y);
@@ -792,7 +802,7 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
       tile_coords(tile, b, r, t0);
       const uint32_t par = LAST ? 0u : (n & 1u);
       const uint32_t ph = n & 1u;
-      const bool valid = (t0 + row) < p.T;
+      const bool valid = (t0 + row) < p.T && (p.Tp == 0 || (t0 + row) % p.Tp < p.Tv);
       const size_t m = (static_cast<size_t>(b) * p.R + r) * p.T + t0 + row;
       float2 o8p[8];   // (even-channel, odd-channel) partial sums of the eight fold columns
 #pragma unroll
@@ -892,14 +902,14 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
           for (int gp = 0; gp < 4; ++gp) {          // two groups of 16 columns per iteration
             tmem_ld_wait();
             tmem_ld16(taddr + (2 * gp + 1) * 16, r1);
-            resid_step2<pass>(r0, s_b2 + hf * 128 + (2 * gp) * 16, stg, 2 * gp, row);
+            resid_step2<pass>(r0, s_b2 + hf * 128 + (2 * gp) * 16, stg, 2 * gp, row, valid);
             tmem_ld_wait();
             if (gp < 3) tmem_ld16(taddr + (2 * gp + 2) * 16, r0);
             else if (pass == 1) {
               tc_fence_before();
               mbar_arrive(epi2_bar);   // all TMEM reads of this tile are done
             }
-            resid_step2<pass>(r1, s_b2 + hf * 128 + (2 * gp + 1) * 16, stg, 2 * gp + 1, row);
+            resid_step2<pass>(r1, s_b2 + hf * 128 + (2 * gp + 1) * 16, stg, 2 * gp + 1, row, valid);
           }
           fence_proxy_async_smem();
           if (hf == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
@@ -939,18 +949,20 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
 // ================================================================================================
 // Small helper kernels
 // ================================================================================================
-// A operand of the polyphase upsample GEMM: aup[b*T + t, j*n_mel + i] = bf16(mel[b, t-j, i]), 0 for t < j.
+// A operand of the polyphase upsample GEMM / the phase-major conditioning: aup[b*Tp + t, j*n_mel + i] = bf16(mel[b, t-j, i]),
+// 0 for t < j and for the gap rows t >= T (Tp = T: no gaps).
 __global__ void upsample_im2col_kernel(const float* __restrict__ mel, __nv_bfloat16* __restrict__ aup, int B, int T,
-                                       int n_mel, int Kup) {
+                                       int n_mel, int Kup, int Tp) {
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const size_t total = static_cast<size_t>(B) * T * Kup;
+  const size_t total = static_cast<size_t>(B) * Tp * Kup;
   if (idx >= total) return;
   const int kk = static_cast<int>(idx % Kup);
   const size_t bt = idx / Kup;
-  const int t = static_cast<int>(bt % T);
+  const int t = static_cast<int>(bt % Tp);
+  const size_t b = bt / Tp;
   const int j = kk / n_mel, i = kk - j * n_mel;
   float v = 0.f;
-  if (j < 4 && t - j >= 0) v = mel[(bt - j) * n_mel + i];
+  if (t < T && j < 4 && t - j >= 0) v = mel[(b * T + t - j) * n_mel + i];
   aup[idx] = __float2bfloat16_rn(v);
 }
 
@@ -1045,6 +1057,7 @@ struct TcPlan {
   CUtensorMap m4_a0{}, m_w0{}, m_h0{};
   bool fold0 = false;
   int n_layers = 0;
+  int Breal = 0, Treal = 0, Tp = 0;   // gap layout: B utterances of T frames, Tp rows apart inside a phase block (pm only)
   bool pm = false;           // phase-major layout (R = 32) with the rank-320 conditioning
   int R = 1, Trows = 0, tiles_per_row = 0;
   int n_cond_kb = 0, wc_col0 = 0, wc_rows_per_layer = 0, wc_rstride = 0;
@@ -1059,32 +1072,36 @@ inline void tc_prepare(TcPlan& pl, int sm_count, int B, int T, int L, int C, int
                        const __nv_bfloat16* W2, __nv_bfloat16* aup16, __nv_bfloat16* spect16, __nv_bfloat16* h16a,
                        __nv_bfloat16* h16b, __nv_bfloat16* hlo, bool pm, int R, const __nv_bfloat16* V,
                        __nv_bfloat16* a0 = nullptr, const __nv_bfloat16* W0 = nullptr, const __nv_bfloat16* H0 = nullptr,
-                       int n_flows = 0) {
+                       int n_flows = 0, int gap = 0) {
   if ((C != 256 && C != 512) || S != WL_S) fail(WG_ERR_UNSUPPORTED, "tensor path is built for C in {256, 512}, S=640 (got C=%d, S=%d)", C, S);
   pl.sm_count = sm_count; pl.B = B; pl.T = T; pl.L = L; pl.C = C; pl.S = S; pl.Kup = Kup; pl.n_mel = n_mel; pl.NupN = NupN;
   pl.aup16 = aup16; pl.spect16 = spect16; pl.h16[0] = h16a; pl.h16[1] = h16b; pl.hlo = hlo;
   pl.pm = pm;
   pl.R = pm ? R : 1;
-  pl.Trows = pm ? T : L;
+  // Phase-major: ONE row sequence per phase holding all utterances Tp = T + gap rows apart (RowGeom, simt_kernels.cuh);
+  // the kernels see a single "utterance" of B*Tp frames whose gap rows are kept zero, and tiles may span utterances.
+  pl.Breal = B; pl.Treal = T; pl.Tp = pm ? T + gap : 0;
+  pl.Trows = pm ? B * pl.Tp : L;
+  const int Bk = pm ? 1 : B;     // batch extent the layer kernels iterate over
   pl.tiles_per_row = (pl.Trows + WL_BM - 1) / WL_BM;
-  pl.n_tiles = pl.tiles_per_row * pl.R * B;
+  pl.n_tiles = pl.tiles_per_row * pl.R * Bk;
   pl.tiles_per_b = pl.tiles_per_row;
   make_map_2d(&pl.m_w1, W1, (uint64_t)n_layers_total * 2 * C, 3 * C + S, 256);
   make_map_2d(&pl.m_w2, W2, (uint64_t)n_layers_total * C, C, 256);
   // phase-major: (channels, frames, phases, batch); position-major: (channels, rows, batch, 1)
-  const uint64_t d3 = pm ? B : 1, d2 = pm ? (uint64_t)R : (uint64_t)B;
+  const uint64_t d3 = 1, d2 = pm ? (uint64_t)R : (uint64_t)B;
   make_map_4d(&pl.m4_h[0], h16a, d3, d2, pl.Trows, C, WL_BM);
   make_map_4d(&pl.m4_h[1], h16b, d3, d2, pl.Trows, C, WL_BM);
   make_map_4d(&pl.m4_lo, hlo, d3, d2, pl.Trows, C, WL_BM);
   if (pm) {
     if (Kup % WL_BK) fail(WG_ERR_UNSUPPORTED, "mel window K (%d) must be a multiple of 64", Kup);
-    make_map_4d(&pl.m4_cond, aup16, B, 1, T, Kup, WL_BM);
+    make_map_4d(&pl.m4_cond, aup16, 1, 1, pl.Trows, Kup, WL_BM);
     make_map_2d(&pl.m_wc, V, (uint64_t)n_layers_total * R * 2 * C, Kup, 256);
     pl.n_cond_kb = Kup / WL_BK; pl.wc_col0 = 0; pl.wc_rows_per_layer = R * 2 * C; pl.wc_rstride = 2 * C;
     pl.fold0 = a0 && W0 && H0 && n_flows > 0;
     if (pl.fold0) {
       pl.n_layers = n_layers_total / n_flows;
-      make_map_4d(&pl.m4_a0, a0, B, R, T, WL_BK, WL_BM);
+      make_map_4d(&pl.m4_a0, a0, 1, R, pl.Trows, WL_BK, WL_BM);
       make_map_2d(&pl.m_w0, W0, (uint64_t)n_flows * 2 * C, WL_BK, 256);
       make_map_2d(&pl.m_h0, H0, (uint64_t)n_flows * C, WL_BK, 256);
     }
@@ -1105,8 +1122,9 @@ inline void tc_prepare(TcPlan& pl, int sm_count, int B, int T, int L, int C, int
 // A operand of the conditioning: 4-frame mel window (always), plus the polyphase upsample GEMM when the
 // position-major path needs the materialised spect.
 inline int tc_upsample(const TcPlan& pl, const float* mel, const float* bup, cudaStream_t st) {
-  const size_t total = (size_t)pl.B * pl.T * pl.Kup;
-  upsample_im2col_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(mel, pl.aup16, pl.B, pl.T, pl.n_mel, pl.Kup);
+  const int Tp = pl.pm ? pl.Tp : pl.T;
+  const size_t total = (size_t)pl.B * Tp * pl.Kup;
+  upsample_im2col_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(mel, pl.aup16, pl.B, pl.T, pl.n_mel, pl.Kup, Tp);
   WG_CK(cudaGetLastError());
   if (pl.pm) return 1;
   const int M = pl.B * pl.T;
@@ -1119,6 +1137,7 @@ inline int tc_upsample(const TcPlan& pl, const float* mel, const float* bup, cud
 inline void tc_fill_params(const TcPlan& pl, WnLayerParams& p, int layer, int dilation, int hcur, float* acc8,
                            const float* b1, const float* b2, unsigned long long* timing, int flags) {
   p.T = pl.Trows; p.R = pl.R; p.tiles_per_row = pl.tiles_per_row; p.n_tiles = pl.n_tiles;
+  p.Tp = pl.pm ? pl.Tp : 0; p.Tv = pl.Treal;
   p.L = pl.Trows; p.tiles_per_b = pl.tiles_per_row;
   p.n_cond_kb = pl.n_cond_kb; p.wc_col0 = pl.wc_col0; p.wc_row0 = layer * pl.wc_rows_per_layer; p.wc_rstride = pl.wc_rstride;
   p.layer = layer; p.dilation = dilation;
@@ -1146,29 +1165,27 @@ inline int tc_wn_layer(const TcPlan& pl, int layer, int dilation, bool last, int
   return 1;
 }
 
-// debug: h = hi + lo as float32, rows re-ordered from ((b*R + r)*T + t) to position-major (b, R*t + r)
+// debug: h = hi + lo as float32, rows re-ordered from the internal order (RowGeom) to position-major (b, R*t + r)
 __global__ void hilo_to_f32_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
-                                   float* __restrict__ out, size_t n_rows, int C, int R, int T) {
+                                   float* __restrict__ out, const RowGeom geo, int C) {
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= n_rows * C) return;
-  const size_t m = idx / C;
-  const int c = static_cast<int>(idx - m * C);
-  const size_t per_b = static_cast<size_t>(R) * T;
-  const size_t b = m / per_b, rem = m - b * per_b;
-  const size_t r = rem / T, t = rem - r * T;
-  out[(b * per_b + t * R + r) * C + c] = __bfloat162float(hi[idx]) + __bfloat162float(lo[idx]);
+  if (idx >= static_cast<size_t>(geo.rows()) * C) return;
+  const int m = static_cast<int>(idx / C);
+  const int c = static_cast<int>(idx - static_cast<size_t>(m) * C);
+  int b, r, t;
+  if (!geo.decode(m, b, r, t)) return;
+  out[geo.position_major(b, r, t) * C + c] = __bfloat162float(hi[idx]) + __bfloat162float(lo[idx]);
 }
 
-// debug: float rows [n_rows, W] re-ordered the same way
-__global__ void unpermute_rows_kernel(const float* __restrict__ in, float* __restrict__ out, size_t n_rows, int W, int R, int T) {
+// debug: float rows [rows, W] re-ordered the same way
+__global__ void unpermute_rows_kernel(const float* __restrict__ in, float* __restrict__ out, const RowGeom geo, int W) {
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= n_rows * W) return;
-  const size_t m = idx / W;
-  const int c = static_cast<int>(idx - m * W);
-  const size_t per_b = static_cast<size_t>(R) * T;
-  const size_t b = m / per_b, rem = m - b * per_b;
-  const size_t r = rem / T, t = rem - r * T;
-  out[(b * per_b + t * R + r) * W + c] = in[idx];
+  if (idx >= static_cast<size_t>(geo.rows()) * W) return;
+  const int m = static_cast<int>(idx / W);
+  const int c = static_cast<int>(idx - static_cast<size_t>(m) * W);
+  int b, r, t;
+  if (!geo.decode(m, b, r, t)) return;
+  out[geo.position_major(b, r, t) * W + c] = in[idx];
 }
 
 inline void tc_bf16_to_f32(const __nv_bfloat16* in, float* out, size_t n, cudaStream_t st) {
