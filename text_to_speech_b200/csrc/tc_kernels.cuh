@@ -302,7 +302,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // the epilogue never reads h back from global memory.
 //
 // TMEM: two 256-column fp32 regions R0/R1.  Tile with parity p:
-//   GEMM1 chunk a (gate channels 0..127)   -> R[p]      K = 22 blocks of 64 (12 conv + 10 cond)
+//   GEMM1 chunk a (gate channels 0..127)   -> R[p]      K = 12 conv blocks of 64 + 10 (spect) or 5 (mel window) cond blocks;
+//                                                       FIRST: 1 start-fold block + cond blocks
 //   GEMM1 chunk b (gate channels 128..255) -> R[p^1]    (issued while the epilogue drains chunk a)
 //   GEMM2 + residual                       -> R[p]      the half that depends only on chunk a's acts
 //                                                       is issued before chunk b's epilogue finishes
@@ -331,10 +332,13 @@ static_assert(WL_SMEM <= 232448, "shared memory budget");
 
 // Row geometry. Position l of utterance b is stored at row ((b*R + r)*T + t) with l = R*t + r:
 //   R = 1  : position-major (T = L rows per utterance), conditioning = upsampled spect [.., 640] (10 K-blocks)
-//   R = 32 : phase-major (T = mel frames). All 128 rows of a tile share the upsample phase r, so the
+//   R = 32 : phase-major. All 128 rows of a tile share the upsample phase r, so the
 //            conditioning GEMM runs at its intrinsic rank: A = 4-frame mel window [.., 320] (5 K-blocks),
 //            B = (Wup_r @ Wcond) folded per (layer, phase). A row shift by s positions is the tile of phase
-//            (r+s) mod R moved by floor((r+s)/R) frames, still one contiguous TMA box.
+//            (r+s) mod R moved by floor((r+s)/R) frames, still one contiguous TMA box. The host passes the batch
+//            as ONE utterance (b = 0) of T = B*Tp frames -- all utterances of a phase in one row sequence, Tp =
+//            frames + gap rows apart (RowGeom, simt_kernels.cuh); the gap rows are stored as zeros (Tp / Tv below),
+//            which is the zero padding between utterances, and tiles span utterance boundaries.
 struct WnLayerParams {
   int T, R, tiles_per_row, n_tiles;
   int L, tiles_per_b;   // legacy names used by the CTA-pair kernel (position-major only): L = T, tiles_per_b = tiles_per_row
