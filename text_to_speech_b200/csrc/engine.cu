@@ -291,6 +291,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
     tc_prepare(plan, e->sm_count, B, T, L, C, S, e->Kup, c.n_mel_channels, c.n_flows * c.n_layers,
                e->Wup16, R * S, e->W1, e->W2, aup16, spect16, h16[0], h16[1], hlo, pm, R, e->V,
                fold0 ? a0 : nullptr, e->W0, e->H0, c.n_flows, pm ? pm_gap(e) : 0);
+    if (const char* to = std::getenv("WG_TILE_ORDER")) plan.tile_order = to[0] != '0';
     if (e->use_pair && !pm && C == 256) tc_pair_prepare(pmaps, c.n_flows * c.n_layers, C, S, e->W1, e->W2);
     if (C == 512) make_map_4d(&m_acts512, acts16, 1, pm ? (uint64_t)R : (uint64_t)B, plan.Trows, C, WL_BM);
     e->launches += tc_upsample(plan, mel, e->bup, st);

@@ -86,6 +86,15 @@ tc512_gate_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
   constexpr int KB_CONV = FIRST ? 1 : W5_KB_CONV;
   const int kb1 = KB_CONV + p.n_cond_kb;
   auto tile_coords = [&](int tile, int& b, int& r, int& t0) {
+    if (p.tile_order) {
+      // phase fastest: the CTAs running at the same time cover ALL phases of a few 128-row ranges, so the dilated-conv
+      // taps (phases r +- d of the same rows) are L2 hits whatever the dilation
+      r = tile % p.R;
+      const int bt = tile / p.R;
+      b = bt / p.tiles_per_row;
+      t0 = (bt - b * p.tiles_per_row) * WL_BM;
+      return;
+    }
     const int tt = tile % p.tiles_per_row, br = tile / p.tiles_per_row;
     r = br % p.R;
     b = br / p.R;
@@ -316,6 +325,15 @@ tc512_res_kernel(const __grid_constant__ CUtensorMap map_acts, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
   const bool pm = p.R > 1;
   auto tile_coords = [&](int tile, int& b, int& r, int& t0) {
+    if (p.tile_order) {
+      // phase fastest: the CTAs running at the same time cover ALL phases of a few 128-row ranges, so the dilated-conv
+      // taps (phases r +- d of the same rows) are L2 hits whatever the dilation
+      r = tile % p.R;
+      const int bt = tile / p.R;
+      b = bt / p.tiles_per_row;
+      t0 = (bt - b * p.tiles_per_row) * WL_BM;
+      return;
+    }
     const int tt = tile % p.tiles_per_row, br = tile / p.tiles_per_row;
     r = br % p.R;
     b = br / p.R;

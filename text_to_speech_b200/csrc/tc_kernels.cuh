@@ -346,6 +346,7 @@ struct WnLayerParams {
   int wc_col0;          // first K column of the conditioning weights inside map_wc
   int wc_row0;          // first N row of this layer's conditioning weights inside map_wc
   int wc_rstride;       // extra N rows per phase (0 or 512)
+  int tile_order; // 1: tile index = (row tile, phase) with the phase fastest (phase-major); 0: phase blocks one after the other
   int Tp, Tv;     // gap layout (phase-major): row t of a phase block is valid iff (t % Tp) < Tv; Tp = 0: every row < T is valid
   int layer;      // row block in the stacked W1 / W2 matrices
   int flow;       // row block in the stacked start-fold matrices W0 / H0 (FIRST variant)
@@ -581,6 +582,15 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
   const int kb1 = KB_CONV + p.n_cond_kb;   // K-blocks of GEMM1 per chunk: 22 (spect), 17 (mel window), 6 (FIRST)
   // tile -> (utterance b, phase r, first row t0 of the 128-row tile inside the (b, r) row block)
   auto tile_coords = [&](int tile, int& b, int& r, int& t0) {
+    if (p.tile_order) {
+      // phase fastest: the CTAs running at the same time cover ALL phases of a few 128-row ranges, so the dilated-conv
+      // taps (phases r +- d of the same rows) are L2 hits whatever the dilation
+      r = tile % p.R;
+      const int bt = tile / p.R;
+      b = bt / p.tiles_per_row;
+      t0 = (bt - b * p.tiles_per_row) * WL_BM;
+      return;
+    }
     const int tt = tile % p.tiles_per_row, br = tile / p.tiles_per_row;
     r = br % p.R;
     b = br / p.R;
@@ -1061,6 +1071,7 @@ struct TcPlan {
   CUtensorMap m4_a0{}, m_w0{}, m_h0{};
   bool fold0 = false;
   int n_layers = 0;
+  int tile_order = 1;
   int Breal = 0, Treal = 0, Tp = 0;   // gap layout: B utterances of T frames, Tp rows apart inside a phase block (pm only)
   bool pm = false;           // phase-major layout (R = 32) with the rank-320 conditioning
   int R = 1, Trows = 0, tiles_per_row = 0;
@@ -1142,6 +1153,7 @@ inline void tc_fill_params(const TcPlan& pl, WnLayerParams& p, int layer, int di
                            const float* b1, const float* b2, unsigned long long* timing, int flags) {
   p.T = pl.Trows; p.R = pl.R; p.tiles_per_row = pl.tiles_per_row; p.n_tiles = pl.n_tiles;
   p.Tp = pl.pm ? pl.Tp : 0; p.Tv = pl.Treal;
+  p.tile_order = pl.pm && pl.tile_order ? 1 : 0;
   p.L = pl.Trows; p.tiles_per_b = pl.tiles_per_row;
   p.n_cond_kb = pl.n_cond_kb; p.wc_col0 = pl.wc_col0; p.wc_row0 = layer * pl.wc_rows_per_layer; p.wc_rstride = pl.wc_rstride;
   p.layer = layer; p.dilation = dilation;
