@@ -57,6 +57,7 @@ struct LayerW {
   float* b1_pm = nullptr; // same + the upsample bias pushed through the cond weights (phase-major path)
   float* b2 = nullptr;    // [C]
   std::vector<float> wse_h;  // [C, 8] = Wskip @ Wend (fp32), host copy: passed in the kernel parameter bank
+  std::vector<float> wse_p;  // the same in the packed-fold layout [channel pair][column][even, odd] (gate_step2)
 };
 
 }  // namespace
@@ -381,13 +382,13 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
         if (e->profiling) e->ev_count.back() += 1;
         if (C == 512)
           e->launches += tc512_wn_layer(plan, m_acts512, k * c.n_layers + i, d, last, hcur, acc8, pm ? lw.b1_pm : lw.b1,
-                                        lw.b2, lw.wse_h.data(), st, fold0 && i == 0);
+                                        lw.b2, lw.wse_p.data(), st, fold0 && i == 0);
         else if (e->use_pair && !pm)
           e->launches += tc_wn_layer_pair(plan, pmaps, k * c.n_layers + i, d, last, hcur, acc8, lw.b1, lw.b2,
                                           lw.wse_h.data(), e->timing, e->dbg_flags, st);
         else
           e->launches += tc_wn_layer(plan, k * c.n_layers + i, d, last, hcur, acc8, pm ? lw.b1_pm : lw.b1, lw.b2,
-                                     lw.wse_h.data(), e->timing, e->dbg_flags, st, fold0 && i == 0);
+                                     lw.wse_p.data(), e->timing, e->dbg_flags, st, fold0 && i == 0);
         if (last || (k == stop_flow && i == stop_layer)) prof_mark();
         if (!last) hcur ^= 1;
       }
@@ -702,6 +703,9 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
           for (int n = 0; n < C; ++n) s += (double)rb.data[skip_off + n] * (double)wend8[(size_t)n * 8 + j];
           bse[j] += s;
         }
+        lw.wse_p.assign((size_t)C * 8, 0.f);
+        for (int ch = 0; ch < C; ++ch)
+          for (int cc = 0; cc < 8; ++cc) lw.wse_p[((size_t)(ch >> 1) * 8 + cc) * 2 + (ch & 1)] = wse[(size_t)ch * 8 + cc];
         lw.b1 = upload(e, b1);
         lw.b2 = upload(e, b2);
       }

@@ -497,8 +497,7 @@ inline int tc512_wn_layer(const TcPlan& pl, const CUtensorMap& m_acts, int layer
   WnLayerParams p{};
   tc_fill_params(pl, p, layer, dilation, hcur, acc8, b1, b2, nullptr, 0);
   Wn512Const cw;
-  for (int ch = 0; ch < W5_C; ++ch)   // packed-fold layout: [channel pair][column][even, odd]
-    for (int cc = 0; cc < 8; ++cc) cw.wse[((ch >> 1) * 8 + cc) * 2 + (ch & 1)] = wse_host[ch * 8 + cc];
+  std::memcpy(cw.wse, wse_host, sizeof cw.wse);   // wse_host: packed-fold layout (LayerW::wse_p)
   const int grid = pl.n_tiles < pl.sm_count ? pl.n_tiles : pl.sm_count;
   if (first && (!pl.fold0 || last || dilation != 1)) fail(WG_ERR_INVALID, "start fold requested for a layer it does not apply to");
   if (last) {

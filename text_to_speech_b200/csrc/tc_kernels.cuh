@@ -1166,9 +1166,8 @@ inline int tc_wn_layer(const TcPlan& pl, int layer, int dilation, bool last, int
                        bool first = false) {
   WnLayerParams p{};
   tc_fill_params(pl, p, layer, dilation, hcur, acc8, b1, b2, timing, flags);
-  WnLayerConst cw;   // packed-fold layout of the single-CTA kernel: [channel pair][column][even, odd]
-  for (int ch = 0; ch < WL_C; ++ch)
-    for (int cc = 0; cc < 8; ++cc) cw.wse[((ch >> 1) * 8 + cc) * 2 + (ch & 1)] = wse_host[ch * 8 + cc];
+  WnLayerConst cw;   // wse_host: packed-fold layout [channel pair][column][even, odd] (LayerW::wse_p)
+  std::memcpy(cw.wse, wse_host, sizeof cw.wse);
   const int grid = pl.n_tiles < pl.sm_count ? pl.n_tiles : pl.sm_count;
   if (first && (!pl.fold0 || last || dilation != 1)) fail(WG_ERR_INVALID, "start fold requested for a layer it does not apply to");
   if (last)
