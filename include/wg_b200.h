@@ -17,8 +17,9 @@
  * negative wg_status; wg_last_error() gives the message (the Python host layer raises RuntimeError
  * with it, as the TensorRT runtime precedent does). A handle is immutable after wg_create, so
  * concurrent wg_infer calls on different streams with different workspaces are safe; wg_infer_host
- * uses engine-owned staging buffers and is NOT re-entrant. There is no CPU fallback: without a
- * CUDA device wg_create fails with WG_ERR_CUDA.
+ * uses engine-owned staging buffers and is NOT re-entrant. Every entry point runs on the engine's
+ * device and restores the caller's current CUDA device before it returns. There is no CPU fallback:
+ * without a CUDA device wg_create fails with WG_ERR_CUDA.
  */
 #ifndef WG_B200_H_
 #define WG_B200_H_
@@ -30,7 +31,7 @@
 extern "C" {
 #endif
 
-#define WG_ABI_VERSION 1
+#define WG_ABI_VERSION 2
 
 typedef enum wg_status {
   WG_OK = 0,
@@ -99,6 +100,23 @@ int wg_infer(wg_handle h, const float* mel, const float* z, float sigma, int32_t
  * private stream and returns after the waveform is in out_host (tensorrt_runtime.py:193-206). */
 int wg_infer_host(wg_handle h, const float* mel_host, const float* z_host, float sigma,
                   int32_t deterministic, int32_t B, int32_t T, float* out_host);
+
+/* Ragged batch: utterance b has T_b[b] frames (1 <= T_b[b] <= T); T_b is a HOST array of B entries that need not
+ * outlive the call. The buffers keep the padded shapes of wg_infer (mel [B, T, n_mel], z [B, T*256/n_group, n_group],
+ * out [B, 256*T]); only the first T_b[b] frames of an utterance are read and its first 256*T_b[b] samples written --
+ * the tail of out is set to zero. No padding frame enters any convolution, so the samples of utterance b equal the
+ * ones wg_infer produces for that utterance passed ALONE with T = T_b[b] -- the reference's call pattern, one trimmed
+ * mel at a time (models/tts/tacotron2.py:183-191, models/tts/waveglow.py:76-82) -- bit for bit when both calls use the
+ * same internal row layout (always, once the WG_PM environment switch pins it; otherwise the layout of a small
+ * stand-alone call is picked by a wave count and the two agree to within the mode's tolerance).
+ * WG_MODE_BF16 packs all utterances into one launch sequence; WG_MODE_FP32 runs them one after the other on `stream`.
+ * Asynchronous, no allocation, graph-capturable (the lengths travel in kernel parameters). */
+int wg_workspace_bytes_ragged(wg_handle h, int32_t B, int32_t T, const int32_t* T_b, size_t* bytes);
+int wg_infer_ragged(wg_handle h, const float* mel, const float* z, float sigma, int32_t deterministic,
+                    int32_t B, int32_t T, const int32_t* T_b, float* out, void* workspace,
+                    size_t workspace_bytes, void* stream);
+int wg_infer_host_ragged(wg_handle h, const float* mel_host, const float* z_host, float sigma,
+                         int32_t deterministic, int32_t B, int32_t T, const int32_t* T_b, float* out_host);
 
 /* Number of kernels the last wg_infer on this handle launched (bench.py's gpu_launches). */
 int wg_last_launch_count(wg_handle h);

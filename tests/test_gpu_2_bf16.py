@@ -229,6 +229,31 @@ def test_bf16_full_size_parity_against_fp32_engine(lib_built):
     assert err <= TOL_BF16_ABS and snr >= TOL_BF16_SNR
 
 
+def test_waveglow512_full_size_parity_against_fp32_engine(lib_built):
+    """BASELINE.json configs[2] at its full size (WaveGlow-512, 32 x 860 frames, 7.0 M samples): the two-kernel tcgen05
+    layer against the fp32 engine (pinned to the reference fp32 waveform at <= 1e-4 on the wg512_t16 fixture) on ALL
+    samples, a CPU-oracle check of an utterance prefix, run-to-run reproducibility and batch independence."""
+    hp = WaveGlowHParams(n_channels=512)
+    w = generate_weights(hp, 1234)
+    mel, z = synthetic_inputs(2026, 32, 860, hp)
+    e16 = _engine(hp, w, "bf16")
+    a = _run(e16, mel, z, 0.6)
+    assert a.shape == (32, 860 * 256) and np.isfinite(a).all()
+    assert np.array_equal(_run(e16, mel, z, 0.6), a)
+    assert np.array_equal(_run(e16, mel[17:18], z[17:18], 0.6)[0], a[17])
+    e16.close()
+    e32 = _engine(hp, w, "fp32")
+    b = np.concatenate([_run(e32, mel[i:i + 8], z[i:i + 8], 0.6) for i in range(0, 32, 8)])   # 8 at a time: fp32 scratch is 9 KB/row
+    e32.close()
+    err, snr = np.abs(a - b).max(), snr_db(b, a)
+    print(f"K3 full size: bf16 vs fp32 engine max-abs {err:.3e}, SNR {snr:.1f} dB, |wave|max {np.abs(b).max():.2f}")
+    assert err <= TOL_BF16_ABS and snr >= TOL_BF16_SNR
+    # the first frames of an utterance only see frames inside the receptive field: oracle on a 48-frame prefix
+    ref = OracleWaveGlow(hp, w)(mel[5:6, :48], z[5:6, :48 * 32], 0.6).numpy()
+    assert np.abs(a[5, :2048] - ref[0, :2048]).max() <= TOL_BF16_ABS
+    assert np.abs(b[5, :2048] - ref[0, :2048]).max() <= 1e-4
+
+
 def test_runtime_plugin_end_to_end(lib_built, tmp_path):
     """The call a user of the reference makes: WaveGlow(runtime='b200', path=...)(mel, sigma=..., z=...)
     with host numpy buffers, plus the extra kwargs the reference's callers pass along."""

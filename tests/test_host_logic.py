@@ -279,3 +279,41 @@ def test_normalize_audio_equals_the_reference_function():
         for kw in (dict(), dict(max_val=1.0), dict(max_val=20000)):
             a, b = normalize_audio(wave, **kw), ref.normalize_audio(wave, **kw)
             assert a.dtype == b.dtype and np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_plan_batches_honours_its_hard_limits(ragged):
+    """many short utterances used to collapse into one giant batch once max_batch forced early cuts."""
+    from text_to_speech_b200 import sharding
+    cases = [([10] * 10000, 1, 20000, 64), ([100] * 1000, 8, 4000, 16), ([5, 900, 7, 33, 860, 12] * 40, 4, 16 * 860, 64),
+             ([3000, 10, 10], 2, 1000, 8)]
+    for lengths, ws, max_frames, max_batch in cases:
+        plan = sharding.plan_batches(lengths, ws, max_frames, max_batch, ragged=ragged)
+        assert len(plan) == ws
+        batches = [b for r in plan for b in r]
+        assert sorted(i for b in batches for i in b.indices) == list(range(len(lengths)))
+        for b in batches:
+            assert len(b.indices) <= max_batch
+            assert b.T == max(lengths[i] for i in b.indices)
+            frames = sum(lengths[i] for i in b.indices) if ragged else b.T * len(b.indices)
+            assert frames <= max_frames or len(b.indices) == 1, (len(b.indices), b.T, frames)
+        loads = [sum((sum(lengths[i] for i in b.indices) if ragged else b.T * len(b.indices)) for b in r) for r in plan]
+        if len(batches) >= 4 * ws:
+            assert max(loads) <= 1.15 * (sum(loads) / ws), loads
+
+
+def test_run_rank_passes_true_lengths_when_ragged():
+    from text_to_speech_b200 import sharding
+    seen = []
+
+    def vocoder(x, lengths=None, **kw):
+        seen.append((x.shape, lengths, kw))
+        return np.repeat(x[:, :, 0], 256, axis=1)
+
+    mels = [np.full((n, 80), float(i), np.float32) for i, n in enumerate([5, 9, 2])]
+    plan = sharding.plan_batches([5, 9, 2], 1, max_frames=100, ragged=True)[0]
+    out = sharding.run_rank(vocoder, mels, plan, ragged=True, sigma=0.6)
+    assert all(l is not None and kw == {"sigma": 0.6} for _, l, kw in seen)
+    assert sorted(x for _, l, _ in seen for x in l) == [2, 5, 9]
+    for i, n in enumerate([5, 9, 2]):
+        assert out[i].shape == (n * 256,) and (out[i] == float(i)).all()

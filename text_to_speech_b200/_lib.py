@@ -14,17 +14,17 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwg_b200.so")
 SOURCES = [os.path.join(_HERE, "csrc", "engine.cu"), os.path.join(_HERE, "csrc", "mel.cu"),
            os.path.join(_HERE, "csrc", "taco.cu")]
-HEADERS = [os.path.join(_HERE, "csrc", f) for f in ("common.cuh", "simt_kernels.cuh", "tc_kernels.cuh", "tc_pair_kernel.cuh", "tc_c512_kernels.cuh")] + \
+HEADERS = [os.path.join(_HERE, "csrc", f) for f in ("common.cuh", "simt_kernels.cuh", "tc_kernels.cuh", "tc_c512_kernels.cuh")] + \
           [os.path.join(os.path.dirname(_HERE), "include", f) for f in ("wg_b200.h", "wg_mel_b200.h", "wg_taco_b200.h")]
 
 WG_OK = 0
 WG_MODE_FP32, WG_MODE_BF16 = 0, 1
 MODES = {"fp32": WG_MODE_FP32, "bf16": WG_MODE_BF16}
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # every symbol include/wg_b200.h declares (tests check the library exports all of them)
 EXPORTS = ["wg_abi_version", "wg_create", "wg_destroy", "wg_last_error", "wg_workspace_bytes", "wg_infer",
-           "wg_infer_host", "wg_last_launch_count", "wg_profile_enable", "wg_profile_read", "wg_debug_read_timing", "wg_debug_infer_prefix", "wg_debug_get_spect",
+           "wg_infer_host", "wg_workspace_bytes_ragged", "wg_infer_ragged", "wg_infer_host_ragged", "wg_last_launch_count", "wg_profile_enable", "wg_profile_read", "wg_debug_read_timing", "wg_debug_infer_prefix", "wg_debug_get_spect",
            "wg_debug_gemm_bf16"]
 # ... and include/wg_mel_b200.h
 MEL_EXPORTS = ["wg_mel_create", "wg_mel_destroy", "wg_mel_last_error", "wg_mel_frames", "wg_mel_spectrogram",
@@ -114,6 +114,13 @@ def load_library():
     lib.wg_infer.argtypes = [vp, vp, vp, c.c_float, i32, i32, i32, vp, vp, c.c_size_t, vp]
     lib.wg_infer_host.restype = c.c_int
     lib.wg_infer_host.argtypes = [vp, f32p, f32p, c.c_float, i32, i32, i32, f32p]
+    i32p = c.POINTER(i32)
+    lib.wg_workspace_bytes_ragged.restype = c.c_int
+    lib.wg_workspace_bytes_ragged.argtypes = [vp, i32, i32, i32p, c.POINTER(c.c_size_t)]
+    lib.wg_infer_ragged.restype = c.c_int
+    lib.wg_infer_ragged.argtypes = [vp, vp, vp, c.c_float, i32, i32, i32, i32p, vp, vp, c.c_size_t, vp]
+    lib.wg_infer_host_ragged.restype = c.c_int
+    lib.wg_infer_host_ragged.argtypes = [vp, f32p, f32p, c.c_float, i32, i32, i32, i32p, f32p]
     lib.wg_last_launch_count.restype = c.c_int
     lib.wg_last_launch_count.argtypes = [vp]
     lib.wg_profile_enable.restype = c.c_int

@@ -20,7 +20,6 @@
 #include "common.cuh"
 #include "simt_kernels.cuh"
 #include "tc_kernels.cuh"
-#include "tc_pair_kernel.cuh"
 #include "tc_c512_kernels.cuh"
 
 namespace {
@@ -93,8 +92,7 @@ struct wg_engine {
   size_t cap_mel = 0, cap_z = 0, cap_out = 0, cap_ws = 0;
   // per-kernel profiling (wg_profile_enable / wg_profile_read)
   unsigned long long* timing = nullptr;   // WG_LAYER_TIMING=1: in-kernel cycle counters (debug)
-  bool use_pair = false;                  // WG_PAIR=1 selects the CTA-pair (cta_group::2) kernel (measured slower, kept for A/B)
-  int dbg_flags = 0;                      // WG_DEBUG_FLAGS (see WnLayerParams::flags)
+  int dbg_flags = 0;                      // WG_DEBUG_FLAGS, honoured only by a -DWG_PROBES build (WnLayerParams::flags)
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;   // pairs: [2i] start, [2i+1] stop
   std::vector<int> ev_count;          // per pair: layer launches bracketed by it
@@ -102,6 +100,22 @@ struct wg_engine {
 };
 
 namespace {
+
+// Entry points run on the engine's device and put the caller's current device back on exit (torch reads it with
+// cudaGetDevice: a process driving several engines must not find it changed behind its back).
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) WG_CK(cudaSetDevice(dev));
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 
 template <typename T>
 T* upload(wg_engine* e, const std::vector<T>& v) {
@@ -165,7 +179,14 @@ inline __nv_bfloat16 f2bf(float x) { return __float2bfloat16_rn(x); }
 struct Ws {  // workspace carving for one (B, T)
   size_t spect = 0, h32 = 0, acts = 0, skip = 0, acc8 = 0, audio0 = 0, audio1 = 0;
   size_t spect16 = 0, h16a = 0, h16b = 0, hlo = 0, aup16 = 0, acts16 = 0, a0 = 0;
+  size_t g_off = 0, g_len = 0, g_rowb = 0;   // ragged geometry tables (RowGeom)
   size_t total = 0;
+};
+
+// Ragged batch: per-utterance frame counts (host copy) and the phase-block row offsets derived from them.
+struct Ragged {
+  std::vector<int> len, off;
+  int rpp = 0;   // rows per phase block = sum(len[b] + gap)
 };
 
 // rows between two utterances inside a phase block: >= max dilation / R frames, all zero (RowGeom)
@@ -186,10 +207,11 @@ bool use_pm(const wg_engine* e, int B, int T) {
   return cost_pm <= cost_pos;
 }
 
-Ws carve(const wg_engine* e, int B, int T) {
+Ws carve(const wg_engine* e, int B, int T, const Ragged* rg = nullptr) {
   Ws w;
-  const bool pm = use_pm(e, B, T);
-  const size_t M = pm ? (size_t)B * (T + pm_gap(e)) * e->R : (size_t)B * T * e->R;   // internal rows (gap rows included)
+  const bool pm = rg ? true : use_pm(e, B, T);
+  const size_t rows1 = rg ? (size_t)rg->rpp : (size_t)B * (T + pm_gap(e));           // rows of one phase block
+  const size_t M = pm ? rows1 * e->R : (size_t)B * T * e->R;   // internal rows (gap rows included)
   size_t off = 0;
   auto take = [&](size_t bytes) {
     size_t o = off;
@@ -209,9 +231,14 @@ Ws carve(const wg_engine* e, int B, int T) {
     w.h16a = take(M * e->C * 2);
     w.h16b = take(M * e->C * 2);
     w.hlo = take(M * e->C * 2);
-    w.aup16 = take((pm ? (size_t)B * (T + pm_gap(e)) : (size_t)B * T) * e->Kup * 2);
+    w.aup16 = take((pm ? rows1 : (size_t)B * T) * e->Kup * 2);
     if (e->C == 512) w.acts16 = take(M * e->C * 2);   // WaveGlow-512: acts travel between the gate and residual kernels
     if (e->W0 && pm) w.a0 = take(M * 64 * 2);   // start fold: A operand of each flow's first layer
+    if (rg) {
+      w.g_off = take((size_t)B * 4);
+      w.g_len = take((size_t)B * 4);
+      w.g_rowb = take(rows1 * 4);
+    }
   }
   w.total = off;
   return w;
@@ -221,6 +248,30 @@ void check_shape(const wg_engine* e, int B, int T) {
   if (B <= 0 || T <= 0) fail(WG_ERR_INVALID, "B and T must be positive (got B=%d, T=%d)", B, T);
   const double M = (double)B * (T + (e->cfg.mode == WG_MODE_BF16 ? pm_gap(e) : 0)) * e->R;   // internal rows, gap rows included
   if (M * std::max(e->S, e->C) > 2.0e9) fail(WG_ERR_INVALID, "B*T too large (B=%d, T=%d)", B, T);
+}
+
+// Validates per-utterance lengths (1 <= T_b[b] <= T) and lays the utterances out one after the other, gap rows apart.
+Ragged make_ragged(const wg_engine* e, int B, int T, const int32_t* T_b) {
+  check_shape(e, B, T);
+  if (!T_b) fail(WG_ERR_INVALID, "T_b must not be NULL");
+  Ragged rg;
+  rg.len.assign(T_b, T_b + B);
+  rg.off.resize(B);
+  const int gap = pm_gap(e);
+  long rows = 0;
+  for (int b = 0; b < B; ++b) {
+    if (T_b[b] <= 0 || T_b[b] > T) fail(WG_ERR_INVALID, "T_b[%d] = %d is outside [1, T=%d]", b, T_b[b], T);
+    rg.off[b] = (int)rows;
+    rows += T_b[b] + gap;
+  }
+  rg.rpp = (int)rows;
+  return rg;
+}
+
+bool is_uniform(const Ragged& rg, int T) {
+  for (int l : rg.len)
+    if (l != T) return false;
+  return true;
 }
 
 template <int EPI>
@@ -240,24 +291,43 @@ void launch_boundary(wg_engine* e, const BoundaryArgs& a, cudaStream_t st) {
 // The launch sequence of WaveGlow.infer. stop_flow/stop_layer >= -1 make it a debug prefix run.
 void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int deterministic, int B,
                int T, float* out, void* workspace, size_t ws_bytes, cudaStream_t st, int stop_flow,
-               int stop_layer, float* h_out, float* acc_out) {
+               int stop_layer, float* h_out, float* acc_out, const Ragged* rg = nullptr) {
   check_shape(e, B, T);
   if (!mel || (!out && stop_flow < 0)) fail(WG_ERR_INVALID, "mel/out must not be NULL");
   if (!deterministic && !z) fail(WG_ERR_INVALID, "z must be given unless deterministic");
-  const Ws w = carve(e, B, T);
+  if (rg && e->cfg.mode != WG_MODE_BF16) fail(WG_ERR_INVALID, "internal: ragged geometry is a BF16-path layout");
+  const Ws w = carve(e, B, T, rg);
   if (!workspace || ws_bytes < w.total)
     fail(WG_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.total, ws_bytes);
   if ((uintptr_t)workspace % 1024 != 0) fail(WG_ERR_WORKSPACE, "workspace must be 1024-byte aligned");
-  CK(cudaSetDevice(e->device));
-  e->launches = 0;
+  DeviceGuard guard(e->device);
 
+  e->launches = 0;
   char* base = static_cast<char*>(workspace);
   const wg_config& c = e->cfg;
   const int C = e->C, S = e->S, R = e->R, L = T * R, M = B * L;
   const bool bf16 = c.mode == WG_MODE_BF16;
-  const bool pm = use_pm(e, B, T);
+  const bool pm = rg ? true : use_pm(e, B, T);
   // internal row geometry of the bf16 buffers (fp32 mode: position-major)
-  const RowGeom geo = pm ? RowGeom{R, T, T + pm_gap(e), B} : RowGeom{1, L, L, B};
+  RowGeom geo = pm ? RowGeom{R, T, T + pm_gap(e), B} : RowGeom{1, L, L, B};
+  if (rg) {
+    // per-utterance lengths: tables in the workspace, written by kernels fed from the parameter bank (256 utterances
+    // per launch) -- no host buffer outlives this call; the waveform tail beyond 256*T_b[b] is defined as zero
+    geo.off = reinterpret_cast<int*>(static_cast<char*>(workspace) + w.g_off);
+    geo.len = reinterpret_cast<int*>(static_cast<char*>(workspace) + w.g_len);
+    geo.row_b = reinterpret_cast<int*>(static_cast<char*>(workspace) + w.g_rowb);
+    geo.rpp = rg->rpp;
+    for (int b0 = 0; b0 < B; b0 += 256) {
+      GeomChunk gc{};
+      gc.b0 = b0; gc.n = std::min(256, B - b0); gc.gap = pm_gap(e);
+      std::memcpy(gc.off, rg->off.data() + b0, gc.n * sizeof(int));
+      std::memcpy(gc.len, rg->len.data() + b0, gc.n * sizeof(int));
+      ragged_geom_kernel<<<gc.n, 128, 0, st>>>(gc, const_cast<int*>(geo.off), const_cast<int*>(geo.len), const_cast<int*>(geo.row_b));
+      CK(cudaGetLastError());
+      e->launches++;
+    }
+    if (out) CK(cudaMemsetAsync(out, 0, (size_t)B * L * c.n_group * sizeof(float), st));
+  }
   const int Mi = geo.rows();   // internal rows (== M unless phase-major: gap rows)
   float* h32 = bf16 ? nullptr : reinterpret_cast<float*>(base + w.h32);
   float* acc8 = reinterpret_cast<float*>(base + w.acc8);
@@ -278,7 +348,6 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
   const float* zz = deterministic ? nullptr : z;
 
   TcPlan plan;
-  TcPairMaps pmaps;
   // ---- (1) upsample + trim + regroup: spect[B*L, S]  (waveglow_arch.py:245-253) ---------------
   if (!bf16) {
     GemmArgs g{};
@@ -291,9 +360,8 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
   } else {
     tc_prepare(plan, e->sm_count, B, T, L, C, S, e->Kup, c.n_mel_channels, c.n_flows * c.n_layers,
                e->Wup16, R * S, e->W1, e->W2, aup16, spect16, h16[0], h16[1], hlo, pm, R, e->V,
-               fold0 ? a0 : nullptr, e->W0, e->H0, c.n_flows, pm ? pm_gap(e) : 0);
+               fold0 ? a0 : nullptr, e->W0, e->H0, c.n_flows, pm ? pm_gap(e) : 0, rg ? &geo : nullptr);
     if (const char* to = std::getenv("WG_TILE_ORDER")) plan.tile_order = to[0] != '0';
-    if (e->use_pair && !pm && C == 256) tc_pair_prepare(pmaps, c.n_flows * c.n_layers, C, S, e->W1, e->W2);
     if (C == 512) make_map_4d(&m_acts512, acts16, 1, pm ? (uint64_t)R : (uint64_t)B, plan.Trows, C, WL_BM);
     e->launches += tc_upsample(plan, mel, e->bup, st);
   }
@@ -303,7 +371,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
   int cur = 0, z_off = 0, hcur = 0;
   {
     BoundaryArgs a{};
-    a.R = geo.R; a.T = geo.T; a.Tp = geo.Tp; a.B = geo.B;
+    a.geo = geo;
     a.first = 1; a.z = zz; a.n_group = c.n_group; a.z_off = 0; a.n_inject = e->flows[F - 1].n_rem;
     a.sigma = sigma; a.audio_out = audio[cur]; a.M = Mi; a.C = C;
     a.Wstart = fold0 ? nullptr : e->flows[F - 1].Wstart; a.bstart = e->flows[F - 1].bstart;
@@ -383,9 +451,6 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
         if (C == 512)
           e->launches += tc512_wn_layer(plan, m_acts512, k * c.n_layers + i, d, last, hcur, acc8, pm ? lw.b1_pm : lw.b1,
                                         lw.b2, lw.wse_p.data(), st, fold0 && i == 0);
-        else if (e->use_pair && !pm)
-          e->launches += tc_wn_layer_pair(plan, pmaps, k * c.n_layers + i, d, last, hcur, acc8, lw.b1, lw.b2,
-                                          lw.wse_h.data(), e->timing, e->dbg_flags, st);
         else
           e->launches += tc_wn_layer(plan, k * c.n_layers + i, d, last, hcur, acc8, pm ? lw.b1_pm : lw.b1, lw.b2,
                                      lw.wse_p.data(), e->timing, e->dbg_flags, st, fold0 && i == 0);
@@ -408,7 +473,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
     }
     // coupling inverse + W^-1 + early re-injection + next start conv (:278-304)
     BoundaryArgs a{};
-    a.R = geo.R; a.T = geo.T; a.Tp = geo.Tp; a.B = geo.B;
+    a.geo = geo;
     a.first = 0; a.acc8 = acc8; a.audio_in = audio[cur]; a.z = zz; a.n_group = c.n_group;
     a.sigma = sigma; a.c_in = 2 * fw.n_half; a.M = Mi; a.C = C;
     std::memcpy(a.winv, fw.winv, sizeof a.winv);
@@ -463,7 +528,7 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
     fail(WG_ERR_CUDA, "no CUDA device available (%s); this engine has no CPU fallback",
          ce != cudaSuccess ? cudaGetErrorString(ce) : "device count 0");
   if (device < 0 || device >= ndev) fail(WG_ERR_INVALID, "device %d out of range [0,%d)", device, ndev);
-  CK(cudaSetDevice(device));
+  DeviceGuard guard(device);
   cudaDeviceProp prop{};
   CK(cudaGetDeviceProperties(&prop, device));
   e->sm_count = prop.multiProcessorCount;
@@ -726,27 +791,31 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
     {   // V[(layer*R + r)*2C + n][k] = sum_s Wup_r[k][s] * Wcond_layer[s][n]   (k < 4*n_mel, padded to Kup)
       const int Kw = (UPSAMPLE_K / HOP) * NM;       // 320
       if (Kw % 16 == 0 && Kw == e->Kup) {
+        // One fp32 GEMM per layer over ALL phases: rows (r, k) of the phase-stacked upsample matrix against the layer's
+        // conditioning weights, [R*Kw, S] @ [S, 2C], then one transposing bf16 store into V (2 launches per layer).
         float* d_wup = nullptr; float* d_wc = nullptr; float* d_tmp = nullptr;
         const size_t vcount = (size_t)F * NL * R * 2 * C * e->Kup;
-        CK(cudaMalloc(&d_wup, wup_f32.size() * 4));
+        std::vector<float> wup_rk((size_t)R * Kw * S);
+        for (int r = 0; r < R; ++r)
+          for (int k = 0; k < Kw; ++k)
+            std::memcpy(&wup_rk[((size_t)r * Kw + k) * S], &wup_f32[(size_t)k * R * S + (size_t)r * S], (size_t)S * 4);
+        CK(cudaMalloc(&d_wup, wup_rk.size() * 4));
         CK(cudaMalloc(&d_wc, (size_t)S * 2 * C * 4));
-        CK(cudaMalloc(&d_tmp, (size_t)Kw * 2 * C * 4));
+        CK(cudaMalloc(&d_tmp, (size_t)R * Kw * 2 * C * 4));
         CK(cudaMalloc(&e->V, vcount * 2));
         e->allocs.push_back(e->V);
-        CK(cudaMemcpy(d_wup, wup_f32.data(), wup_f32.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_wup, wup_rk.data(), wup_rk.size() * 4, cudaMemcpyHostToDevice));
         for (int li = 0; li < F * NL; ++li) {
           CK(cudaMemcpy(d_wc, wcond_packed[li].data(), (size_t)S * 2 * C * 4, cudaMemcpyHostToDevice));
-          for (int r = 0; r < R; ++r) {
-            GemmArgs g{};
-            g.nseg = 1;
-            g.seg[0] = ASeg{d_wup + (size_t)r * S, R * S, S, 0};
-            g.W = d_wc; g.bias = nullptr; g.M = Kw; g.N = 2 * C; g.L = Kw;
-            g.out0 = d_tmp; g.ld0 = 2 * C;
-            dim3 grid((g.N + SG_BN - 1) / SG_BN, (g.M + SG_BM - 1) / SG_BM);
-            gemm_f32_kernel<EPI_STORE><<<grid, SG_THREADS>>>(g);
-            const int n = Kw * 2 * C;
-            transpose_f32_to_bf16_kernel<<<(n + 255) / 256, 256>>>(d_tmp, e->V + ((size_t)li * R + r) * 2 * C * e->Kup, Kw, 2 * C);
-          }
+          GemmArgs g{};
+          g.nseg = 1;
+          g.seg[0] = ASeg{d_wup, S, S, 0};
+          g.W = d_wc; g.bias = nullptr; g.M = R * Kw; g.N = 2 * C; g.L = R * Kw;
+          g.out0 = d_tmp; g.ld0 = 2 * C;
+          dim3 grid((g.N + SG_BN - 1) / SG_BN, (g.M + SG_BM - 1) / SG_BM);
+          gemm_f32_kernel<EPI_STORE><<<grid, SG_THREADS>>>(g);
+          const size_t n = (size_t)R * Kw * 2 * C;
+          fold_store_bf16_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_tmp, e->V + (size_t)li * R * 2 * C * e->Kup, R, Kw, 2 * C);
         }
         CK(cudaGetLastError());
         CK(cudaDeviceSynchronize());
@@ -754,13 +823,13 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
       }
       if (const char* pmv = std::getenv("WG_PM")) e->pm_policy = std::atoi(pmv);
     }
-    tc_pair_init();
     tc512_init();
-    if (const char* pr = std::getenv("WG_PAIR")) e->use_pair = pr[0] == '1';
-    // A/B probes that deliberately BREAK the result to isolate a cost (profiles/r01_probes.md): honoured only when
-    // the caller also sets WG_ALLOW_PROBES=1, so a stray variable can never corrupt a production run.
+#ifdef WG_PROBES
+    // A/B probes that deliberately BREAK the result to isolate a cost (profiles/r01_probes.md): compiled only into a
+    // -DWG_PROBES build, and even there honoured only when the caller also sets WG_ALLOW_PROBES=1.
     if (const char* f = std::getenv("WG_DEBUG_FLAGS"))
       if (const char* ok = std::getenv("WG_ALLOW_PROBES")) e->dbg_flags = ok[0] == '1' ? std::atoi(f) : 0;
+#endif
     if (const char* t = std::getenv("WG_LAYER_TIMING")) {
       if (t[0] == '1') {
         CK(cudaMalloc(&e->timing, 128 * sizeof(unsigned long long)));
@@ -774,6 +843,8 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
 
 void destroy_engine(wg_engine* e) {
   if (!e) return;
+  int prev = -1;
+  if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
   cudaSetDevice(e->device);
   for (void* p : e->allocs) cudaFree(p);
   if (e->pin_mel) cudaFreeHost(e->pin_mel);
@@ -785,6 +856,7 @@ void destroy_engine(wg_engine* e) {
   if (e->dev_ws) cudaFree(e->dev_ws);
   if (e->stream) cudaStreamDestroy(e->stream);
   for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
+  if (prev >= 0) cudaSetDevice(prev);
   delete e;
 }
 
@@ -816,6 +888,79 @@ void ensure_pair(float*& pin, float*& dev, size_t& cap, size_t bytes) {
   CK(cudaMallocHost(reinterpret_cast<void**>(&pin), bytes));
   CK(cudaMalloc(reinterpret_cast<void**>(&dev), bytes));
   cap = bytes;
+}
+
+// WaveGlow.infer on a batch whose utterances have their own frame counts T_b[b] <= T (caller buffers keep the padded
+// [B, T, ..] shapes). Every utterance is computed exactly as if it had been passed alone -- no padding frame enters
+// any convolution (models/tts/tacotron2.py:183-191 vocodes one trimmed mel at a time).
+void infer_ragged(wg_engine* e, const float* mel, const float* z, float sigma, int deterministic, int B, int T,
+                  const int32_t* T_b, float* out, void* workspace, size_t ws_bytes, cudaStream_t st) {
+  const Ragged rg = make_ragged(e, B, T, T_b);
+  if (!mel || !out) fail(WG_ERR_INVALID, "mel/out must not be NULL");
+  if (!deterministic && !z) fail(WG_ERR_INVALID, "z must be given unless deterministic");
+  if (is_uniform(rg, T)) {
+    run_infer(e, mel, z, sigma, deterministic, B, T, out, workspace, ws_bytes, st, -2, -2, nullptr, nullptr);
+    return;
+  }
+  if (e->cfg.mode == WG_MODE_BF16) {
+    run_infer(e, mel, z, sigma, deterministic, B, T, out, workspace, ws_bytes, st, -2, -2, nullptr, nullptr, &rg);
+    return;
+  }
+  // FP32 (position-major FFMA) mode: one utterance after the other on the same stream and scratch
+  DeviceGuard guard(e->device);
+  const size_t Lg = (size_t)T * e->R, G = e->cfg.n_group;
+  CK(cudaMemsetAsync(out, 0, (size_t)B * Lg * G * sizeof(float), st));
+  int launches = 0;
+  for (int b = 0; b < B; ++b) {
+    run_infer(e, mel + (size_t)b * T * e->cfg.n_mel_channels, z ? z + (size_t)b * Lg * G : nullptr, sigma, deterministic,
+              1, rg.len[b], out + (size_t)b * Lg * G, workspace, ws_bytes, st, -2, -2, nullptr, nullptr);
+    launches += e->launches;
+  }
+  e->launches = launches;
+}
+
+void infer_host(wg_engine* h, const float* mel_host, const float* z_host, float sigma, int deterministic, int B, int T,
+                const int32_t* T_b, float* out_host) {
+  check_shape(h, B, T);
+  if (!mel_host || !out_host) fail(WG_ERR_INVALID, "mel_host/out_host must not be NULL");
+  if (!deterministic && !z_host) fail(WG_ERR_INVALID, "z_host must be given unless deterministic");
+  DeviceGuard guard(h->device);
+  size_t ws_b = 0;
+  if (T_b) {
+    const Ragged rg = make_ragged(h, B, T, T_b);
+    int tmax = 0;
+    for (int l : rg.len) tmax = std::max(tmax, l);
+    ws_b = h->cfg.mode != WG_MODE_BF16 ? carve(h, 1, tmax).total : is_uniform(rg, T) ? carve(h, B, T).total : carve(h, B, T, &rg).total;
+  } else {
+    ws_b = carve(h, B, T).total;
+  }
+  const size_t L = (size_t)T * h->R;
+  const size_t mel_b = (size_t)B * T * h->cfg.n_mel_channels * 4, z_b = (size_t)B * L * h->cfg.n_group * 4,
+               out_b = (size_t)B * L * h->cfg.n_group * 4;
+  ensure_pair(h->pin_mel, h->dev_mel, h->cap_mel, mel_b);
+  ensure_pair(h->pin_out, h->dev_out, h->cap_out, out_b);
+  if (!deterministic) ensure_pair(h->pin_z, h->dev_z, h->cap_z, z_b);
+  if (h->cap_ws < ws_b) {
+    if (h->dev_ws) cudaFree(h->dev_ws);
+    h->dev_ws = nullptr; h->cap_ws = 0;
+    CK(cudaMalloc(&h->dev_ws, ws_b));
+    h->cap_ws = ws_b;
+  }
+  std::memcpy(h->pin_mel, mel_host, mel_b);
+  CK(cudaMemcpyAsync(h->dev_mel, h->pin_mel, mel_b, cudaMemcpyHostToDevice, h->stream));
+  if (!deterministic) {
+    std::memcpy(h->pin_z, z_host, z_b);
+    CK(cudaMemcpyAsync(h->dev_z, h->pin_z, z_b, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (T_b)
+    infer_ragged(h, h->dev_mel, deterministic ? nullptr : h->dev_z, sigma, deterministic, B, T, T_b, h->dev_out, h->dev_ws,
+                 h->cap_ws, h->stream);
+  else
+    run_infer(h, h->dev_mel, deterministic ? nullptr : h->dev_z, sigma, deterministic, B, T, h->dev_out, h->dev_ws,
+              h->cap_ws, h->stream, -2, -2, nullptr, nullptr);
+  CK(cudaMemcpyAsync(h->pin_out, h->dev_out, out_b, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  std::memcpy(out_host, h->pin_out, out_b);
 }
 
 }  // namespace
@@ -868,37 +1013,41 @@ int wg_infer(wg_handle h, const float* mel, const float* z, float sigma, int32_t
   });
 }
 
+int wg_workspace_bytes_ragged(wg_handle h, int32_t B, int32_t T, const int32_t* T_b, size_t* bytes) {
+  if (!h || !bytes) return WG_ERR_INVALID;
+  return guarded(h, [&] {
+    const Ragged rg = make_ragged(h, B, T, T_b);
+    if (h->cfg.mode != WG_MODE_BF16) {   // FP32 mode runs the utterances one after the other in the same scratch
+      int tmax = 0;
+      for (int l : rg.len) tmax = std::max(tmax, l);
+      *bytes = carve(h, 1, tmax).total;
+    } else {
+      *bytes = is_uniform(rg, T) ? carve(h, B, T).total : carve(h, B, T, &rg).total;
+    }
+  });
+}
+
+int wg_infer_ragged(wg_handle h, const float* mel, const float* z, float sigma, int32_t deterministic, int32_t B,
+                    int32_t T, const int32_t* T_b, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h) return WG_ERR_INVALID;
+  return guarded(h, [&] {
+    infer_ragged(h, mel, z, sigma, deterministic, B, T, T_b, out, workspace, workspace_bytes,
+                 static_cast<cudaStream_t>(stream));
+  });
+}
+
 int wg_infer_host(wg_handle h, const float* mel_host, const float* z_host, float sigma, int32_t deterministic,
                   int32_t B, int32_t T, float* out_host) {
   if (!h) return WG_ERR_INVALID;
+  return guarded(h, [&] { infer_host(h, mel_host, z_host, sigma, deterministic, B, T, nullptr, out_host); });
+}
+
+int wg_infer_host_ragged(wg_handle h, const float* mel_host, const float* z_host, float sigma, int32_t deterministic,
+                         int32_t B, int32_t T, const int32_t* T_b, float* out_host) {
+  if (!h) return WG_ERR_INVALID;
   return guarded(h, [&] {
-    check_shape(h, B, T);
-    if (!mel_host || !out_host) fail(WG_ERR_INVALID, "mel_host/out_host must not be NULL");
-    if (!deterministic && !z_host) fail(WG_ERR_INVALID, "z_host must be given unless deterministic");
-    CK(cudaSetDevice(h->device));
-    const size_t L = (size_t)T * h->R;
-    const size_t mel_b = (size_t)B * T * h->cfg.n_mel_channels * 4, z_b = (size_t)B * L * h->cfg.n_group * 4,
-                 out_b = (size_t)B * L * h->cfg.n_group * 4, ws_b = carve(h, B, T).total;
-    ensure_pair(h->pin_mel, h->dev_mel, h->cap_mel, mel_b);
-    ensure_pair(h->pin_out, h->dev_out, h->cap_out, out_b);
-    if (!deterministic) ensure_pair(h->pin_z, h->dev_z, h->cap_z, z_b);
-    if (h->cap_ws < ws_b) {
-      if (h->dev_ws) cudaFree(h->dev_ws);
-      h->dev_ws = nullptr; h->cap_ws = 0;
-      CK(cudaMalloc(&h->dev_ws, ws_b));
-      h->cap_ws = ws_b;
-    }
-    std::memcpy(h->pin_mel, mel_host, mel_b);
-    CK(cudaMemcpyAsync(h->dev_mel, h->pin_mel, mel_b, cudaMemcpyHostToDevice, h->stream));
-    if (!deterministic) {
-      std::memcpy(h->pin_z, z_host, z_b);
-      CK(cudaMemcpyAsync(h->dev_z, h->pin_z, z_b, cudaMemcpyHostToDevice, h->stream));
-    }
-    run_infer(h, h->dev_mel, deterministic ? nullptr : h->dev_z, sigma, deterministic, B, T, h->dev_out, h->dev_ws,
-              h->cap_ws, h->stream, -2, -2, nullptr, nullptr);
-    CK(cudaMemcpyAsync(h->pin_out, h->dev_out, out_b, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    std::memcpy(out_host, h->pin_out, out_b);
+    if (!T_b) fail(WG_ERR_INVALID, "T_b must not be NULL");
+    infer_host(h, mel_host, z_host, sigma, deterministic, B, T, T_b, out_host);
   });
 }
 

@@ -206,22 +206,61 @@ end_conv_kernel(const float* __restrict__ skip, const float* __restrict__ Wend /
 // (gap >= max dilation / R frames) and 128-row tiles may span utterances (no ragged last tile per utterance).
 struct RowGeom {
   int R, T, Tp, B;
-  __host__ __device__ int rows() const { return R * B * Tp; }
-  // internal row -> (b, r, t); returns false for a gap row
-  __device__ bool decode(int m, int& b, int& r, int& t) const {
-    const int per_r = B * Tp;
-    r = m / per_r;
-    const int rem = m - r * per_r;
+  // Ragged batches (wg_infer_ragged): utterance b has len[b] <= T frames and starts at row off[b] of every phase block;
+  // row_b[t] = utterance of phase-block row t, -1 for a gap row; rpp = rows per phase block (sum of len[b] + gap).
+  // All three null / rpp == 0: uniform layout (every utterance T frames, Tp rows apart). The caller-side buffers
+  // (mel, z, waveform) keep the padded [B, T, ..] shape either way.
+  const int* off = nullptr;
+  const int* len = nullptr;
+  const int* row_b = nullptr;
+  int rpp = 0;
+  __host__ __device__ int rows_per_phase() const { return row_b ? rpp : B * Tp; }
+  __host__ __device__ int rows() const { return R * rows_per_phase(); }
+  __device__ int frames(int b) const { return len ? len[b] : T; }
+  // phase-block row -> (b, t); returns false for a gap row
+  __device__ bool decode_row(int rem, int& b, int& t) const {
+    if (row_b) {
+      b = row_b[rem];
+      if (b < 0) return false;
+      t = rem - off[b];
+      return true;
+    }
     b = rem / Tp;
     t = rem - b * Tp;
     return t < T;
   }
+  // internal row -> (b, r, t); returns false for a gap row
+  __device__ bool decode(int m, int& b, int& r, int& t) const {
+    const int per_r = rows_per_phase();
+    r = m / per_r;
+    return decode_row(m - r * per_r, b, t);
+  }
   __device__ size_t internal(int b, int l) const {   // position l = R*t + r of utterance b
     const int t = l / R, r = l - t * R;
+    if (row_b) return static_cast<size_t>(r) * rpp + off[b] + t;
     return (static_cast<size_t>(r) * B + b) * Tp + t;
   }
   __device__ size_t position_major(int b, int r, int t) const { return static_cast<size_t>(b) * R * T + static_cast<size_t>(t) * R + r; }
 };
+
+// Ragged geometry tables, one block per utterance: off/len from the kernel parameters (no host buffer has to outlive
+// the call, so wg_infer_ragged stays asynchronous and graph-capturable), row_b for the utterance's rows and its gap.
+struct GeomChunk {
+  int b0, n, gap;
+  int off[256];
+  int len[256];
+};
+__global__ void __launch_bounds__(128)
+ragged_geom_kernel(const __grid_constant__ GeomChunk c, int* __restrict__ off, int* __restrict__ len, int* __restrict__ row_b) {
+  const int j = blockIdx.x;
+  if (j >= c.n) return;
+  const int o = c.off[j], n = c.len[j];
+  if (threadIdx.x == 0) {
+    off[c.b0 + j] = o;
+    len[c.b0 + j] = n;
+  }
+  for (int t = threadIdx.x; t < n + c.gap; t += blockDim.x) row_b[o + t] = t < n ? c.b0 + j : -1;
+}
 
 struct BoundaryArgs {
   const float* acc8;      // [M,8]: cols [0,n_half) = b, [n_half, 2 n_half) = log s   (null when first)
@@ -250,8 +289,8 @@ struct BoundaryArgs {
   float acc8_init[8];
   // Row geometry of the internal buffers (RowGeom below): position l = R*t + r of utterance b lives at row
   // (r*B + b)*Tp + t; rows with t >= T are zero gap rows. z and the final waveform are always position-major.
-  // M counts INTERNAL rows (R*B*Tp).
-  int R, T, Tp, B;
+  // M counts INTERNAL rows (geo.rows()).
+  RowGeom geo;
   int final_out;          // audio_out is the caller's waveform buffer (position-major)
 };
 
@@ -263,7 +302,7 @@ flow_boundary_kernel(const __grid_constant__ BoundaryArgs a) {
   __shared__ int s_gap[FB_ROWS];
   const int m0 = blockIdx.x * FB_ROWS;
   const int tid = threadIdx.x;
-  const RowGeom geo{a.R, a.T, a.Tp, a.B};
+  const RowGeom& geo = a.geo;
   if (tid < FB_ROWS) {
     const int m = m0 + tid;
     s_gap[tid] = 0;
@@ -387,7 +426,7 @@ a0_build_kernel(const float* __restrict__ audio, __nv_bfloat16* __restrict__ a0,
   uint32_t w[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) w[j] = 0u;
-  if (valid && l >= 0 && l < geo.R * geo.T) {
+  if (valid && l >= 0 && l < geo.R * geo.frames(b)) {
     const size_t src = geo.internal(b, l);
     const float4 v4 = *reinterpret_cast<const float4*>(audio + src * 8);
     float v[4] = {v4.x, v4.y, v4.z, v4.w};

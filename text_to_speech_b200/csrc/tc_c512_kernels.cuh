@@ -178,7 +178,7 @@ tc512_gate_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       int b, r, t0;
       tile_coords(tile, b, r, t0);
-      const bool valid = (t0 + row) < p.T && (p.Tp == 0 || (t0 + row) % p.Tp < p.Tv);
+      const bool valid = wn_row_valid(p, t0 + row);
       const size_t m = (static_cast<size_t>(b) * p.R + r) * p.T + t0 + row;
       float2 o8p[8];   // (even-channel, odd-channel) partial sums of the fold columns (gate_step2)
 #pragma unroll
@@ -433,7 +433,7 @@ tc512_res_kernel(const __grid_constant__ CUtensorMap map_acts, const __grid_cons
       int b, r, t0;
       tile_coords(tile, b, r, t0);
       const int c2 = pm ? r : b, c3 = pm ? b : 0;
-      const bool valid = (t0 + row) < p.T && (p.Tp == 0 || (t0 + row) % p.Tp < p.Tv);   // gap rows are stored as zeros
+      const bool valid = wn_row_valid(p, t0 + row);   // gap rows are stored as zeros
 #pragma unroll 1
       for (int nn = 0; nn < 2; ++nn) {
         mbar_wait(dfull_bar(nn), n & 1u);

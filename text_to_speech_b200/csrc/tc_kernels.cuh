@@ -348,6 +348,7 @@ struct WnLayerParams {
   int wc_rstride;       // extra N rows per phase (0 or 512)
   int tile_order; // 1: tile index = (row tile, phase) with the phase fastest (phase-major); 0: phase blocks one after the other
   int Tp, Tv;     // gap layout (phase-major): row t of a phase block is valid iff (t % Tp) < Tv; Tp = 0: every row < T is valid
+  const int* row_b;   // ragged batches (wg_infer_ragged): row t is valid iff row_b[t] >= 0 (overrides Tp / Tv); else null
   int layer;      // row block in the stacked W1 / W2 matrices
   int flow;       // row block in the stacked start-fold matrices W0 / H0 (FIRST variant)
   int dilation;
@@ -357,9 +358,16 @@ struct WnLayerParams {
   __nv_bfloat16* lo;       // [B*L, 256] bf16(h - hi), updated in place (rows are tile-private)
   float* acc8;       // [B*L, 8] folded skip/end accumulator (read-modify-write, one thread per row)
   unsigned long long* timing;   // optional [16] cycle counters (debug), may be null
-  int flags;   // debug/tuning: 1 = skip every other W1 tile load (wrong results; L2-bandwidth probe),
-               //               2 = skip every other activation tile load (same), 8 = L2-prefetch the next tile
+  int flags;   // only read when compiled with -DWG_PROBES (result-breaking A/B probes, profiles/r01_probes.md):
+               //   1 = skip every other W1 tile load, 2 = skip every other activation tile load
 };
+
+// Row validity of phase-block row t (gap rows between utterances hold zeros and never touch acc8).
+__device__ __forceinline__ bool wn_row_valid(const WnLayerParams& p, int t) {
+  if (t >= p.T) return false;
+  if (p.row_b) return p.row_b[t] >= 0;
+  return p.Tp == 0 || t % p.Tp < p.Tv;
+}
 
 struct WnLayerConst {   // kernel-parameter (constant bank) copy: every read is warp-uniform
   float wse[WL_C * 8];  // Wskip @ Wend, [256][8]
@@ -618,7 +626,11 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
         tile_coords(tile, b, r, t0);
         for (int q = 0; q < 2; ++q) {
           for (int kb = 0; kb < kb1; ++kb, ++it) {
+#ifdef WG_PROBES
             const bool skip_b = (p.flags & 1) && (kb & 1), skip_a = (p.flags & 2) && (kb & 1);
+#else
+            constexpr bool skip_b = false, skip_a = false;
+#endif
             const uint32_t s = acquire((skip_a ? 0 : WL_A_BYTES) + (skip_b ? 0 : WL_B_BYTES));
             const uint32_t a_dst = smem_base + s * WL_STAGE_BYTES;
             if (elect_one()) {
@@ -816,7 +828,7 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
       tile_coords(tile, b, r, t0);
       const uint32_t par = LAST ? 0u : (n & 1u);
       const uint32_t ph = n & 1u;
-      const bool valid = (t0 + row) < p.T && (p.Tp == 0 || (t0 + row) % p.Tp < p.Tv);
+      const bool valid = wn_row_valid(p, t0 + row);
       const size_t m = (static_cast<size_t>(b) * p.R + r) * p.T + t0 + row;
       float2 o8p[8];   // (even-channel, odd-channel) partial sums of the eight fold columns
 #pragma unroll
@@ -963,20 +975,21 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
 // ================================================================================================
 // Small helper kernels
 // ================================================================================================
-// A operand of the polyphase upsample GEMM / the phase-major conditioning: aup[b*Tp + t, j*n_mel + i] = bf16(mel[b, t-j, i]),
-// 0 for t < j and for the gap rows t >= T (Tp = T: no gaps).
-__global__ void upsample_im2col_kernel(const float* __restrict__ mel, __nv_bfloat16* __restrict__ aup, int B, int T,
-                                       int n_mel, int Kup, int Tp) {
+// A operand of the polyphase upsample GEMM / the phase-major conditioning: row (b, t) of ONE phase block (RowGeom with
+// R = 1: utterances Tp rows apart, or the ragged tables) holds aup[row, j*n_mel + i] = bf16(mel[b, t-j, i]), 0 for t < j
+// and for gap rows. mel is the caller's padded [B, T, n_mel].
+__global__ void upsample_im2col_kernel(const float* __restrict__ mel, __nv_bfloat16* __restrict__ aup, const RowGeom geo,
+                                       int n_mel, int Kup) {
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const size_t total = static_cast<size_t>(B) * Tp * Kup;
+  const size_t total = static_cast<size_t>(geo.rows_per_phase()) * Kup;
   if (idx >= total) return;
   const int kk = static_cast<int>(idx % Kup);
-  const size_t bt = idx / Kup;
-  const int t = static_cast<int>(bt % Tp);
-  const size_t b = bt / Tp;
+  const int row = static_cast<int>(idx / Kup);
+  int b, t;
+  const bool valid = geo.decode_row(row, b, t);
   const int j = kk / n_mel, i = kk - j * n_mel;
   float v = 0.f;
-  if (t < T && j < 4 && t - j >= 0) v = mel[(b * T + t - j) * n_mel + i];
+  if (valid && j < 4 && t - j >= 0) v = mel[(static_cast<size_t>(b) * geo.T + t - j) * n_mel + i];
   aup[idx] = __float2bfloat16_rn(v);
 }
 
@@ -986,6 +999,17 @@ __global__ void transpose_f32_to_bf16_kernel(const float* __restrict__ in, __nv_
   if (idx >= K * N) return;
   const int n = idx / K, k = idx - n * K;
   out[idx] = __float2bfloat16_rn(in[static_cast<size_t>(k) * N + n]);
+}
+
+// weight prep of the folded conditioning weights: in [(r, k), n] fp32 (one GEMM over all phases) ->
+// out[(r*N + n)*K + k] = bf16(in[(r*K + k)*N + n])   (per phase a K-major [N, K] matrix)
+__global__ void fold_store_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int R, int K, int N) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<size_t>(R) * K * N) return;
+  const int k = static_cast<int>(idx % K);
+  const size_t rn = idx / K;
+  const int n = static_cast<int>(rn % N), r = static_cast<int>(rn / N);
+  out[idx] = __float2bfloat16_rn(in[(static_cast<size_t>(r) * K + k) * N + n]);
 }
 
 __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, size_t n) {
@@ -1073,6 +1097,7 @@ struct TcPlan {
   int n_layers = 0;
   int tile_order = 1;
   int Breal = 0, Treal = 0, Tp = 0;   // gap layout: B utterances of T frames, Tp rows apart inside a phase block (pm only)
+  RowGeom geo1{};                     // one phase block (R = 1) in the caller's utterance geometry: the mel-window rows
   bool pm = false;           // phase-major layout (R = 32) with the rank-320 conditioning
   int R = 1, Trows = 0, tiles_per_row = 0;
   int n_cond_kb = 0, wc_col0 = 0, wc_rows_per_layer = 0, wc_rstride = 0;
@@ -1087,7 +1112,7 @@ inline void tc_prepare(TcPlan& pl, int sm_count, int B, int T, int L, int C, int
                        const __nv_bfloat16* W2, __nv_bfloat16* aup16, __nv_bfloat16* spect16, __nv_bfloat16* h16a,
                        __nv_bfloat16* h16b, __nv_bfloat16* hlo, bool pm, int R, const __nv_bfloat16* V,
                        __nv_bfloat16* a0 = nullptr, const __nv_bfloat16* W0 = nullptr, const __nv_bfloat16* H0 = nullptr,
-                       int n_flows = 0, int gap = 0) {
+                       int n_flows = 0, int gap = 0, const RowGeom* ragged = nullptr) {
   if ((C != 256 && C != 512) || S != WL_S) fail(WG_ERR_UNSUPPORTED, "tensor path is built for C in {256, 512}, S=640 (got C=%d, S=%d)", C, S);
   pl.sm_count = sm_count; pl.B = B; pl.T = T; pl.L = L; pl.C = C; pl.S = S; pl.Kup = Kup; pl.n_mel = n_mel; pl.NupN = NupN;
   pl.aup16 = aup16; pl.spect16 = spect16; pl.h16[0] = h16a; pl.h16[1] = h16b; pl.hlo = hlo;
@@ -1097,6 +1122,13 @@ inline void tc_prepare(TcPlan& pl, int sm_count, int B, int T, int L, int C, int
   // the kernels see a single "utterance" of B*Tp frames whose gap rows are kept zero, and tiles may span utterances.
   pl.Breal = B; pl.Treal = T; pl.Tp = pm ? T + gap : 0;
   pl.Trows = pm ? B * pl.Tp : L;
+  pl.geo1 = RowGeom{1, T, pm ? pl.Tp : T, B};
+  if (ragged) {   // per-utterance lengths: phase-major only, rows per phase block from the tables
+    if (!pm) fail(WG_ERR_INVALID, "ragged batches need the phase-major layout");
+    pl.Trows = ragged->rpp;
+    pl.geo1 = *ragged;
+    pl.geo1.R = 1;
+  }
   const int Bk = pm ? 1 : B;     // batch extent the layer kernels iterate over
   pl.tiles_per_row = (pl.Trows + WL_BM - 1) / WL_BM;
   pl.n_tiles = pl.tiles_per_row * pl.R * Bk;
@@ -1137,9 +1169,8 @@ inline void tc_prepare(TcPlan& pl, int sm_count, int B, int T, int L, int C, int
 // A operand of the conditioning: 4-frame mel window (always), plus the polyphase upsample GEMM when the
 // position-major path needs the materialised spect.
 inline int tc_upsample(const TcPlan& pl, const float* mel, const float* bup, cudaStream_t st) {
-  const int Tp = pl.pm ? pl.Tp : pl.T;
-  const size_t total = (size_t)pl.B * Tp * pl.Kup;
-  upsample_im2col_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(mel, pl.aup16, pl.B, pl.T, pl.n_mel, pl.Kup, Tp);
+  const size_t total = (size_t)pl.geo1.rows_per_phase() * pl.Kup;
+  upsample_im2col_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(mel, pl.aup16, pl.geo1, pl.n_mel, pl.Kup);
   WG_CK(cudaGetLastError());
   if (pl.pm) return 1;
   const int M = pl.B * pl.T;
@@ -1153,6 +1184,7 @@ inline void tc_fill_params(const TcPlan& pl, WnLayerParams& p, int layer, int di
                            const float* b1, const float* b2, unsigned long long* timing, int flags) {
   p.T = pl.Trows; p.R = pl.R; p.tiles_per_row = pl.tiles_per_row; p.n_tiles = pl.n_tiles;
   p.Tp = pl.pm ? pl.Tp : 0; p.Tv = pl.Treal;
+  p.row_b = pl.geo1.row_b;
   p.tile_order = pl.pm && pl.tile_order ? 1 : 0;
   p.L = pl.Trows; p.tiles_per_b = pl.tiles_per_row;
   p.n_cond_kb = pl.n_cond_kb; p.wc_col0 = pl.wc_col0; p.wc_row0 = layer * pl.wc_rows_per_layer; p.wc_rstride = pl.wc_rstride;

@@ -65,9 +65,21 @@ class WaveGlowEngine:
         self._check(self._lib.wg_workspace_bytes(self._h, B, T, ctypes.byref(n)), "wg_workspace_bytes")
         return n.value
 
-    def _workspace(self, B, T):
+    def workspace_bytes_ragged(self, B, T, lengths):
+        n = ctypes.c_size_t()
+        self._check(self._lib.wg_workspace_bytes_ragged(self._h, B, T, lengths, ctypes.byref(n)), "wg_workspace_bytes_ragged")
+        return n.value
+
+    def _lengths(self, lengths, B, T):
+        """Per-utterance frame counts -> a C int32 array (validated here so a bad list never reaches the C side)."""
+        ls = [int(x) for x in lengths]
+        if len(ls) != B or any(l <= 0 or l > T for l in ls):
+            raise ValueError(f"lengths must hold {B} frame counts in [1, {T}], got {ls[:8]}{'...' if len(ls) > 8 else ''}")
+        return (ctypes.c_int32 * B)(*ls)
+
+    def _workspace(self, B, T, lengths=None):
         import torch
-        need = self.workspace_bytes(B, T)
+        need = self.workspace_bytes(B, T) if lengths is None else self.workspace_bytes_ragged(B, T, lengths)
         if self._ws is None or self._ws.numel() < need:
             self._ws = None
             self._ws = torch.empty(need + 1024, dtype=torch.uint8, device=f"cuda:{self.device}")
@@ -93,8 +105,10 @@ class WaveGlowEngine:
         return list(buf)
 
     # -- device-resident call (inputs already in HBM) ------------------------------------------------
-    def infer_device(self, mel, z=None, sigma=1.0, deterministic=False, out=None):
+    def infer_device(self, mel, z=None, sigma=1.0, deterministic=False, out=None, lengths=None):
         """mel [B,T,n_mel] / z [B,32T,8] / out [B,256T]: float32 CUDA tensors on this engine's device.
+        `lengths`: optional per-utterance frame counts (<= T) of a padded batch -- wg_infer_ragged: utterance b is
+        computed exactly as if it were passed alone with its own length; the waveform tail beyond 256*lengths[b] is 0.
         Asynchronous on torch's current stream."""
         import torch
         dev = torch.device("cuda", self.device)
@@ -111,23 +125,44 @@ class WaveGlowEngine:
             z = z.contiguous()
         if out is None:
             out = torch.empty(B, T * HOP, dtype=torch.float32, device=dev)
-        ws_ptr, ws_bytes = self._workspace(B, T)
+        elif out.device != dev or out.dtype != torch.float32 or tuple(out.shape) != (B, T * HOP) or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous float32 [{B},{T * HOP}] tensor on {dev}")
         stream = torch.cuda.current_stream(dev).cuda_stream
+        if lengths is not None:
+            lens = self._lengths(lengths, B, T)
+            ws_ptr, ws_bytes = self._workspace(B, T, lens)
+            rc = self._lib.wg_infer_ragged(self._h, mel.data_ptr(), 0 if deterministic else z.data_ptr(), float(sigma),
+                                           int(bool(deterministic)), B, T, lens, out.data_ptr(), ws_ptr, ws_bytes, stream)
+            self._check(rc, "wg_infer_ragged")
+            return out
+        ws_ptr, ws_bytes = self._workspace(B, T)
         rc = self._lib.wg_infer(self._h, mel.data_ptr(), 0 if deterministic else z.data_ptr(), float(sigma),
                                 int(bool(deterministic)), B, T, out.data_ptr(), ws_ptr, ws_bytes, stream)
         self._check(rc, "wg_infer")
         return out
 
     # -- host call through the C ABI's own staging (no torch on the data path) --------------------------
-    def infer_host(self, mel, z=None, sigma=1.0, deterministic=False):
+    def infer_host(self, mel, z=None, sigma=1.0, deterministic=False, lengths=None):
         mel = np.ascontiguousarray(mel, dtype=np.float32)
+        if mel.ndim != 3 or mel.shape[2] != self.hp.n_mel_channels or mel.shape[0] == 0 or mel.shape[1] == 0:
+            raise ValueError(f"mel must be a non-empty float32 [B,T,{self.hp.n_mel_channels}] array, got {mel.shape}")
         B, T = mel.shape[0], mel.shape[1]
         out = np.empty((B, T * HOP), dtype=np.float32)
         f32p = ctypes.POINTER(ctypes.c_float)
         zp = None
         if not deterministic:
+            if z is None:
+                raise ValueError("z is required unless deterministic (the Runtime layer draws it when omitted)")
             z = np.ascontiguousarray(z, dtype=np.float32)
+            Lg = T * HOP // self.hp.n_group
+            if z.shape != (B, Lg, self.hp.n_group):
+                raise ValueError(f"z must be a float32 [{B},{Lg},{self.hp.n_group}] array, got {z.shape}")
             zp = z.ctypes.data_as(f32p)
+        if lengths is not None:
+            rc = self._lib.wg_infer_host_ragged(self._h, mel.ctypes.data_as(f32p), zp, float(sigma), int(bool(deterministic)),
+                                                B, T, self._lengths(lengths, B, T), out.ctypes.data_as(f32p))
+            self._check(rc, "wg_infer_host_ragged")
+            return out
         rc = self._lib.wg_infer_host(self._h, mel.ctypes.data_as(f32p), zp, float(sigma), int(bool(deterministic)),
                                      B, T, out.ctypes.data_as(f32p))
         self._check(rc, "wg_infer_host")

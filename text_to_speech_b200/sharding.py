@@ -48,36 +48,51 @@ def make_batches(indices: Sequence[int], lengths: Sequence[int], max_frames: int
     return batches
 
 
-def plan_batches(lengths: Sequence[int], world_size: int, max_frames: int, max_batch: int = 64) -> List[List[Batch]]:
+def plan_batches(lengths: Sequence[int], world_size: int, max_frames: int, max_batch: int = 64,
+                 ragged: bool = False) -> List[List[Batch]]:
     """Global plan used by bench.py / the multi-GPU driver. ALL utterances are bucketed by length first
     (so the spread inside a batch, hence the padding waste, does not grow with the number of ranks);
-    the number of batches is a multiple of world_size and the cuts are placed at equal shares of the
-    total frame count, so every rank gets the same number of near-equal batches; batches then go to
-    ranks longest-processing-time-first (cost = B * T_max frames). Deterministic: every rank computes
-    the same plan without communicating."""
+    the target number of batches is a multiple of world_size and the cuts are placed at equal shares of
+    the total frame count, so every rank gets the same number of near-equal batches; batches then go to
+    ranks longest-processing-time-first. Hard limits always cut: a batch never holds more than
+    `max_batch` utterances nor (unless a single utterance is longer) more than `max_frames` frames --
+    B * T_max padded frames, or the sum of the true lengths when `ragged` (wg_infer_ragged computes no
+    padding frames). Deterministic: every rank computes the same plan without communicating."""
+    if world_size <= 0 or max_frames <= 0 or max_batch <= 0:
+        raise ValueError("world_size, max_frames and max_batch must be positive")
     n = len(lengths)
     idx = sorted(range(n), key=lambda i: (-int(lengths[i]), i))
     total = sum(int(l) for l in lengths)
-    nb = world_size * max(1, -(-total // (max_frames * world_size)))
-    nb = min(nb, n) if n >= world_size else nb
+    nb = max(-(-total // max_frames), -(-n // max_batch), 1)
+    nb = -(-nb // world_size) * world_size
+    if n >= world_size:
+        nb = min(nb, n)
+
+    def cost(ids):
+        return sum(int(lengths[i]) for i in ids) if ragged else int(lengths[ids[0]]) * len(ids)
+
     batches, cur, acc, k = [], [], 0, 1
     for i in idx:
+        if cur and (len(cur) >= max_batch or cost(cur + [i]) > max_frames):     # hard limits
+            batches.append(cur)
+            cur = []
         cur.append(i)
         acc += int(lengths[i])
-        if (acc >= total * k / nb or len(cur) >= max_batch) and len(batches) < nb - 1:
-            batches.append(Batch(cur, int(lengths[cur[0]])))
+        if acc * nb >= total * k and len(batches) < nb - 1:                       # equal-share cut
+            batches.append(cur)
             cur = []
-            while acc >= total * k / nb:
-                k += 1
+        while acc * nb >= total * k:
+            k += 1
     if cur:
-        batches.append(Batch(cur, int(lengths[cur[0]])))
-    order = sorted(range(len(batches)), key=lambda j: (-batches[j].T * len(batches[j].indices), j))
+        batches.append(cur)
+    out = [Batch(b, int(lengths[b[0]])) for b in batches]
+    order = sorted(range(len(out)), key=lambda j: (-cost(out[j].indices), j))
     load = [0] * world_size
     per_rank: List[List[Batch]] = [[] for _ in range(world_size)]
     for j in order:
         r = min(range(world_size), key=lambda q: (load[q], q))
-        per_rank[r].append(batches[j])
-        load[r] += batches[j].T * len(batches[j].indices)
+        per_rank[r].append(out[j])
+        load[r] += cost(out[j].indices)
     return per_rank
 
 
@@ -87,10 +102,13 @@ def padding_waste(batches: Sequence[Batch], lengths: Sequence[int]) -> float:
     return 0.0 if padded == 0 else 1.0 - real / padded
 
 
-def run_rank(vocoder, mels, plan_for_rank, pad_mel_value=-11.0, hop=256):
+def run_rank(vocoder, mels, plan_for_rank, pad_mel_value=-11.0, hop=256, ragged=False, **vocoder_kwargs):
     """Runs one rank's batches through `vocoder(mel[B,T,80]) -> [B, hop*T]` and returns {utterance id:
     waveform trimmed to its own length} (models/tts/waveglow.py:82 trims the same way). `mels` is the
-    global list of [T_i, 80] arrays; only this rank's utterances are touched."""
+    global list of [T_i, 80] arrays; only this rank's utterances are touched.
+    ragged=True passes the true frame counts (`lengths=`, B200WaveGlowRuntime -> wg_infer_ragged): every
+    utterance then equals the reference's one-at-a-time call on it (models/tts/tacotron2.py:183-191) instead
+    of a call on the padded mel, whose last ~second differs (WaveGlow is not causal)."""
     import numpy as np
     out = {}
     for batch in plan_for_rank:
@@ -98,7 +116,10 @@ def run_rank(vocoder, mels, plan_for_rank, pad_mel_value=-11.0, hop=256):
         x = np.full((len(batch.indices), batch.T, n_mel), pad_mel_value, dtype=np.float32)
         for j, i in enumerate(batch.indices):
             x[j, :mels[i].shape[0]] = mels[i]
-        y = np.asarray(vocoder(x))
+        kw = dict(vocoder_kwargs)
+        if ragged:
+            kw["lengths"] = [int(mels[i].shape[0]) for i in batch.indices]
+        y = np.asarray(vocoder(x, **kw))
         for j, i in enumerate(batch.indices):
             out[i] = y[j, :mels[i].shape[0] * hop].copy()
     return out

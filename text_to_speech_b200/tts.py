@@ -64,7 +64,8 @@ def tts(token_seqs: Sequence[np.ndarray], tacotron, vocoder, *, max_length=10.0,
         x = torch.full((len(batch.indices), batch.T, 80), PAD_MEL_VALUE, dtype=torch.float32, device=mels[batch.indices[0]].device)
         for j, i in enumerate(batch.indices):
             x[j, :frames[i]] = mels[i]
-        wave_d = vocoder(x, sigma=sigma)
+        # true frame counts: each utterance is vocoded as if alone (tacotron2.py:183-187), no padding frame is computed
+        wave_d = vocoder(x, sigma=sigma, lengths=[frames[i] for i in batch.indices])
         # waveforms and mels leave the device through pinned staging (one asynchronous copy each, one sync)
         wave_h = torch.empty(wave_d.shape, dtype=torch.float32, pin_memory=True)
         mel_h = torch.empty(x.shape, dtype=torch.float32, pin_memory=True)
