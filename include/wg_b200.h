@@ -44,7 +44,10 @@ typedef enum wg_status {
 
 typedef enum wg_mode {
   WG_MODE_FP32 = 0,  /* fp32 FFMA arithmetic in the reference's op order; <= 1e-4 max-abs vs reference fp32 */
-  WG_MODE_BF16 = 1   /* tcgen05 BF16 operands, fp32 accumulate/residual; <= 2e-2 max-abs, >= 35 dB SNR */
+  WG_MODE_BF16 = 1,  /* tcgen05 BF16 operands, fp32 accumulate/residual; <= 2e-2 max-abs, >= 35 dB SNR */
+  WG_MODE_TF32X3 = 2 /* fp32-grade on the tensor cores: tcgen05 kind::tf32, every product issued as
+                        a_hi*b_hi + a_lo*b_hi + a_hi*b_lo on fp32 (hi, lo) operand pairs, fp32 accumulation in TMEM,
+                        accurate tanh/exp in the gate; <= 1e-4 max-abs vs reference fp32 (the "fp32/3xTF32 mode") */
 } wg_mode;
 
 /* Constructor arguments of architectures.WaveGlow (waveglow_arch.py:164-181) + arithmetic mode. */
@@ -109,7 +112,8 @@ int wg_infer_host(wg_handle h, const float* mel_host, const float* z_host, float
  * mel at a time (models/tts/tacotron2.py:183-191, models/tts/waveglow.py:76-82) -- bit for bit when both calls use the
  * same internal row layout (always, once the WG_PM environment switch pins it; otherwise the layout of a small
  * stand-alone call is picked by a wave count and the two agree to within the mode's tolerance).
- * WG_MODE_BF16 packs all utterances into one launch sequence; WG_MODE_FP32 runs them one after the other on `stream`.
+ * WG_MODE_BF16 / WG_MODE_TF32X3 pack all utterances into one launch sequence; WG_MODE_FP32 runs them one after the
+ * other on `stream`.
  * Asynchronous, no allocation, graph-capturable (the lengths travel in kernel parameters). */
 int wg_workspace_bytes_ragged(wg_handle h, int32_t B, int32_t T, const int32_t* T_b, size_t* bytes);
 int wg_infer_ragged(wg_handle h, const float* mel, const float* z, float sigma, int32_t deterministic,

@@ -248,8 +248,8 @@ def test_waveglow512_full_size_parity_against_fp32_engine(lib_built):
     err, snr = np.abs(a - b).max(), snr_db(b, a)
     print(f"K3 full size: bf16 vs fp32 engine max-abs {err:.3e}, SNR {snr:.1f} dB, |wave|max {np.abs(b).max():.2f}")
     assert err <= TOL_BF16_ABS and snr >= TOL_BF16_SNR
-    # the first frames of an utterance only see frames inside the receptive field: oracle on a 48-frame prefix
-    ref = OracleWaveGlow(hp, w)(mel[5:6, :48], z[5:6, :48 * 32], 0.6).numpy()
+    # the first 8 frames only see frames < 8 + receptive field (12 flows x 255 positions = 96 frames): oracle on a 120-frame prefix
+    ref = OracleWaveGlow(hp, w)(mel[5:6, :120], z[5:6, :120 * 32], 0.6).numpy()
     assert np.abs(a[5, :2048] - ref[0, :2048]).max() <= TOL_BF16_ABS
     assert np.abs(b[5, :2048] - ref[0, :2048]).max() <= 1e-4
 
@@ -368,7 +368,7 @@ def test_concurrent_wg_infer_on_two_streams(lib_built):
         t.join()
     torch.cuda.synchronize()
     for j in jobs:
-        assert j["rc"] == [0] * 5
+        assert j["rc"] == [0] * 5, lib.wg_last_error(h)
         assert np.array_equal(j["out"].cpu().numpy(), j["serial"])
 
 

@@ -1,0 +1,104 @@
+"""GPU parity, WG_MODE_TF32X3: the fp32-grade mode on the tensor cores (tcgen05 kind::tf32, three products per
+multiply on fp32 (hi, lo) operand pairs). Bar from BASELINE.json north_star: "an fp32/3xTF32 mode within 1e-4 max-abs
+of the reference's fp32 waveform"."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle.waveglow_oracle import OracleWaveGlow
+from text_to_speech_b200.weights import WaveGlowHParams, generate_weights, synthetic_inputs
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _engine(hp, w, mode="tf32x3"):
+    from text_to_speech_b200.engine import WaveGlowEngine
+    return WaveGlowEngine(hp, w, mode=mode, device=0)
+
+
+def _run(eng, mel, z, sigma, deterministic=False, lengths=None):
+    mel_d = torch.from_numpy(np.ascontiguousarray(mel)).cuda()
+    z_d = None if z is None else torch.from_numpy(np.ascontiguousarray(z)).cuda()
+    out = eng.infer_device(mel_d, z_d, sigma=sigma, deterministic=deterministic, lengths=lengths)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+@pytest.mark.parametrize("case", ["wg256_t24", "wg256_bias_t33", "wg256_k1", "wg512_t16"])
+def test_tf32x3_matches_golden(lib_built, case):
+    """The reference-source fixtures (oracle/gen_golden.py), incl. BASELINE.json configs[0] (wg256_k1: 1 x 200 frames)
+    and the 512-channel default width."""
+    hp, w, f = load_golden(case)
+    eng = _engine(hp, w)
+    sigma = float(f["sigma"])
+    out = _run(eng, f["mel"], f["z"], sigma)
+    assert out.shape == f["wave_reference_fp32"].shape
+    err = np.abs(out - f["wave_reference_fp32"]).max()
+    err64 = np.abs(out - f["wave_oracle_fp64"]).max()
+    print(f"{case}: tf32x3 err vs reference fp32 {err:.2e}, vs fp64 {err64:.2e}, launches {eng.last_launch_count}")
+    assert err <= TOL and err64 <= TOL
+    det = _run(eng, f["mel"], None, sigma, deterministic=True)
+    assert np.abs(det - f["wave_reference_deterministic"]).max() <= TOL
+    eng.close()
+
+
+def test_tf32x3_intermediates_against_oracle_taps(lib_built):
+    hp = WaveGlowHParams()
+    w = generate_weights(hp, 32, bias_std=0.05)
+    mel, z = synthetic_inputs(5, 2, 7, hp)          # 2 x (7 + 4) phase-block rows: one partially filled tile per phase
+    taps = {}
+    OracleWaveGlow(hp, w).infer(mel, z, 0.6, taps=taps)
+    eng = _engine(hp, w)
+    mel_d, z_d = torch.from_numpy(mel).cuda(), torch.from_numpy(z).cuda()
+    for (k, i) in [(11, -1), (11, 0), (11, 7), (7, 3), (0, 6)]:
+        h, acc = eng.debug_prefix(mel_d, z_d, 0.6, k, i)
+        torch.cuda.synchronize()
+        if i >= 0 and i < 7:
+            ref_h = taps[f"flow{k}/layer{i}/audio"].reshape(-1, hp.n_channels).numpy()
+            err = np.abs(h.cpu().numpy() - ref_h).max()
+            print(f"flow {k} layer {i}: residual stream max-abs err {err:.2e} (|h|max {np.abs(ref_h).max():.2f})")
+            assert err <= 2e-5 * max(1.0, np.abs(ref_h).max()), (k, i)
+    eng.close()
+
+
+@pytest.mark.parametrize("B,T", [(1, 1), (2, 5), (3, 37), (2, 150)])
+def test_tf32x3_shapes_against_fp32_engine_and_oracle(lib_built, B, T):
+    hp = WaveGlowHParams()
+    w = generate_weights(hp, 31, bias_std=0.05)
+    mel, z = synthetic_inputs(100 + B * 10 + T, B, T, hp)
+    e3 = _engine(hp, w)
+    out = _run(e3, mel, z, 0.8)
+    ffma = _run(_engine(hp, w, "fp32"), mel, z, 0.8)
+    err = np.abs(out - ffma).max()
+    print(f"{B} x {T}: tf32x3 vs the FFMA fp32 engine {err:.2e}")
+    assert err <= TOL
+    if B * T <= 120:
+        assert np.abs(out - OracleWaveGlow(hp, w)(mel, z, 0.8).numpy()).max() <= TOL
+    assert np.array_equal(_run(e3, mel, z, 0.8), out)                                  # reproducible
+    assert np.array_equal(_run(e3, mel[B - 1:B], z[B - 1:B], 0.8)[0], out[B - 1])      # utterances never interact
+    e3.close()
+
+
+def test_tf32x3_ragged_batch(lib_built):
+    hp = WaveGlowHParams()
+    w = generate_weights(hp, 1234)
+    lengths = [40, 9, 23]
+    mel, z = synthetic_inputs(3, 3, 40, hp)
+    eng = _engine(hp, w)
+    out = _run(eng, mel, z, 0.6, lengths=lengths)
+    oracle = OracleWaveGlow(hp, w)
+    for b, n in enumerate(lengths):
+        alone = _run(eng, mel[b:b + 1, :n], z[b:b + 1, :n * 32], 0.6)[0]
+        assert np.array_equal(out[b, :n * 256], alone) and not out[b, n * 256:].any()
+        ref = oracle(mel[b:b + 1, :n], z[b:b + 1, :n * 32], 0.6).numpy()[0]
+        assert np.abs(out[b, :n * 256] - ref).max() <= TOL
+    eng.close()
+
+
+def test_tf32x3_refuses_what_it_cannot_run(lib_built):
+    from text_to_speech_b200.engine import WaveGlowEngine, WaveGlowError
+    hp = WaveGlowHParams(n_channels=64)
+    with pytest.raises(WaveGlowError, match="TF32X3"):
+        WaveGlowEngine(hp, generate_weights(hp, 1), mode="tf32x3")

@@ -14,12 +14,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwg_b200.so")
 SOURCES = [os.path.join(_HERE, "csrc", "engine.cu"), os.path.join(_HERE, "csrc", "mel.cu"),
            os.path.join(_HERE, "csrc", "taco.cu")]
-HEADERS = [os.path.join(_HERE, "csrc", f) for f in ("common.cuh", "simt_kernels.cuh", "tc_kernels.cuh", "tc_c512_kernels.cuh")] + \
+HEADERS = [os.path.join(_HERE, "csrc", f) for f in ("common.cuh", "simt_kernels.cuh", "tc_kernels.cuh", "tc_c512_kernels.cuh", "tc_tf32_kernels.cuh")] + \
           [os.path.join(os.path.dirname(_HERE), "include", f) for f in ("wg_b200.h", "wg_mel_b200.h", "wg_taco_b200.h")]
 
 WG_OK = 0
-WG_MODE_FP32, WG_MODE_BF16 = 0, 1
-MODES = {"fp32": WG_MODE_FP32, "bf16": WG_MODE_BF16}
+WG_MODE_FP32, WG_MODE_BF16, WG_MODE_TF32X3 = 0, 1, 2
+MODES = {"fp32": WG_MODE_FP32, "bf16": WG_MODE_BF16, "tf32x3": WG_MODE_TF32X3}
 ABI_VERSION = 2
 
 # every symbol include/wg_b200.h declares (tests check the library exports all of them)

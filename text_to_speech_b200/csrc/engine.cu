@@ -21,6 +21,7 @@
 #include "simt_kernels.cuh"
 #include "tc_kernels.cuh"
 #include "tc_c512_kernels.cuh"
+#include "tc_tf32_kernels.cuh"
 
 namespace {
 
@@ -57,6 +58,7 @@ struct LayerW {
   float* b2 = nullptr;    // [C]
   std::vector<float> wse_h;  // [C, 8] = Wskip @ Wend (fp32), host copy: passed in the kernel parameter bank
   std::vector<float> wse_p;  // the same in the packed-fold layout [channel pair][column][even, odd] (gate_step2)
+  float* wse_d = nullptr;    // tf32x3 mode: device copy of wse_h
 };
 
 }  // namespace
@@ -74,6 +76,8 @@ struct wg_engine {
   __nv_bfloat16* W1 = nullptr;     // [n_flows*n_layers*2C, 3C+S]
   __nv_bfloat16* W2 = nullptr;     // [n_flows*n_layers*C, C]
   __nv_bfloat16* V = nullptr;      // [n_flows*n_layers*R*2C, Kup]: (Wup_r @ Wcond) per layer and upsample phase
+  // tf32x3 mode: the same stacked matrices as fp32 (hi, lo) pairs (tc_tf32_kernels.cuh); W1 holds the conv part only
+  wg::Tf32Weights t3{};
   // start-conv fold (phase-major bf16 path): layer 0 of a flow consumes the audio rows directly
   __nv_bfloat16* W0 = nullptr;     // [n_flows*2C, 64]: per tap [Wstart@Win_tap hi | same | lo | bstart@Win_tap hi | lo | 0 0], chunk-packed rows
   __nv_bfloat16* H0 = nullptr;     // [n_flows*C, 64]: columns 48..63 = [Wstart hi | same | lo | bstart hi | lo | 0 0]
@@ -107,8 +111,8 @@ struct DeviceGuard {
   int prev = -1;
   explicit DeviceGuard(int dev) {
     if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-    if (prev != dev) WG_CK(cudaSetDevice(dev));
-    else prev = -1;
+    WG_CK(cudaSetDevice(dev));   // always: this also binds the device's primary context to a thread that has none yet
+    if (prev == dev) prev = -1;
   }
   ~DeviceGuard() {
     if (prev >= 0) cudaSetDevice(prev);
@@ -180,6 +184,7 @@ struct Ws {  // workspace carving for one (B, T)
   size_t spect = 0, h32 = 0, acts = 0, skip = 0, acc8 = 0, audio0 = 0, audio1 = 0;
   size_t spect16 = 0, h16a = 0, h16b = 0, hlo = 0, aup16 = 0, acts16 = 0, a0 = 0;
   size_t g_off = 0, g_len = 0, g_rowb = 0;   // ragged geometry tables (RowGeom)
+  size_t t3_hhi0 = 0, t3_hhi1 = 0, t3_hlo0 = 0, t3_hlo1 = 0, t3_ahi = 0, t3_alo = 0, t3_chi = 0, t3_clo = 0;
   size_t total = 0;
 };
 
@@ -197,6 +202,7 @@ int pm_gap(const wg_engine* e) { return ((1 << (e->cfg.n_layers - 1)) + e->R - 1
 // 22 + 22 + 6 and need the materialised spect. They only differ in speed -- both meet the same parity bar -- and only
 // small inputs (a few hundred tiles) ever pick position-major. WG_PM=0/1 forces one.
 bool use_pm(const wg_engine* e, int B, int T) {
+  if (e->cfg.mode == WG_MODE_TF32X3) return true;    // the tf32x3 kernels only exist for the phase-major layout
   if (e->cfg.mode != WG_MODE_BF16 || !e->V) return false;
   if (e->pm_policy == 0) return false;
   if (e->pm_policy == 1) return true;
@@ -219,13 +225,25 @@ Ws carve(const wg_engine* e, int B, int T, const Ragged* rg = nullptr) {
     return o;
   };
   if (e->cfg.mode == WG_MODE_FP32) w.h32 = take(M * e->C * 4);
-  w.acc8 = take(M * 8 * 4);
+  const size_t acc_parts = e->cfg.mode == WG_MODE_TF32X3 ? (size_t)(2 * e->C / 256) : 1;   // tf32x3: one partial per gate chunk
+  w.acc8 = take(acc_parts * M * 8 * 4);
   w.audio0 = take(M * 8 * 4);
   w.audio1 = take(M * 8 * 4);
   if (e->cfg.mode == WG_MODE_FP32) {
     w.spect = take(M * e->S * 4);
     w.acts = take(M * e->C * 4);
     w.skip = take(M * e->C * 4);
+  } else if (e->cfg.mode == WG_MODE_TF32X3) {
+    // fp32 (hi, lo) pairs: residual stream x2 (ping-pong), acts, mel window; one partial fold accumulator per gate chunk
+    w.t3_hhi0 = take(M * e->C * 4); w.t3_hhi1 = take(M * e->C * 4);
+    w.t3_hlo0 = take(M * e->C * 4); w.t3_hlo1 = take(M * e->C * 4);
+    w.t3_ahi = take(M * e->C * 4); w.t3_alo = take(M * e->C * 4);
+    w.t3_chi = take(rows1 * e->Kup * 4); w.t3_clo = take(rows1 * e->Kup * 4);
+    if (rg) {
+      w.g_off = take((size_t)B * 4);
+      w.g_len = take((size_t)B * 4);
+      w.g_rowb = take(rows1 * 4);
+    }
   } else {
     if (!pm) w.spect16 = take(M * e->S * 2);
     w.h16a = take(M * e->C * 2);
@@ -246,7 +264,7 @@ Ws carve(const wg_engine* e, int B, int T, const Ragged* rg = nullptr) {
 
 void check_shape(const wg_engine* e, int B, int T) {
   if (B <= 0 || T <= 0) fail(WG_ERR_INVALID, "B and T must be positive (got B=%d, T=%d)", B, T);
-  const double M = (double)B * (T + (e->cfg.mode == WG_MODE_BF16 ? pm_gap(e) : 0)) * e->R;   // internal rows, gap rows included
+  const double M = (double)B * (T + (e->cfg.mode != WG_MODE_FP32 ? pm_gap(e) : 0)) * e->R;   // internal rows, gap rows included
   if (M * std::max(e->S, e->C) > 2.0e9) fail(WG_ERR_INVALID, "B*T too large (B=%d, T=%d)", B, T);
 }
 
@@ -295,7 +313,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
   check_shape(e, B, T);
   if (!mel || (!out && stop_flow < 0)) fail(WG_ERR_INVALID, "mel/out must not be NULL");
   if (!deterministic && !z) fail(WG_ERR_INVALID, "z must be given unless deterministic");
-  if (rg && e->cfg.mode != WG_MODE_BF16) fail(WG_ERR_INVALID, "internal: ragged geometry is a BF16-path layout");
+  if (rg && e->cfg.mode == WG_MODE_FP32) fail(WG_ERR_INVALID, "internal: ragged geometry belongs to the phase-major layouts");
   const Ws w = carve(e, B, T, rg);
   if (!workspace || ws_bytes < w.total)
     fail(WG_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.total, ws_bytes);
@@ -306,7 +324,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
   char* base = static_cast<char*>(workspace);
   const wg_config& c = e->cfg;
   const int C = e->C, S = e->S, R = e->R, L = T * R, M = B * L;
-  const bool bf16 = c.mode == WG_MODE_BF16;
+  const bool bf16 = c.mode == WG_MODE_BF16, tf32 = c.mode == WG_MODE_TF32X3, ffma = c.mode == WG_MODE_FP32;
   const bool pm = rg ? true : use_pm(e, B, T);
   // internal row geometry of the bf16 buffers (fp32 mode: position-major)
   RowGeom geo = pm ? RowGeom{R, T, T + pm_gap(e), B} : RowGeom{1, L, L, B};
@@ -329,7 +347,11 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
     if (out) CK(cudaMemsetAsync(out, 0, (size_t)B * L * c.n_group * sizeof(float), st));
   }
   const int Mi = geo.rows();   // internal rows (== M unless phase-major: gap rows)
-  float* h32 = bf16 ? nullptr : reinterpret_cast<float*>(base + w.h32);
+  float* h32 = ffma ? reinterpret_cast<float*>(base + w.h32) : nullptr;
+  float* t3_hhi[2] = {reinterpret_cast<float*>(base + w.t3_hhi0), reinterpret_cast<float*>(base + w.t3_hhi1)};
+  float* t3_hlo[2] = {reinterpret_cast<float*>(base + w.t3_hlo0), reinterpret_cast<float*>(base + w.t3_hlo1)};
+  const int t3_parts = tf32 ? 2 * C / 256 : 1;                       // partial fold accumulators (one per gate chunk)
+  const size_t t3_acc_stride = (size_t)geo.rows() * 8;                // floats between two partials
   float* acc8 = reinterpret_cast<float*>(base + w.acc8);
   float* audio[2] = {reinterpret_cast<float*>(base + w.audio0), reinterpret_cast<float*>(base + w.audio1)};
   float* spect = reinterpret_cast<float*>(base + w.spect);
@@ -348,8 +370,17 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
   const float* zz = deterministic ? nullptr : z;
 
   TcPlan plan;
+  Tf32Plan plan3;
   // ---- (1) upsample + trim + regroup: spect[B*L, S]  (waveglow_arch.py:245-253) ---------------
-  if (!bf16) {
+  if (tf32) {
+    RowGeom geo1 = geo;
+    geo1.R = 1;
+    tf32_prepare(plan3, e->sm_count, C, R, e->Kup, c.n_mel_channels, c.n_flows * c.n_layers, geo.rows_per_phase(), geo1,
+                 rg ? 0 : geo.Tp, geo.T, e->t3, t3_hhi[0], t3_hhi[1], t3_hlo[0], t3_hlo[1],
+                 reinterpret_cast<float*>(base + w.t3_chi), reinterpret_cast<float*>(base + w.t3_clo),
+                 reinterpret_cast<float*>(base + w.t3_ahi), reinterpret_cast<float*>(base + w.t3_alo), acc8, t3_acc_stride);
+    e->launches += tf32_upsample(plan3, mel, st);
+  } else if (ffma) {
     GemmArgs g{};
     g.nseg = UPSAMPLE_K / HOP;
     for (int j = 0; j < g.nseg; ++j) g.seg[j] = ASeg{mel, c.n_mel_channels, c.n_mel_channels, -j};
@@ -376,7 +407,9 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
     a.sigma = sigma; a.audio_out = audio[cur]; a.M = Mi; a.C = C;
     a.Wstart = fold0 ? nullptr : e->flows[F - 1].Wstart; a.bstart = e->flows[F - 1].bstart;
     a.n_half_next = e->flows[F - 1].n_half; a.h32 = h32; a.h16 = bf16 ? h16[hcur] : nullptr; a.hlo = bf16 ? hlo : nullptr;
-    if (bf16) { a.acc8_rearm = acc8; std::memcpy(a.acc8_init, e->flows[F - 1].bse8, sizeof a.acc8_init); }
+    if (tf32) { a.hf_hi = t3_hhi[hcur]; a.hf_lo = t3_hlo[hcur]; }
+    a.acc_parts = t3_parts; a.acc_part_stride = t3_acc_stride;
+    if (!ffma) { a.acc8_rearm = acc8; std::memcpy(a.acc8_init, e->flows[F - 1].bse8, sizeof a.acc8_init); }
     launch_boundary(e, a, st);
     z_off = a.n_inject;
   }
@@ -398,7 +431,12 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
   };
 
   auto dump = [&](void) {
-    if (h_out && !bf16) CK(cudaMemcpyAsync(h_out, h32, (size_t)M * C * 4, cudaMemcpyDeviceToDevice, st));
+    if (h_out && ffma) CK(cudaMemcpyAsync(h_out, h32, (size_t)M * C * 4, cudaMemcpyDeviceToDevice, st));
+    if (h_out && tf32) {
+      const size_t n = (size_t)Mi * C;
+      hilo_f32_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t3_hhi[hcur], t3_hlo[hcur], h_out, geo, C);
+      CK(cudaGetLastError());
+    }
     if (h_out && bf16) {
       const size_t n = (size_t)Mi * C;
       hilo_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h16[hcur], hlo, h_out, geo, C);
@@ -406,7 +444,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
     }
     if (acc_out) {
       const size_t n = (size_t)Mi * 8;
-      unpermute_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc8, acc_out, geo, 8);
+      unpermute_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc8, acc_out, geo, 8, t3_parts, t3_acc_stride);
       CK(cudaGetLastError());
     }
   };
@@ -418,7 +456,17 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
       const LayerW& lw = e->layers[k * c.n_layers + i];
       const int d = 1 << i;
       const bool last = i == c.n_layers - 1;
-      if (!bf16) {
+      if (tf32) {
+        // one event pair per flow around its back-to-back layer launches (gate + residual kernel per layer)
+        if (i == 0) {
+          prof_mark();
+          if (e->profiling) e->ev_count.push_back(0);
+        }
+        if (e->profiling) e->ev_count.back() += 1;
+        e->launches += tf32_wn_layer(plan3, k * c.n_layers + i, d, last, hcur, lw.b1_pm, lw.b2, lw.wse_d, st);
+        if (last || (k == stop_flow && i == stop_layer)) prof_mark();
+        if (!last) hcur ^= 1;
+      } else if (ffma) {
         // in-conv (dilated k=3) + cond 1x1 as one K = 3C+S contraction, gate fused (:113-127, :19-24)
         GemmArgs g{};
         g.nseg = 4;
@@ -458,7 +506,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
         if (!last) hcur ^= 1;
       }
       if (k == stop_flow && i == stop_layer) {
-        if (!bf16 && acc_out) {
+        if (ffma && acc_out) {
           end_conv_kernel<<<(M * 32 + 255) / 256, 256, 0, st>>>(skip, fw.Wend8, fw.bend8, acc8, M, C);
           CK(cudaGetLastError());
         }
@@ -466,7 +514,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
         return;
       }
     }
-    if (!bf16) {
+    if (ffma) {
       end_conv_kernel<<<(int)(((size_t)M * 32 + 255) / 256), 256, 0, st>>>(skip, fw.Wend8, fw.bend8, acc8, M, C);
       CK(cudaGetLastError());
       e->launches++;
@@ -476,6 +524,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
     a.geo = geo;
     a.first = 0; a.acc8 = acc8; a.audio_in = audio[cur]; a.z = zz; a.n_group = c.n_group;
     a.sigma = sigma; a.c_in = 2 * fw.n_half; a.M = Mi; a.C = C;
+    a.acc_parts = t3_parts; a.acc_part_stride = t3_acc_stride;
     std::memcpy(a.winv, fw.winv, sizeof a.winv);
     const bool early = (k % c.n_early_every == 0) && k > 0;
     a.n_inject = early ? c.n_early_size : 0;
@@ -487,7 +536,8 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
       a.n_half_next = e->flows[k - 1].n_half; a.h32 = h32;
       hcur = 0;
       a.h16 = bf16 ? h16[hcur] : nullptr; a.hlo = bf16 ? hlo : nullptr;
-      if (bf16) { a.acc8_rearm = acc8; std::memcpy(a.acc8_init, e->flows[k - 1].bse8, sizeof a.acc8_init); }
+      if (tf32) { a.hf_hi = t3_hhi[hcur]; a.hf_lo = t3_hlo[hcur]; }
+      if (!ffma) { a.acc8_rearm = acc8; std::memcpy(a.acc8_init, e->flows[k - 1].bse8, sizeof a.acc8_init); }
     } else {
       a.audio_out = out;  // [B*L, 8] == [B, 8L]  (waveglow_arch.py:306)
       a.final_out = 1;
@@ -503,7 +553,8 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
   const wg_config& c = *cfg;
   e->cfg = c;
   e->device = device;
-  if (c.mode != WG_MODE_FP32 && c.mode != WG_MODE_BF16) fail(WG_ERR_INVALID, "unknown mode %d", c.mode);
+  if (c.mode != WG_MODE_FP32 && c.mode != WG_MODE_BF16 && c.mode != WG_MODE_TF32X3) fail(WG_ERR_INVALID, "unknown mode %d", c.mode);
+  const bool tf32 = c.mode == WG_MODE_TF32X3;
   if (c.kernel_size != 3) fail(WG_ERR_UNSUPPORTED, "kernel_size must be 3 (got %d)", c.kernel_size);
   if (c.n_group < 2 || c.n_group > 8 || c.n_group % 2 || HOP % c.n_group)
     fail(WG_ERR_UNSUPPORTED, "n_group must be an even divisor of 256 that is <= 8 (got %d)", c.n_group);
@@ -532,9 +583,12 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
   cudaDeviceProp prop{};
   CK(cudaGetDeviceProperties(&prop, device));
   e->sm_count = prop.multiProcessorCount;
-  if (c.mode == WG_MODE_BF16 && prop.major != 10)
-    fail(WG_ERR_UNSUPPORTED, "WG_MODE_BF16 needs an sm_100 GPU (tcgen05/TMEM); device is sm_%d%d", prop.major,
+  if (c.mode != WG_MODE_FP32 && prop.major != 10)
+    fail(WG_ERR_UNSUPPORTED, "WG_MODE_BF16 / WG_MODE_TF32X3 need an sm_100 GPU (tcgen05/TMEM); device is sm_%d%d", prop.major,
          prop.minor);
+  if (tf32 && (c.n_channels % 128 || (UPSAMPLE_K / HOP * c.n_mel_channels) % 32))
+    fail(WG_ERR_UNSUPPORTED, "WG_MODE_TF32X3 needs n_channels %% 128 == 0 and 4*n_mel_channels %% 32 == 0 (got %d, %d)",
+         c.n_channels, c.n_mel_channels);
 
   const int C = c.n_channels, NL = c.n_layers, F = c.n_flows;
   e->C = C;
@@ -593,6 +647,8 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
       for (int g = 0; g < G; ++g) ub_vec[m * G + g] = ub.data[m];
     if (c.mode == WG_MODE_FP32) {
       e->Wup = upload(e, wup_f32);
+    } else if (tf32) {
+      e->Kup = J * NM;      // 320: ten K-blocks of 32 floats
     } else {
       e->Kup = (int)align_up((size_t)J * NM, 64);
       std::vector<__nv_bfloat16> wp((size_t)N * e->Kup, f2bf(0.f));
@@ -611,6 +667,11 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
   e->layers.resize((size_t)F * NL);
   const int K1 = 3 * C + S;
   std::vector<__nv_bfloat16> w1all, w2all, w0all, h0all;
+  std::vector<float> t3w1h, t3w1l, t3w2h, t3w2l;      // tf32x3: (hi, lo) pairs, stacked over the layers
+  if (tf32) {
+    t3w1h.assign((size_t)F * NL * 2 * C * 3 * C, 0.f); t3w1l.assign(t3w1h.size(), 0.f);
+    t3w2h.assign((size_t)F * NL * C * C, 0.f); t3w2l.assign(t3w2h.size(), 0.f);
+  }
   const bool build_fold0 = c.mode == WG_MODE_BF16 && NL > 1;
   if (c.mode == WG_MODE_BF16) {
     w1all.assign((size_t)F * NL * 2 * C * K1, f2bf(0.f));
@@ -685,12 +746,21 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
         std::vector<float> b1((size_t)2 * C), b2((size_t)C, 0.f);
         lw.wse_h.assign((size_t)C * 8, 0.f);
         std::vector<float>& wse = lw.wse_h;
-        __nv_bfloat16* w1 = w1all.data() + ((size_t)k * NL + i) * 2 * C * K1;
+        __nv_bfloat16* w1 = tf32 ? nullptr : w1all.data() + ((size_t)k * NL + i) * 2 * C * K1;
         for (int pcol = 0; pcol < 2 * C; ++pcol) {
           const int chunk = pcol >> 8, wi = pcol & 255;
           const int col = wi < 128 ? 128 * chunk + wi : C + 128 * chunk + (wi - 128);
           b1[pcol] = inb.data[col] + cb.data[col];
-          for (int kk = 0; kk < K1; ++kk) w1[(size_t)pcol * K1 + kk] = f2bf(wsrc(kk, col));
+          if (tf32) {
+            const size_t row = (((size_t)k * NL + i) * 2 * C + pcol) * 3 * C;
+            for (int kk = 0; kk < 3 * C; ++kk) {
+              const float v = wsrc(kk, col), hi = tf32_rna_host(v);
+              t3w1h[row + kk] = hi;
+              t3w1l[row + kk] = v - hi;
+            }
+          } else {
+            for (int kk = 0; kk < K1; ++kk) w1[(size_t)pcol * K1 + kk] = f2bf(wsrc(kk, col));
+          }
         }
         if (build_fold0 && i == 0) {
           // start fold (a0_build_kernel): 16 K columns per tap = [G hi (4) | G hi (4) | G lo (4) | g hi | g lo | 0 0] with
@@ -749,10 +819,19 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
         }
         const int skip_off = (i < NL - 1) ? C : 0;
         if (i < NL - 1) {
-          __nv_bfloat16* w2 = w2all.data() + ((size_t)k * NL + i) * C * C;
+          __nv_bfloat16* w2 = tf32 ? nullptr : w2all.data() + ((size_t)k * NL + i) * C * C;
           for (int n = 0; n < C; ++n) {
             b2[n] = rb.data[n];
-            for (int kk = 0; kk < C; ++kk) w2[(size_t)n * C + kk] = f2bf(rw.data[(size_t)kk * rs + n]);
+            for (int kk = 0; kk < C; ++kk) {
+              const float v = rw.data[(size_t)kk * rs + n];
+              if (tf32) {
+                const size_t at = (((size_t)k * NL + i) * C + n) * C + kk;
+                t3w2h[at] = tf32_rna_host(v);
+                t3w2l[at] = v - t3w2h[at];
+              } else {
+                w2[(size_t)n * C + kk] = f2bf(v);
+              }
+            }
           }
         }
         // skip o end fold: acc8 += acts @ (Wskip @ Wend);  bias folded into bse8
@@ -773,11 +852,51 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
           for (int cc = 0; cc < 8; ++cc) lw.wse_p[((size_t)(ch >> 1) * 8 + cc) * 2 + (ch & 1)] = wse[(size_t)ch * 8 + cc];
         lw.b1 = upload(e, b1);
         lw.b2 = upload(e, b2);
+        if (tf32) lw.wse_d = upload(e, lw.wse_h);
       }
     }
-    if (c.mode == WG_MODE_BF16) {
+    if (c.mode != WG_MODE_FP32) {
       for (int j = 0; j < 8; ++j) fw.bse8[j] = (float)bse[j];
     }
+  }
+  if (tf32) {
+    e->t3.W1h = upload(e, t3w1h); e->t3.W1l = upload(e, t3w1l);
+    e->t3.W2h = upload(e, t3w2h); e->t3.W2l = upload(e, t3w2l);
+    tc_init();
+    tf32_init();
+    // folded conditioning weights as an fp32 (hi, lo) pair: V[(layer*R + r)*2C + n][k] = sum_s Wup_r[k][s] * Wcond[s][n]
+    const int Kw = e->Kup;
+    float *d_wup = nullptr, *d_wc = nullptr, *d_tmp = nullptr, *vh = nullptr, *vl = nullptr;
+    const size_t vcount = (size_t)F * NL * R * 2 * C * Kw;
+    std::vector<float> wup_rk((size_t)R * Kw * S);
+    for (int r = 0; r < R; ++r)
+      for (int kk = 0; kk < Kw; ++kk)
+        std::memcpy(&wup_rk[((size_t)r * Kw + kk) * S], &wup_f32[(size_t)kk * R * S + (size_t)r * S], (size_t)S * 4);
+    CK(cudaMalloc(&d_wup, wup_rk.size() * 4));
+    CK(cudaMalloc(&d_wc, (size_t)S * 2 * C * 4));
+    CK(cudaMalloc(&d_tmp, (size_t)R * Kw * 2 * C * 4));
+    CK(cudaMalloc(&vh, vcount * 4));
+    e->allocs.push_back(vh);
+    CK(cudaMalloc(&vl, vcount * 4));
+    e->allocs.push_back(vl);
+    CK(cudaMemcpy(d_wup, wup_rk.data(), wup_rk.size() * 4, cudaMemcpyHostToDevice));
+    for (int li = 0; li < F * NL; ++li) {
+      CK(cudaMemcpy(d_wc, wcond_packed[li].data(), (size_t)S * 2 * C * 4, cudaMemcpyHostToDevice));
+      GemmArgs g{};
+      g.nseg = 1;
+      g.seg[0] = ASeg{d_wup, S, S, 0};
+      g.W = d_wc; g.bias = nullptr; g.M = R * Kw; g.N = 2 * C; g.L = R * Kw;
+      g.out0 = d_tmp; g.ld0 = 2 * C;
+      dim3 grid((g.N + SG_BN - 1) / SG_BN, (g.M + SG_BM - 1) / SG_BM);
+      gemm_f32_kernel<EPI_STORE><<<grid, SG_THREADS>>>(g);
+      const size_t n = (size_t)R * Kw * 2 * C;
+      const size_t at = (size_t)li * R * 2 * C * Kw;
+      fold_store_tf32_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_tmp, vh + at, vl + at, R, Kw, 2 * C);
+    }
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    cudaFree(d_wup); cudaFree(d_wc); cudaFree(d_tmp);
+    e->t3.Vh = vh; e->t3.Vl = vl;
   }
   if (c.mode == WG_MODE_BF16) {
     e->W1 = upload(e, w1all);
@@ -902,7 +1021,7 @@ void infer_ragged(wg_engine* e, const float* mel, const float* z, float sigma, i
     run_infer(e, mel, z, sigma, deterministic, B, T, out, workspace, ws_bytes, st, -2, -2, nullptr, nullptr);
     return;
   }
-  if (e->cfg.mode == WG_MODE_BF16) {
+  if (e->cfg.mode != WG_MODE_FP32) {
     run_infer(e, mel, z, sigma, deterministic, B, T, out, workspace, ws_bytes, st, -2, -2, nullptr, nullptr, &rg);
     return;
   }
@@ -930,7 +1049,7 @@ void infer_host(wg_engine* h, const float* mel_host, const float* z_host, float 
     const Ragged rg = make_ragged(h, B, T, T_b);
     int tmax = 0;
     for (int l : rg.len) tmax = std::max(tmax, l);
-    ws_b = h->cfg.mode != WG_MODE_BF16 ? carve(h, 1, tmax).total : is_uniform(rg, T) ? carve(h, B, T).total : carve(h, B, T, &rg).total;
+    ws_b = h->cfg.mode == WG_MODE_FP32 ? carve(h, 1, tmax).total : is_uniform(rg, T) ? carve(h, B, T).total : carve(h, B, T, &rg).total;
   } else {
     ws_b = carve(h, B, T).total;
   }
@@ -1017,7 +1136,7 @@ int wg_workspace_bytes_ragged(wg_handle h, int32_t B, int32_t T, const int32_t* 
   if (!h || !bytes) return WG_ERR_INVALID;
   return guarded(h, [&] {
     const Ragged rg = make_ragged(h, B, T, T_b);
-    if (h->cfg.mode != WG_MODE_BF16) {   // FP32 mode runs the utterances one after the other in the same scratch
+    if (h->cfg.mode == WG_MODE_FP32) {   // FP32 mode runs the utterances one after the other in the same scratch
       int tmax = 0;
       for (int l : rg.len) tmax = std::max(tmax, l);
       *bytes = carve(h, 1, tmax).total;

@@ -282,6 +282,10 @@ struct BoundaryArgs {
   float* h32;             // [M, C]
   __nv_bfloat16* h16;     // [M, C] or null: bf16(h)            (bf16 mode: residual stream = hi + lo)
   __nv_bfloat16* hlo;     // [M, C] or null: bf16(h - bf16(h))
+  float* hf_hi;           // [M, C] or null: tf32(h)            (tf32x3 mode: residual stream = hi + lo, both fp32)
+  float* hf_lo;           // [M, C] or null: h - tf32(h)
+  int acc_parts;          // acc8 is the sum of this many partial accumulators (tf32x3: one per gate chunk), >= 1
+  size_t acc_part_stride; // floats between two partials
   int M;
   // bf16 mode: re-arm the folded skip/end accumulator for the next flow (acc8 = bias term) once
   // this flow's value has been consumed
@@ -326,8 +330,14 @@ flow_boundary_kernel(const __grid_constant__ BoundaryArgs a) {
         const int nh = a.c_in >> 1;
         const float4 i0 = *reinterpret_cast<const float4*>(a.audio_in + (size_t)m * 8);
         const float4 i1 = *reinterpret_cast<const float4*>(a.audio_in + (size_t)m * 8 + 4);
-        const float4 o0 = *reinterpret_cast<const float4*>(a.acc8 + (size_t)m * 8);
-        const float4 o1 = *reinterpret_cast<const float4*>(a.acc8 + (size_t)m * 8 + 4);
+        float4 o0 = *reinterpret_cast<const float4*>(a.acc8 + (size_t)m * 8);
+        float4 o1 = *reinterpret_cast<const float4*>(a.acc8 + (size_t)m * 8 + 4);
+        for (int pp = 1; pp < a.acc_parts; ++pp) {      // partial accumulators, summed in a fixed order
+          const float4 q0 = *reinterpret_cast<const float4*>(a.acc8 + pp * a.acc_part_stride + (size_t)m * 8);
+          const float4 q1 = *reinterpret_cast<const float4*>(a.acc8 + pp * a.acc_part_stride + (size_t)m * 8 + 4);
+          o0.x += q0.x; o0.y += q0.y; o0.z += q0.z; o0.w += q0.w;
+          o1.x += q1.x; o1.y += q1.y; o1.z += q1.z; o1.w += q1.w;
+        }
         float in[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
         const float o[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
         for (int j = 0; j < nh; ++j) in[nh + j] = (in[nh + j] - o[j]) / expf(o[nh + j]);
@@ -350,6 +360,10 @@ flow_boundary_kernel(const __grid_constant__ BoundaryArgs a) {
             make_float4(a.acc8_init[0], a.acc8_init[1], a.acc8_init[2], a.acc8_init[3]);
         *reinterpret_cast<float4*>(a.acc8_rearm + (size_t)m * 8 + 4) =
             make_float4(a.acc8_init[4], a.acc8_init[5], a.acc8_init[6], a.acc8_init[7]);
+        for (int pp = 1; pp < a.acc_parts; ++pp) {
+          *reinterpret_cast<float4*>(a.acc8_rearm + pp * a.acc_part_stride + (size_t)m * 8) = make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(a.acc8_rearm + pp * a.acc_part_stride + (size_t)m * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) s_a0[tid][j] = x[j];
@@ -397,6 +411,20 @@ flow_boundary_kernel(const __grid_constant__ BoundaryArgs a) {
       }
       *reinterpret_cast<uint4*>(a.h16 + (size_t)m * a.C + c8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
       *reinterpret_cast<uint4*>(a.hlo + (size_t)m * a.C + c8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+    if (a.hf_hi) {
+      float hi[8], lo[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        uint32_t u;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v[q]));
+        hi[q] = __uint_as_float(u);
+        lo[q] = v[q] - hi[q];
+      }
+      *reinterpret_cast<float4*>(a.hf_hi + (size_t)m * a.C + c8) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<float4*>(a.hf_hi + (size_t)m * a.C + c8 + 4) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+      *reinterpret_cast<float4*>(a.hf_lo + (size_t)m * a.C + c8) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      *reinterpret_cast<float4*>(a.hf_lo + (size_t)m * a.C + c8 + 4) = make_float4(lo[4], lo[5], lo[6], lo[7]);
     }
   }
 }

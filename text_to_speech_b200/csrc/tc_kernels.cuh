@@ -1224,15 +1224,30 @@ __global__ void hilo_to_f32_kernel(const __nv_bfloat16* __restrict__ hi, const _
   out[geo.position_major(b, r, t) * C + c] = __bfloat162float(hi[idx]) + __bfloat162float(lo[idx]);
 }
 
-// debug: float rows [rows, W] re-ordered the same way
-__global__ void unpermute_rows_kernel(const float* __restrict__ in, float* __restrict__ out, const RowGeom geo, int W) {
+// debug: float rows [rows, W] re-ordered the same way; `parts` partial buffers `stride` floats apart are summed
+__global__ void unpermute_rows_kernel(const float* __restrict__ in, float* __restrict__ out, const RowGeom geo, int W,
+                                      int parts = 1, size_t stride = 0) {
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<size_t>(geo.rows()) * W) return;
   const int m = static_cast<int>(idx / W);
   const int c = static_cast<int>(idx - static_cast<size_t>(m) * W);
   int b, r, t;
   if (!geo.decode(m, b, r, t)) return;
-  out[geo.position_major(b, r, t) * W + c] = in[idx];
+  float v = in[idx];
+  for (int pp = 1; pp < parts; ++pp) v += in[pp * stride + idx];
+  out[geo.position_major(b, r, t) * W + c] = v;
+}
+
+// debug (tf32x3 mode): h = hi + lo, both fp32
+__global__ void hilo_f32_to_f32_kernel(const float* __restrict__ hi, const float* __restrict__ lo, float* __restrict__ out,
+                                       const RowGeom geo, int C) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<size_t>(geo.rows()) * C) return;
+  const int m = static_cast<int>(idx / C);
+  const int c = static_cast<int>(idx - static_cast<size_t>(m) * C);
+  int b, r, t;
+  if (!geo.decode(m, b, r, t)) return;
+  out[geo.position_major(b, r, t) * C + c] = hi[idx] + lo[idx];
 }
 
 inline void tc_bf16_to_f32(const __nv_bfloat16* in, float* out, size_t n, cudaStream_t st) {
