@@ -123,3 +123,87 @@ def run_rank(vocoder, mels, plan_for_rank, pad_mel_value=-11.0, hop=256, ragged=
         for j, i in enumerate(batch.indices):
             out[i] = y[j, :mels[i].shape[0] * hop].copy()
     return out
+
+
+def bind_rank_to_cpus(local_rank: int, local_world: int):
+    """Gives each rank of a box its own slice of the CPUs this process may run on (its staging memcpys and the
+    launch thread then never share a core with another rank's). Returns the CPU list, or None if unsupported."""
+    import os
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        return None
+    if local_world <= 1 or len(cpus) < 2 * local_world:
+        return cpus
+    per = len(cpus) // local_world
+    mine = cpus[local_rank * per:(local_rank + 1) * per]
+    try:
+        os.sched_setaffinity(0, mine)
+    except OSError:
+        return cpus
+    return mine
+
+
+def run_rank_pipelined(runtime, mels, plan_for_rank, pad_mel_value=-11.0, hop=256, ragged=True, sigma=1.0, z_seed=None,
+                       deterministic=False):
+    """One rank's share of a sharded sweep with the transfers off the critical path (inputs scattered /
+    waveforms gathered through pinned host buffers): while the kernels of batch i run, the mels of batch i+1 are
+    staged and copied host->device and the waveforms of batch i-1 travel device->host on a copy stream into a
+    two-deep ring of pinned buffers; the host only blocks on the copy it is about to consume. `runtime` is a
+    B200WaveGlowRuntime (device tensors in, device tensors out); noise is drawn on the device (z=None, the
+    reference's default call) unless `deterministic`. Returns ({utterance id: waveform [hop * T_i] numpy},
+    {"h2d_bytes": .., "d2h_bytes": ..})."""
+    import numpy as np
+    import torch
+    dev = torch.device("cuda", runtime.engine.device)
+    copy_stream = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    n_mel = runtime.engine.hp.n_mel_channels
+    cap_in = max((len(b.indices) * b.T * n_mel for b in plan_for_rank), default=0)
+    cap_out = max((len(b.indices) * b.T * hop for b in plan_for_rank), default=0)
+    pin_in = [torch.empty(cap_in, dtype=torch.float32).pin_memory() for _ in range(2)]
+    pin_out = [torch.empty(cap_out, dtype=torch.float32).pin_memory() for _ in range(2)]
+    in_free = [None, None]        # event: the H2D copy that read pin_in[i] has finished
+    if z_seed is not None:
+        runtime._seed, runtime._gen = int(z_seed), None
+    out, pending = {}, []         # pending: (batch, pinned view, event) whose D2H is in flight
+    h2d = d2h = 0
+
+    def drain(upto):
+        while len(pending) > upto:
+            batch, view, ev = pending.pop(0)
+            ev.synchronize()
+            for j, i in enumerate(batch.indices):
+                out[i] = view[j, :mels[i].shape[0] * hop].numpy().copy()
+
+    for k, batch in enumerate(plan_for_rank):
+        B, T = len(batch.indices), batch.T
+        slot = k % 2
+        if in_free[slot] is not None:
+            in_free[slot].synchronize()
+        x = pin_in[slot][:B * T * n_mel].view(B, T, n_mel)
+        xn = x.numpy()
+        for j, i in enumerate(batch.indices):
+            n = mels[i].shape[0]
+            xn[j, :n] = mels[i]
+            xn[j, n:] = pad_mel_value
+        x_d = x.to(dev, non_blocking=True)
+        in_free[slot] = torch.cuda.Event()
+        in_free[slot].record(main)
+        h2d += x.numel() * 4
+        lengths = [int(mels[i].shape[0]) for i in batch.indices] if ragged else None
+        y_d = runtime(x_d, sigma=sigma, deterministic=deterministic, lengths=lengths)
+        done = torch.cuda.Event()
+        done.record(main)
+        drain(1)                   # at most one older D2H in flight: its pinned slot is the one reused next
+        view = pin_out[slot][:B * T * hop].view(B, T * hop)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done)
+            view.copy_(y_d, non_blocking=True)
+            y_d.record_stream(copy_stream)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        pending.append((batch, view, ev))
+        d2h += B * T * hop * 4
+    drain(0)
+    return out, {"h2d_bytes": h2d, "d2h_bytes": d2h}
