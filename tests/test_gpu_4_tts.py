@@ -229,3 +229,27 @@ def test_b200_decoder_against_reference_source_fixture(lib_built, lstm):
         assert float(attn[i, :, len(m):].abs().max()) == 0.0 if len(m) < attn.shape[2] else True
     print(f"\nCUDA decoder [{lstm} LSTM path] vs reference-source fixture (float64), {frames} frames: max abs error {worst:.2e}")
     assert worst <= (1e-5 if lstm == "fp32" else 1e-4)
+
+
+def test_stream_one_sentence_at_a_time_with_savers(models, tmp_path):
+    """tts.stream (Tacotron2.stream, models/tts/tacotron2.py:354-367): pre-warm, then one sentence per call from a
+    queue; every audio equals the vocoder's stand-alone call on the produced mel; audios/*.wav + map.json appear."""
+    import json
+    import queue
+    from text_to_speech_b200.tts import stream, synthetic_texts
+    taco, voc = models[0], models[1]
+    texts = synthetic_texts(3, 5, 6, 20)
+    q = queue.Queue()
+    for i, t in enumerate(texts):
+        q.put((f"sentence {i}", t))
+    q.put(None)
+    res = list(stream(q, taco, voc, directory=str(tmp_path), max_length=24, early_stopping=False, deterministic=True,
+                      multiples=(64,), max_tokens=64, max_frames=64))
+    assert [r["text"] for r in res] == ["sentence 0", "sentence 1", "sentence 2"]
+    for r in res:
+        assert r["mel"].shape == (24, 80) and r["audio"].shape == (24 * 256,) and np.isfinite(r["audio"]).all()
+        alone = voc(torch.from_numpy(r["mel"][None]).cuda(), sigma=0.6, deterministic=True)[0].cpu().numpy()
+        assert np.array_equal(r["audio"], alone)
+        assert r["infos"]["audio"].endswith(".wav")
+    m = json.load(open(tmp_path / "map.json"))
+    assert list(m) == ["sentence 0", "sentence 1", "sentence 2"] and abs(m["sentence 1"]["time"] - 24 * 256 / 22050) < 1e-9

@@ -317,3 +317,29 @@ def test_run_rank_passes_true_lengths_when_ragged():
     assert sorted(x for _, l, _ in seen for x in l) == [2, 5, 9]
     for i, n in enumerate([5, 9, 2]):
         assert out[i].shape == (n * 256,) and (out[i] == float(i)).all()
+
+
+def test_audio_and_json_savers_write_the_reference_layout(tmp_path):
+    """AudioSaver / JSONSaver (utils/callbacks/file_saver.py:100-125, example_outputs/en/map.json): audios/audio-<n>.wav
+    and a map.json whose entries hold everything but the arrays, with the audio replaced by its file path."""
+    import json
+    from scipy.io import wavfile
+    from text_to_speech_b200.audio_io import AudioSaver, JSONSaver, normalize_audio
+    d = str(tmp_path / "out")
+    savers = [AudioSaver(d), JSONSaver(d)]
+    rng = np.random.default_rng(0)
+    for n, text in enumerate(["hello world", "second sentence"]):
+        audio = rng.standard_normal(2205).astype(np.float32) * 0.1
+        output = {"text": text, "mel": np.zeros((3, 80), np.float32), "audio": audio, "rate": 22050, "time": 0.1}
+        infos = {k: v for k, v in output.items() if k not in ("mel", "audio")}
+        for s in savers:
+            s.apply(infos, output)
+        rate, data = wavfile.read(infos["audio"])
+        assert rate == 22050 and np.array_equal(data, normalize_audio(audio))
+        assert infos["audio"].endswith(f"audios/audio-{n}.wav")
+    m = json.load(open(tmp_path / "out" / "map.json"))
+    assert list(m) == ["hello world", "second sentence"]
+    assert set(m["hello world"]) == {"text", "rate", "time", "audio"} and m["second sentence"]["audio"].endswith("audio-1.wav")
+    again = JSONSaver(d)                      # an existing map is extended, not overwritten
+    again.apply({"text": "third", "rate": 22050, "time": 0.2, "audio": "x.wav"})
+    assert list(json.load(open(tmp_path / "out" / "map.json"))) == ["hello world", "second sentence", "third"]

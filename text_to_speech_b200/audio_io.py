@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["normalize_audio", "write_audio"]
+__all__ = ["normalize_audio", "write_audio", "AudioSaver", "JSONSaver"]
 
 
 def normalize_audio(audio, max_val=32767, dtype=np.int16):
@@ -37,3 +37,55 @@ def write_audio(filename, audio, rate, normalize=True, factor=32767):
     from scipy.io.wavfile import write
     write(filename, rate, audio)
     return filename
+
+
+class AudioSaver:
+    """`utils/callbacks/file_saver.py:118-125` (+ `FileSaver.apply` :100-109): writes `output['audio']` to
+    `<directory>/audios/audio-<n>.wav` with `write_audio(filename, audio, rate=output['rate'])` and records the path in
+    `infos['audio']`. The reference's default container is `.mp3` (pydub / ffmpeg, absent here): `.wav` is the one written."""
+
+    def __init__(self, directory, key="audio", file_format="audio-{}.wav", subdir="audios"):
+        import os
+        self.key, self.directory = key, os.path.join(directory, subdir) if subdir else directory
+        self.file_format = file_format
+        os.makedirs(self.directory, exist_ok=True)
+        self._index = 0
+
+    def apply(self, infos, output, **_):
+        import os
+        if isinstance(output.get(self.key), str):
+            infos.setdefault(self.key, output[self.key])
+            return
+        if infos.get(self.key) is None:
+            infos[self.key] = os.path.join(self.directory, self.file_format.format(self._index))
+            self._index += 1
+        write_audio(infos[self.key], output[self.key], rate=output["rate"])
+
+    def join(self):
+        pass
+
+
+class JSONSaver:
+    """The `map.json` of a prediction directory (`example_outputs/en/map.json`): {key text: {'text', 'cleaned'?,
+    'splitted'?, 'rate', 'time', 'audio': path}} -- everything of an entry except the arrays ('mel', 'attention', raw
+    'audio'; `models/tts/tacotron2.py:226-230`). Rewritten after every entry so a stream can be followed on disk."""
+
+    def __init__(self, directory, filename="map.json"):
+        import json
+        import os
+        os.makedirs(directory, exist_ok=True)
+        self.path = os.path.join(directory, filename)
+        self.data = {}
+        if os.path.exists(self.path):
+            with open(self.path, encoding="utf-8") as f:
+                self.data = json.load(f)
+
+    def apply(self, infos, output=None, **_):
+        import json
+        entry = {k: v for k, v in infos.items() if not isinstance(v, np.ndarray) and k not in ("mel", "attention")}
+        self.data[infos["text"]] = entry
+        with open(self.path, "w", encoding="utf-8") as f:
+            json.dump(self.data, f, indent=4, default=float)
+
+    def join(self):
+        pass

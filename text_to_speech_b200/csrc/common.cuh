@@ -34,4 +34,20 @@ struct Fail {
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Entry points run on the engine's device and put the caller's current device back on exit (torch reads it with
+// cudaGetDevice: a process driving several engines must not find it changed behind its back).
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    WG_CK(cudaSetDevice(dev));   // always: this also binds the device's primary context to a thread that has none yet
+    if (prev == dev) prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 }  // namespace wg

@@ -278,7 +278,7 @@ void build_mel(wg_mel_engine* e, const wg_mel_config* cfg, const float* window, 
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
     fail(WG_ERR_CUDA, "wg_mel_create: no CUDA device (the B200 mel front-end has no CPU fallback)");
   if (device < 0 || device >= n_dev) fail(WG_ERR_INVALID, "wg_mel_create: device %d of %d", device, n_dev);
-  CK(cudaSetDevice(device));
+  wg::DeviceGuard dev_guard(device);
   CK(cudaDeviceGetAttribute(&e->n_sm, cudaDevAttrMultiProcessorCount, device));
 
   // mel basis, one column (channel) at a time: the bins with a non-zero weight, stored channel-minor
@@ -349,7 +349,7 @@ void launch_mel(wg_mel_engine* e, const float* audio, int B, long long n, float*
   if (B < 1) fail(WG_ERR_INVALID, "wg_mel_spectrogram: B %d < 1", B);
   long long F = mel_frames(e, n);
   if (F > 0x7fffff00LL) fail(WG_ERR_INVALID, "wg_mel_spectrogram: %lld frames per row", F);
-  CK(cudaSetDevice(e->device));
+  wg::DeviceGuard dev_guard(e->device);
   MelArgs a{};
   a.audio = audio; a.mel = mel; a.N = n; a.Neff = mel_neff(e, n);
   a.B = B; a.F = static_cast<int>(F); a.hop = e->cfg.hop_length; a.n_mel = e->cfg.n_mel_channels; a.ell_w = e->ell_w;
@@ -422,7 +422,7 @@ int wg_mel_spectrogram_host(wg_mel_handle h, const float* audio, int32_t B, int6
     if (!audio || !mel) fail(WG_ERR_INVALID, "wg_mel_spectrogram_host: NULL buffer");
     if (B < 1) fail(WG_ERR_INVALID, "wg_mel_spectrogram_host: B %d < 1", B);
     long long F = mel_frames(h, n_samples);
-    CK(cudaSetDevice(h->device));
+    wg::DeviceGuard dev_guard(h->device);
     size_t in_bytes = static_cast<size_t>(B) * n_samples * sizeof(float);
     size_t out_bytes = static_cast<size_t>(B) * F * h->cfg.n_mel_channels * sizeof(float);
     ensure_stage(h->pin_in, h->dev_in, h->cap_in, in_bytes);

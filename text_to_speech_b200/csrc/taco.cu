@@ -634,6 +634,8 @@ struct wg_taco_engine {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   std::map<std::tuple<int, int, int>, cudaGraphExec_t> graphs;   // (B, S, chunk)
+  std::map<std::tuple<int, int, int>, unsigned long long> graph_used;   // last use (LRU: at most TACO_MAX_GRAPHS are kept)
+  unsigned long long graph_clock = 0;
   std::string err;
 };
 
@@ -642,9 +644,12 @@ namespace {
 std::mutex g_taco_err_mu;
 std::string g_taco_create_err;
 
+constexpr size_t TACO_MAX_GRAPHS = 16;   // every new (B, S, chunk) captures a graph: a long-running process must not grow for ever
+
 void drop_graphs(wg_taco_engine* e) {
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
   e->graphs.clear();
+  e->graph_used.clear();
 }
 
 void destroy_taco(wg_taco_engine* e) {
@@ -807,7 +812,7 @@ void build_taco(wg_taco_engine* e, const wg_taco_config* cfg, const wg_tensor* t
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
     fail(WG_ERR_CUDA, "wg_taco_create: no CUDA device (the B200 Tacotron2 decoder has no CPU fallback)");
   if (device < 0 || device >= n_dev) fail(WG_ERR_INVALID, "wg_taco_create: device %d of %d", device, n_dev);
-  CK(cudaSetDevice(device));
+  wg::DeviceGuard dev_guard(device);
   Dims& d = e->d;
   d.NM = c.n_mel_channels; d.E = c.embedding_dim; d.A = c.attention_rnn_dim; d.D = c.decoder_rnn_dim;
   d.KS = c.attention_kernel_size; d.S = 0;
@@ -1001,7 +1006,7 @@ void decode(wg_taco_engine* e, const float* memory, const int32_t* text_lengths,
   for (int b = 0; b < B; ++b)
     if (text_lengths[b] < 1 || text_lengths[b] > S)
       fail(WG_ERR_INVALID, "wg_taco_decode: text_lengths[%d] = %d outside [1, %d]", b, text_lengths[b], S);
-  CK(cudaSetDevice(e->device));
+  wg::DeviceGuard dev_guard(e->device);
   Dims d = e->d;
   d.S = S;
   CK(cudaFuncSetAttribute(energy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(energy_smem(d))));
@@ -1065,8 +1070,20 @@ void decode(wg_taco_engine* e, const float* memory, const int32_t* text_lengths,
       cudaError_t rc = cudaGraphInstantiate(&exec, graph, 0);
       cudaGraphDestroy(graph);
       if (rc != cudaSuccess) fail(WG_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(rc));
+      if (e->graphs.size() >= TACO_MAX_GRAPHS) {      // evict the least recently used graph
+        auto lru = e->graph_used.begin();
+        for (auto u = e->graph_used.begin(); u != e->graph_used.end(); ++u)
+          if (u->second < lru->second) lru = u;
+        auto victim = e->graphs.find(lru->first);
+        if (victim != e->graphs.end()) {
+          cudaGraphExecDestroy(victim->second);
+          e->graphs.erase(victim);
+        }
+        e->graph_used.erase(lru);
+      }
       it = e->graphs.emplace(key, exec).first;
     }
+    e->graph_used[key] = ++e->graph_clock;
     while (done < max_length) {
       CK(cudaGraphLaunch(it->second, st));
       done += chunk;

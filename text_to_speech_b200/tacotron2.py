@@ -162,6 +162,7 @@ class Tacotron2:
         self.out_b = torch.cat([t("decoder/linear_projection/bias"), t("decoder/gate_output/bias")])
         self.post_convs = [self._conv_bn(t, f"postnet/conv_{i}", f"postnet/bn_{i}") for i in range(hp.postnet_n_conv)]
         self._graphs = {}
+        self.max_graphs = 8
         self._decoder_weights = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in weights.items()
                                  if k.startswith("decoder/")}
         self._b200 = None
@@ -347,7 +348,12 @@ class Tacotron2:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 run_chunk()
-            g = self._graphs[key] = (graph, st, buf)
+            while len(self._graphs) >= self.max_graphs:          # LRU: each entry pins static state / memory buffers
+                self._graphs.pop(next(iter(self._graphs)))
+            g = (graph, st, buf)
+        else:
+            self._graphs.pop(key)
+        self._graphs[key] = g                                     # most recently used last
         graph, st, buf = g
         for k, v in s.items():
             st[k].copy_(v)

@@ -83,3 +83,77 @@ def tts(token_seqs: Sequence[np.ndarray], tacotron, vocoder, *, max_length=10.0,
         timings.update(synthesizer_s=t1 - t0, vocoder_s=t2 - t1, utterances=len(mine),
                        samples=int(sum(len(r["audio"]) for r in results.values())))
     return results
+
+
+def precompile_for_stream(tacotron, vocoder, *, multiples=(64, 128), max_frames=None, max_tokens=128, max_length=10.0,
+                          decoder="b200", graph_chunk=32, **_):
+    """`Tacotron2.precompile_for_stream` (models/tts/tacotron2.py:354-356) warms the reference's compiled graphs with
+    one dummy sentence per padding multiple (64, 128). The B200 analogue pre-pays everything a first call would:
+    the vocoder's scratch, pinned staging and CUDA graphs for B = 1 at every multiple of `multiples` up to
+    `max_frames` (B200WaveGlowRuntime.precompile), and the synthesizer's decoder graphs for token counts at those
+    multiples up to `max_tokens`."""
+    shapes = vocoder.precompile(multiples=multiples, max_frames=max_frames)
+    tok_lens = sorted({m for mult in multiples for m in range(int(mult), int(max_tokens) + 1, int(mult))})
+    for S in tok_lens:
+        toks = np.ones((1, S), dtype=np.int64)
+        tacotron.infer(toks, max_length=2 * graph_chunk, early_stopping=False, deterministic=True, use_graph=True,
+                       decoder=decoder, graph_chunk=graph_chunk, return_attention=False)
+    return {"vocoder_shapes": shapes, "token_lengths": tok_lens}
+
+
+def stream(items, tacotron, vocoder, *, callbacks=None, directory=None, precompile=True, max_length=10.0, sigma=0.6,
+           silence_time=0.15, decoder="b200", padding_multiple=64, pad_token=0, early_stopping=True,
+           deterministic=False, seed=0, **kwargs):
+    """`Tacotron2.stream` (models/tts/tacotron2.py:364-367 -> BaseModel.predict, base_model.py:676-713): pre-warm, then
+    take sentences one at a time from `items` -- an iterable (list, generator, `queue.Queue` drained until `None`) of
+    token arrays or `(text, tokens)` pairs -- synthesise, vocode and hand every result to the callbacks
+    (`AudioSaver` + `JSONSaver` when `directory` is given: audios/audio-<n>.wav and map.json). One sentence per call,
+    batch 1, like the reference's loop (:154-191). Tokens are padded to `padding_multiple` (the synthesizer masks the
+    padding), so the pre-captured decoder graphs are hit; the vocoder gets the true frame count, so the audio is the
+    stand-alone result. Yields the result dicts ({'text', 'mel', 'audio', 'rate', 'time', 'infos'})."""
+    import queue as _queue
+    from .audio_io import AudioSaver, JSONSaver
+    callbacks = list(callbacks or [])
+    if directory is not None:
+        callbacks += [AudioSaver(directory), JSONSaver(directory)]
+    if precompile:
+        precompile_for_stream(tacotron, vocoder, max_length=max_length, decoder=decoder, **kwargs)
+
+    def source():
+        if isinstance(items, _queue.Queue):
+            while True:
+                it = items.get()
+                if it is None:
+                    return
+                yield it
+        else:
+            yield from items
+
+    for n, item in enumerate(source()):
+        text, tokens = item if isinstance(item, tuple) else (str(n), item)
+        tokens = np.asarray(tokens, dtype=np.int64)
+        S = len(tokens)
+        Sp = -(-S // padding_multiple) * padding_multiple if padding_multiple else S
+        toks = np.full((1, Sp), pad_token, dtype=np.int64)
+        toks[0, :S] = tokens
+        t0 = time.perf_counter()
+        ml = int(S * max_length) if isinstance(max_length, float) else int(max_length)
+        out = tacotron.infer(toks, max_length=ml, early_stopping=early_stopping, deterministic=deterministic,
+                             use_graph=True, decoder=decoder, seed=seed + n, return_attention=False)
+        frames = int(out.lengths[0])
+        if frames == 0:                                            # tacotron2.py:205-210
+            audio = np.zeros(int(silence_time * SAMPLE_RATE), np.float32)
+            mel = np.zeros((0, 80), np.float32)
+        else:
+            mel_d = out.mel[:1, :frames]                           # tacotron2.py:183
+            audio = np.array(vocoder(mel_d, sigma=sigma, deterministic=deterministic)[0, :frames * HOP].cpu().numpy())
+            mel = mel_d[0].cpu().numpy()
+        result = {"text": text, "mel": mel, "audio": audio, "rate": SAMPLE_RATE, "time": len(audio) / SAMPLE_RATE,
+                  "generation_time": time.perf_counter() - t0}
+        infos = {k: v for k, v in result.items() if k not in ("mel", "audio")}
+        for cb in callbacks:
+            cb.apply(infos, result)
+        result["infos"] = infos                                    # the map.json entry ('audio' = file path once saved)
+        yield result
+    for cb in callbacks:
+        cb.join()
