@@ -1,5 +1,7 @@
 """CPU: NVIDIA-WaveGlow state_dict import. The converted weights must reproduce, through the
 oracle, what NVIDIA's channels-first formulation computes from the torch-layout tensors."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -85,3 +87,53 @@ def test_layout_rule_is_the_reference_transpose_weights():
                 full = ref.transpose_weights(np.asarray(sd[f"WN.{k}.cond_layer.weight"]))
                 for i in range(hp.n_layers):
                     assert np.array_equal(full[..., i * C2:(i + 1) * C2], got[f"block-{k}/cond_layer-{i}/kernel"])
+
+
+def test_h5_reader_on_a_file_written_by_the_real_hdf5_library():
+    """The only genuine HDF5 file on this machine: scipy's MATLAB v7.3 test file (512-byte user block, written by the
+    HDF5 library itself). scipy's own test expects `testdouble` = linspace(0, 2 pi, 9)."""
+    import glob
+    import scipy.io
+    from text_to_speech_b200.h5lite import read_h5_datasets
+    hits = glob.glob(os.path.join(os.path.dirname(scipy.io.__file__), "matlab", "tests", "data", "testhdf5*.mat"))
+    if not hits:
+        pytest.skip("scipy's HDF5 test file is not installed")
+    d = read_h5_datasets(hits[0])
+    assert list(d) == ["testdouble"] and d["testdouble"].dtype == np.float64
+    assert np.allclose(d["testdouble"].ravel(), np.linspace(0, 2 * np.pi, 9))
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_keras_weights_h5_import_round_trip(tmp_path, fused):
+    """`.weights.h5` import (checkpoint_manager.py:169-216): a file laid out as Keras 3 lays out the reference's
+    WaveGlow (attribute-named groups, list elements conv1d / conv1d_1 / ... stored ALPHABETICALLY by the HDF5 library,
+    > 8 links per group = several symbol-table nodes) is read back to exactly the weight set and hparams."""
+    from oracle.h5_writer import write_h5, keras3_waveglow_layout
+    from text_to_speech_b200.convert import from_keras_weights_h5
+    from text_to_speech_b200.h5lite import H5File, H5FormatError
+    hp = WaveGlowHParams(n_flows=12, n_layers=11, n_channels=16)          # 11 layers: conv1d_10 sorts before conv1d_2
+    w = generate_weights(hp, 3, bias_std=0.1)
+    path = str(tmp_path / "waveglow.weights.h5")
+    write_h5(path, keras3_waveglow_layout(hp, w, fused=fused))
+    with H5File(path) as f:
+        names = [p for p, _, g in f.walk() if not g]
+    n_vars = len([k for k in w if not k.startswith("__")])
+    assert len(names) == (n_vars if not fused else n_vars - 2 * hp.n_flows * (hp.n_layers - 1))
+    assert names.index("blocks/waveglow_block/in_layers/conv1d_10/vars/0") < names.index("blocks/waveglow_block/in_layers/conv1d_2/vars/0")
+    hp2, w2 = from_keras_weights_h5(path)
+    assert hp2 == hp
+    assert sorted(w2) == sorted(k for k in w if not k.startswith("__"))
+    for k in w2:
+        assert np.array_equal(w2[k], w[k]), k
+    # layer-named groups (block-3/in_conv-5/vars/0) are accepted as well
+    alt = {}
+    for k, v in w.items():
+        if not k.startswith("__"):
+            alt[k.rsplit("/", 1)[0] + "/vars/" + ("0" if k.endswith("kernel") else "1")] = v
+    write_h5(path, alt)
+    hp3, w3 = from_keras_weights_h5(path)
+    assert hp3 == hp and all(np.array_equal(w3[k], w[k]) for k in w3)
+    with open(path, "wb") as f:
+        f.write(b"not an hdf5 file at all")
+    with pytest.raises(H5FormatError):
+        from_keras_weights_h5(path)

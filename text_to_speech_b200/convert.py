@@ -100,3 +100,97 @@ def to_nvidia_state_dict(hp: WaveGlowHParams, weights, *, fused_cond=False):
             sd[q + "cond_layer.weight"] = np.concatenate(cw, axis=0)
             sd[q + "cond_layer.bias"] = np.concatenate(cb, axis=0)
     return {k: np.asarray(v, dtype=np.float32) for k, v in sd.items()}
+
+
+# ---- Keras 3 `.weights.h5` (models restored by `CheckpointManager.load`, custom_train_objects/checkpoint_manager.py:169-216)
+_SUFFIX = re.compile(r"^(.*?)(?:_(\d+))?$")
+
+
+def _list_index(name):
+    """Keras names the saveables of a list attribute by class: 'conv1d', 'conv1d_1', 'conv1d_2', ... (the HDF5 library
+    then stores the links alphabetically, so 'conv1d_10' sorts before 'conv1d_2'): the numeric suffix is the position."""
+    m = _SUFFIX.match(name)
+    return int(m.group(2)) if m.group(2) is not None else 0
+
+
+def from_keras_weights_h5(path, *, n_early_every=4, n_early_size=2):
+    """Reads the variables of the reference's `architectures.WaveGlow` from a Keras 3 `.weights.h5` file.
+
+    Keras 3 (`keras/src/saving/saving_lib.py`) walks the model by ATTRIBUTE name and stores each layer's variables as
+    `<path>/vars/<i>` in creation order (kernel 0, bias 1); list attributes get one sub-group per element named after
+    the element's class in snake case with a running suffix. For the reference's model (waveglow_arch.py:164-223) that
+    gives
+        upsample/vars/{0,1}
+        blocks/waveglow_block[_k]/{start,end}/vars/{0,1}
+        blocks/waveglow_block[_k]/{in_layers,cond_layers,res_skip_layers}/conv1d[_i]/vars/{0,1}   (fused: cond_layer/vars)
+        convinv/invertible1x1_conv[_k]/conv/vars/0
+    A file whose groups carry the LAYER names instead (`block-3/in_conv-5/vars/0`, as older savers wrote) is accepted
+    too. No Keras is installable here, so this layout is taken from the library's published saving algorithm and is
+    NOT verified against a file written by Keras itself; the HDF5 container parsing is (text_to_speech_b200/h5lite.py).
+    Returns (WaveGlowHParams, {keras variable name: float32 array}) like `from_nvidia_state_dict`."""
+    from .h5lite import read_h5_datasets
+    ds = {k.strip("/"): v for k, v in read_h5_datasets(path).items()}
+    tree = {}
+    for k, v in ds.items():
+        parts = k.split("/")
+        if len(parts) < 3 or parts[-2] != "vars":
+            continue
+        tree.setdefault(tuple(parts[:-2]), {})[int(parts[-1])] = np.asarray(v, dtype=np.float32)
+    if not tree:
+        raise ValueError(f"{path}: no '<layer>/vars/<i>' datasets found (not a Keras weights file?)")
+
+    w = {}
+    by_layer_name = any(p and re.fullmatch(r"block-\d+", p[0]) for p in tree)
+    if by_layer_name:
+        for p, vs in tree.items():
+            base = "/".join(p)
+            w[base + "/kernel"] = vs[0]
+            if 1 in vs:
+                w[base + "/bias"] = vs[1]
+    else:
+        def children(prefix):
+            names = sorted({p[len(prefix)] for p in tree if len(p) > len(prefix) and p[:len(prefix)] == prefix}, key=_list_index)
+            return names
+
+        def put(dst, path_):
+            if path_ not in tree:
+                raise ValueError(f"{path}: group '{'/'.join(path_)}/vars' is missing")
+            w[dst + "/kernel"] = tree[path_][0]
+            if 1 in tree[path_]:
+                w[dst + "/bias"] = tree[path_][1]
+
+        put("upsample", ("upsample",))
+        blocks, convs = children(("blocks",)), children(("convinv",))
+        if not blocks or len(blocks) != len(convs):
+            raise ValueError(f"{path}: found {len(blocks)} 'blocks' and {len(convs)} 'convinv' groups")
+        for k, (bn, cn) in enumerate(zip(blocks, convs)):
+            put(f"invertible_conv-{k}/conv", ("convinv", cn, "conv"))
+            put(f"block-{k}/start_conv", ("blocks", bn, "start"))
+            put(f"block-{k}/end_conv", ("blocks", bn, "end"))
+            ins = children(("blocks", bn, "in_layers"))
+            for i, name in enumerate(ins):
+                put(f"block-{k}/in_conv-{i}", ("blocks", bn, "in_layers", name))
+            for i, name in enumerate(children(("blocks", bn, "res_skip_layers"))):
+                put(f"block-{k}/res_skip_conv-{i}", ("blocks", bn, "res_skip_layers", name))
+            conds = children(("blocks", bn, "cond_layers"))
+            if conds:
+                for i, name in enumerate(conds):
+                    put(f"block-{k}/cond_layer-{i}", ("blocks", bn, "cond_layers", name))
+            else:                                               # fused=True: one 640 -> 2C*n_layers conv, sliced per layer
+                put(f"block-{k}/__fused", ("blocks", bn, "cond_layer"))
+                fk, fb = w.pop(f"block-{k}/__fused/kernel"), w.pop(f"block-{k}/__fused/bias")
+                n_layers, C2 = len(ins), fk.shape[2] // len(ins)
+                for i in range(n_layers):
+                    w[f"block-{k}/cond_layer-{i}/kernel"] = np.ascontiguousarray(fk[:, :, i * C2:(i + 1) * C2])
+                    w[f"block-{k}/cond_layer-{i}/bias"] = np.ascontiguousarray(fb[i * C2:(i + 1) * C2])
+    n_flows = 1 + max(int(m.group(1)) for k in w for m in [re.match(r"block-(\d+)/", k)] if m)
+    n_layers = 1 + max(int(m.group(1)) for k in w for m in [re.match(r"block-0/in_conv-(\d+)/", k)] if m)
+    up = w["upsample/kernel"]
+    hp = WaveGlowHParams(n_mel_channels=int(up.shape[1]), n_flows=n_flows,
+                         n_group=int(w["invertible_conv-0/conv/kernel"].shape[1]), n_early_every=n_early_every,
+                         n_early_size=n_early_size, n_layers=n_layers,
+                         n_channels=int(w["block-0/start_conv/kernel"].shape[2]),
+                         kernel_size=int(w["block-0/in_conv-0/kernel"].shape[0]))
+    w = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in w.items()}
+    check_weights(hp, w)
+    return hp, w

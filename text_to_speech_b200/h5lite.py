@@ -217,6 +217,26 @@ class H5File:
         n = int(np.prod(shape, dtype=np.int64)) if shape else 1
         p = layout
         ver = self.buf[p]
+        if ver in (1, 2):                                  # old libraries: dimensionality, class, address, 4-byte dims
+            rank1, cls = self.buf[p + 1], self.buf[p + 2]
+            q = p + 8
+            if cls == 0:
+                q += 4 * rank1
+                size = self._u(q, 4)
+                raw = self.buf[q + 4:q + 4 + size]
+                return np.frombuffer(raw, dtype=dtype, count=n).reshape(shape).astype(dtype.newbyteorder("="))
+            a = self._u(q, self.so)
+            if cls == 1:
+                if a == (1 << (8 * self.so)) - 1:
+                    return np.zeros(shape, dtype.newbyteorder("="))
+                a += self.base
+                return np.frombuffer(self.buf[a:a + n * dtype.itemsize], dtype=dtype, count=n).reshape(shape).astype(dtype.newbyteorder("="))
+            if cls == 2:
+                cdims = tuple(self._u(q + self.so + 4 * i, 4) for i in range(rank1 - 1))
+                out = np.zeros(shape, dtype)
+                self._read_chunks(a + self.base, rank1, cdims, out)
+                return out.astype(dtype.newbyteorder("="))
+            raise H5FormatError(f"unsupported data layout class {cls}")
         if ver != 3:
             raise H5FormatError(f"unsupported data layout message version {ver}")
         cls = self.buf[p + 1]

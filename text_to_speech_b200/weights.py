@@ -145,7 +145,12 @@ def save_weights(path, hp: WaveGlowHParams, weights):
 
 
 def load_weights(path):
-    """Returns (hparams, {name: float32 array}). Validates names and shapes against the topology."""
+    """Returns (hparams, {name: float32 array}). Validates names and shapes against the topology.
+    `.npz`: this package's own container; `.h5` / `.weights.h5`: a Keras 3 weights file of the reference's model
+    (what `CheckpointManager.load` restores, custom_train_objects/checkpoint_manager.py:169-216)."""
+    if str(path).endswith(".h5"):
+        from .convert import from_keras_weights_h5
+        return from_keras_weights_h5(path)
     with np.load(path) as f:
         if "__hparams__" not in f.files:
             raise ValueError(f"{path}: not a WaveGlow weight file (no __hparams__ entry)")
