@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "simt_kernels.cuh"
 #include "tc_kernels.cuh"
+#include "tc_pair_kernels.cuh"
 #include "tc_c512_kernels.cuh"
 #include "tc_tf32_kernels.cuh"
 
@@ -27,6 +28,9 @@ namespace {
 
 using namespace wg;
 
+#ifndef WG_PAIR_DEFAULT
+#define WG_PAIR_DEFAULT 0        // measured default of the CTA-pair layer kernel
+#endif
 constexpr int HOP = 256;         // upsample stride (waveglow_arch.py:197)
 constexpr int UPSAMPLE_K = 1024; // upsample kernel size
 
@@ -97,6 +101,7 @@ struct wg_engine {
   // per-kernel profiling (wg_profile_enable / wg_profile_read)
   unsigned long long* timing = nullptr;   // WG_LAYER_TIMING=1: in-kernel cycle counters (debug)
   int dbg_flags = 0;                      // WG_DEBUG_FLAGS, honoured only by a -DWG_PROBES build (WnLayerParams::flags)
+  int pair_policy = -1;                   // WG_PAIR: 1 = CTA-pair (cta_group::2) layer kernel, 0 = single-CTA kernel, -1 = default
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;   // pairs: [2i] start, [2i+1] stop
   std::vector<int> ev_count;          // per pair: layer launches bracketed by it
@@ -195,6 +200,13 @@ bool use_pm(const wg_engine* e, int B, int T) {
   const long tiles_pos = (long)B * (((long)T * e->R + 127) / 128);
   const long cost_pm = ((tiles_pm + sm - 1) / sm) * 40, cost_pos = ((tiles_pos + sm - 1) / sm) * 50 + 2;
   return cost_pm <= cost_pos;
+}
+
+// CTA-pair layer kernel (phase-major, C = 256): needs at least one full wave of pair tiles to pay off; WG_PAIR=0/1 forces.
+bool use_pair(const wg_engine* e, const TcPlan& pl) {
+  if (e->pair_policy == 0 || e->timing) return false;
+  if (e->pair_policy == 1) return true;
+  return WG_PAIR_DEFAULT && ((pl.tiles_per_row + 1) / 2) * pl.R >= e->sm_count / 2;
 }
 
 Ws carve(const wg_engine* e, int B, int T, const Ragged* rg = nullptr) {
@@ -354,6 +366,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
   const float* zz = deterministic ? nullptr : z;
 
   TcPlan plan;
+  TcPairMaps pmaps;
   Tf32Plan plan3;
   // ---- (1) upsample + trim + regroup: spect[B*L, S]  (waveglow_arch.py:245-253) ---------------
   if (tf32) {
@@ -377,6 +390,8 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
                e->Wup16, R * S, e->W1, e->W2, aup16, spect16, h16[0], h16[1], hlo, pm, R, e->V,
                fold0 ? a0 : nullptr, e->W0, e->H0, c.n_flows, pm ? pm_gap(e) : 0, rg ? &geo : nullptr);
     if (const char* to = std::getenv("WG_TILE_ORDER")) plan.tile_order = to[0] != '0';
+    if (pm && C == 256 && use_pair(e, plan))
+      tc_pair_prepare(pmaps, plan, c.n_flows * c.n_layers, c.n_flows, R, e->W1, e->W2, e->V, e->W0, e->H0);
     if (C == 512) make_map_4d(&m_acts512, acts16, 1, pm ? (uint64_t)R : (uint64_t)B, plan.Trows, C, WL_BM);
     e->launches += tc_upsample(plan, mel, e->bup, st);
   }
@@ -483,6 +498,9 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
         if (C == 512)
           e->launches += tc512_wn_layer(plan, m_acts512, k * c.n_layers + i, d, last, hcur, acc8, pm ? lw.b1_pm : lw.b1,
                                         lw.b2, lw.wse_p.data(), st, fold0 && i == 0);
+        else if (pmaps.ready)
+          e->launches += tc_wn_layer_pair(plan, pmaps, k * c.n_layers + i, d, last, hcur, acc8, lw.b1_pm, lw.b2,
+                                          lw.wse_p.data(), st, fold0 && i == 0);
         else
           e->launches += tc_wn_layer(plan, k * c.n_layers + i, d, last, hcur, acc8, pm ? lw.b1_pm : lw.b1, lw.b2,
                                      lw.wse_p.data(), e->timing, e->dbg_flags, st, fold0 && i == 0);
@@ -927,6 +945,8 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
       if (const char* pmv = std::getenv("WG_PM")) e->pm_policy = std::atoi(pmv);
     }
     tc512_init();
+    tc_pair_init();
+    if (const char* pr = std::getenv("WG_PAIR")) e->pair_policy = std::atoi(pr);
 #ifdef WG_PROBES
     // A/B probes that deliberately BREAK the result to isolate a cost (profiles/r01_probes.md): compiled only into a
     // -DWG_PROBES build, and even there honoured only when the caller also sets WG_ALLOW_PROBES=1.

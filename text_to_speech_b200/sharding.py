@@ -152,33 +152,45 @@ def run_rank_pipelined(runtime, mels, plan_for_rank, pad_mel_value=-11.0, hop=25
     two-deep ring of pinned buffers; the host only blocks on the copy it is about to consume. `runtime` is a
     B200WaveGlowRuntime (device tensors in, device tensors out); noise is drawn on the device (z=None, the
     reference's default call) unless `deterministic`. Returns ({utterance id: waveform [hop * T_i] numpy},
-    {"h2d_bytes": .., "d2h_bytes": ..})."""
+    stats: h2d / d2h bytes and where the host spent its time)."""
+    import time
     import numpy as np
     import torch
     dev = torch.device("cuda", runtime.engine.device)
-    copy_stream = torch.cuda.Stream(device=dev)
     main = torch.cuda.current_stream(dev)
     n_mel = runtime.engine.hp.n_mel_channels
     cap_in = max((len(b.indices) * b.T * n_mel for b in plan_for_rank), default=0)
     cap_out = max((len(b.indices) * b.T * hop for b in plan_for_rank), default=0)
-    pin_in = [torch.empty(cap_in, dtype=torch.float32).pin_memory() for _ in range(2)]
-    pin_out = [torch.empty(cap_out, dtype=torch.float32).pin_memory() for _ in range(2)]
+    st = getattr(runtime, "_sweep_state", None)          # pinned rings and the copy stream live with the runtime
+    if st is None or st["cap_in"] < cap_in or st["cap_out"] < cap_out:
+        st = {"cap_in": cap_in, "cap_out": cap_out, "copy_stream": torch.cuda.Stream(device=dev),
+              "pin_in": [torch.empty(cap_in, dtype=torch.float32, pin_memory=True) for _ in range(2)],
+              "pin_out": [torch.empty(cap_out, dtype=torch.float32, pin_memory=True) for _ in range(2)]}
+        runtime._sweep_state = st
+    copy_stream, pin_in, pin_out = st["copy_stream"], st["pin_in"], st["pin_out"]
     in_free = [None, None]        # event: the H2D copy that read pin_in[i] has finished
     if z_seed is not None:
         runtime._seed, runtime._gen = int(z_seed), None
     out, pending = {}, []         # pending: (batch, pinned view, event) whose D2H is in flight
-    h2d = d2h = 0
+    stats = {"h2d_bytes": 0, "d2h_bytes": 0, "host_stage_s": 0.0, "host_wait_d2h_s": 0.0, "host_copy_out_s": 0.0,
+             "host_launch_s": 0.0}
 
     def drain(upto):
         while len(pending) > upto:
             batch, view, ev = pending.pop(0)
+            t0 = time.perf_counter()
             ev.synchronize()
+            t1 = time.perf_counter()
+            vn = view.numpy()
             for j, i in enumerate(batch.indices):
-                out[i] = view[j, :mels[i].shape[0] * hop].numpy().copy()
+                out[i] = vn[j, :mels[i].shape[0] * hop].copy()
+            stats["host_wait_d2h_s"] += t1 - t0
+            stats["host_copy_out_s"] += time.perf_counter() - t1
 
     for k, batch in enumerate(plan_for_rank):
         B, T = len(batch.indices), batch.T
         slot = k % 2
+        t0 = time.perf_counter()
         if in_free[slot] is not None:
             in_free[slot].synchronize()
         x = pin_in[slot][:B * T * n_mel].view(B, T, n_mel)
@@ -190,11 +202,15 @@ def run_rank_pipelined(runtime, mels, plan_for_rank, pad_mel_value=-11.0, hop=25
         x_d = x.to(dev, non_blocking=True)
         in_free[slot] = torch.cuda.Event()
         in_free[slot].record(main)
-        h2d += x.numel() * 4
+        stats["h2d_bytes"] += x.numel() * 4
+        t1 = time.perf_counter()
         lengths = [int(mels[i].shape[0]) for i in batch.indices] if ragged else None
         y_d = runtime(x_d, sigma=sigma, deterministic=deterministic, lengths=lengths)
         done = torch.cuda.Event()
         done.record(main)
+        t2 = time.perf_counter()
+        stats["host_stage_s"] += t1 - t0
+        stats["host_launch_s"] += t2 - t1
         drain(1)                   # at most one older D2H in flight: its pinned slot is the one reused next
         view = pin_out[slot][:B * T * hop].view(B, T * hop)
         with torch.cuda.stream(copy_stream):
@@ -204,6 +220,6 @@ def run_rank_pipelined(runtime, mels, plan_for_rank, pad_mel_value=-11.0, hop=25
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         pending.append((batch, view, ev))
-        d2h += B * T * hop * 4
+        stats["d2h_bytes"] += B * T * hop * 4
     drain(0)
-    return out, {"h2d_bytes": h2d, "d2h_bytes": d2h}
+    return out, stats
