@@ -204,7 +204,7 @@ bool use_pm(const wg_engine* e, int B, int T) {
 
 // CTA-pair layer kernel (phase-major, C = 256): needs at least one full wave of pair tiles to pay off; WG_PAIR=0/1 forces.
 bool use_pair(const wg_engine* e, const TcPlan& pl) {
-  if (e->pair_policy == 0 || e->timing) return false;
+  if (e->pair_policy == 0) return false;
   if (e->pair_policy == 1) return true;
   return WG_PAIR_DEFAULT && ((pl.tiles_per_row + 1) / 2) * pl.R >= e->sm_count / 2;
 }
@@ -500,7 +500,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
                                         lw.b2, lw.wse_p.data(), st, fold0 && i == 0);
         else if (pmaps.ready)
           e->launches += tc_wn_layer_pair(plan, pmaps, k * c.n_layers + i, d, last, hcur, acc8, lw.b1_pm, lw.b2,
-                                          lw.wse_p.data(), st, fold0 && i == 0);
+                                          lw.wse_p.data(), st, fold0 && i == 0, e->timing);
         else
           e->launches += tc_wn_layer(plan, k * c.n_layers + i, d, last, hcur, acc8, pm ? lw.b1_pm : lw.b1, lw.b2,
                                      lw.wse_p.data(), e->timing, e->dbg_flags, st, fold0 && i == 0);

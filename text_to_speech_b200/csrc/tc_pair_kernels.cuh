@@ -193,6 +193,7 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
   cluster_sync_all();   // both CTAs' barriers / TMEM / constant tiles exist before anyone signals across
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const bool timing = p.timing != nullptr;   // WG_LAYER_TIMING=1: in-kernel cycle counters (same slots as the single-CTA kernel)
   constexpr int KB_CONV = FIRST ? 1 : WL_KB_CONV;
   const int kb1 = KB_CONV + p.n_cond_kb;
 
@@ -200,9 +201,13 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
     // ===================================== TMA producer (both CTAs) ============================
     uint32_t it = 0;
     // `pair_bytes`: what BOTH CTAs load into this stage (the leader's barrier counts them all)
+    long long t_wait = 0;
     auto acquire = [&](uint32_t pair_bytes) -> uint32_t {
       const int s = it % STAGES;
+      long long tq = 0;
+      if (timing) tq = clock64();
       mbar_wait(empty_bar(s), ((it / STAGES) & 1) ^ 1);
+      if (timing) t_wait += clock64() - tq;
       if (leader && elect_one()) mbar_expect_tx(full_bar(s), pair_bytes);
       __syncwarp();
       return static_cast<uint32_t>(s);
@@ -272,6 +277,7 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
         }
       }
     }
+    if (timing && leader && lane == 0) atomicAdd(p.timing + 8, static_cast<unsigned long long>(t_wait));
   } else if (warp == 1) {
     // ====================================== MMA issuer (leader CTA only) =======================
     if (leader) {
@@ -279,14 +285,22 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
       constexpr uint32_t idesc_id = umma_idesc_bf16(256, 64);
       const uint64_t idesc64 = umma_desc_sw128(smem_base + G::OFF_I64);
       uint32_t it = 0, n = 0;
+      long long t_full = 0, t_epi = 0, t_begin = 0;
+      if (timing) t_begin = clock64();
       auto wait_full = [&]() -> uint32_t {
         const int s = it % STAGES;
+        long long tq = 0;
+        if (timing) tq = clock64();
         mbar_wait(full_bar(s), (it / STAGES) & 1);
+        if (timing) t_full += clock64() - tq;
         tc_fence_after();
         return smem_base + s * WP_STAGE_BYTES;
       };
       auto wait_epi = [&](uint32_t bar, uint32_t ph) {
+        long long tq = 0;
+        if (timing) tq = clock64();
         mbar_wait(bar, ph);
+        if (timing) t_epi += clock64() - tq;
         tc_fence_after();
       };
       for (int pt = pair; pt < n_pair_tiles; pt += n_pairs, ++n) {
@@ -372,6 +386,11 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
           }
         }
       }
+      if (timing && lane == 0) {
+        atomicAdd(p.timing + 0, static_cast<unsigned long long>(clock64() - t_begin));
+        atomicAdd(p.timing + 1, static_cast<unsigned long long>(t_full));
+        atomicAdd(p.timing + 2, static_cast<unsigned long long>(t_epi));
+      }
     }
   } else {
     // ======================================= epilogue (both CTAs) ==============================
@@ -385,6 +404,8 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
     const uint32_t r_drained0 = mapa_u32(drained_bar(0), 0), r_drained1 = mapa_u32(drained_bar(1), 0);
     const uint32_t r_actsa = mapa_u32(actsa_bar, 0), r_acts = mapa_u32(acts_bar, 0);
     const uint32_t r_epi2 = mapa_u32(epi2_bar, 0), r_acts2 = mapa_u32(acts2_bar, 0);
+    const bool tmr = timing && leader && we == 0 && lane == 0;
+    long long t_w0 = 0, t_w1 = 0, t_w2 = 0, t_e1 = 0, t_e2 = 0;
     uint32_t n = 0;
     for (int pt = pair; pt < n_pair_tiles; pt += n_pairs, ++n) {
       int r, t0;
@@ -399,8 +420,11 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
 
 #pragma unroll 1
       for (int q = 0; q < 2; ++q) {
+        long long tw0 = 0, tw1 = 0;
+        if (tmr) tw0 = clock64();
         mbar_wait(dfull_bar(q), ph);
         tc_fence_after();
+        if (tmr) { tw1 = clock64(); (q == 0 ? t_w0 : t_w1) += tw1 - tw0; }
         const uint32_t taddr = tmem_base + lane_addr + 256u * (q == 0 ? par : (par ^ 1u)) + hf * 32;
         uint32_t t0r[16], g0r[16], t1r[16], g1r[16];
         tmem_ld16(taddr, t0r);
@@ -433,6 +457,7 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
           fence_proxy_async_smem();   // acts (generic-proxy writes) -> visible to the MMA (async proxy)
           mbar_arrive_cluster(q == 0 ? r_actsa : r_acts);
         }
+        if (tmr) t_e1 += clock64() - tw1;
       }
       float o8[8];
 #pragma unroll
@@ -453,8 +478,11 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
       }
 
       if (!LAST) {
+        long long tw0 = 0, tw1 = 0;
+        if (tmr) tw0 = clock64();
         mbar_wait(dfull_bar(2), ph);
         tc_fence_after();
+        if (tmr) { tw1 = clock64(); t_w2 += tw1 - tw0; }
         const uint32_t taddr = tmem_base + lane_addr + 256u * par + hf * 128;
         uint8_t* stg = acts + (hf * 2) * WL_A_BYTES + row * 128;
         const uint32_t stg_addr = smem_base + G::OFF_ACTS + (hf * 2) * WL_A_BYTES;
@@ -494,10 +522,18 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
         resid_pass(std::integral_constant<int, 0>{});
         resid_pass(std::integral_constant<int, 1>{});
         if (issuer) bulk_wait_read0();
+        if (tmr) t_e2 += clock64() - tw1;
       }
       asm volatile("bar.sync 1, %0;" ::"n"(WL_EPI_THREADS) : "memory");
     }
     if (!LAST && lane == 0 && (we == 0 || we == 4)) bulk_wait0();
+    if (tmr) {
+      atomicAdd(p.timing + 3, static_cast<unsigned long long>(t_w0));
+      atomicAdd(p.timing + 4, static_cast<unsigned long long>(t_w1));
+      atomicAdd(p.timing + 5, static_cast<unsigned long long>(t_w2));
+      atomicAdd(p.timing + 6, static_cast<unsigned long long>(t_e1));
+      atomicAdd(p.timing + 7, static_cast<unsigned long long>(t_e2));
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -538,10 +574,10 @@ inline void tc_pair_prepare(TcPairMaps& pm, const TcPlan& pl, int n_layers_total
 
 inline int tc_wn_layer_pair(const TcPlan& pl, const TcPairMaps& pm, int layer, int dilation, bool last, int hcur,
                             float* acc8, const float* b1, const float* b2, const float* wse_host, cudaStream_t st,
-                            bool first = false) {
+                            bool first = false, unsigned long long* timing = nullptr) {
   if (!pl.pm || pl.C != 256) fail(WG_ERR_UNSUPPORTED, "the CTA-pair kernel is built for the phase-major layout, C = 256");
   WnLayerParams p{};
-  tc_fill_params(pl, p, layer, dilation, hcur, acc8, b1, b2, nullptr, 0);
+  tc_fill_params(pl, p, layer, dilation, hcur, acc8, b1, b2, timing, 0);
   WnLayerConst cw;
   std::memcpy(cw.wse, wse_host, sizeof cw.wse);
   const int max_pairs = pl.sm_count / 2;
