@@ -142,6 +142,11 @@ int wg_profile_read(wg_handle h, double* layer_ms_sum, int32_t* layer_launches);
  * [8] TMA producer waiting for free stages. */
 int wg_debug_read_timing(wg_handle h, uint64_t* out128);   /* [16..80): MMA wait-for-data cycles by stage position in the tile */
 
+/* CTA-pair (cta_group::2) layer kernel of WG_MODE_BF16, C = 256: *max_pairs = clusters of two CTAs that can be resident at
+ * once on this device (74 on a B200 whose 148 SMs form 74 complete TPCs; fewer on parts whose disabled SMs are spread over
+ * TPCs -- the engine then keeps the single-CTA kernel), *last_used = 1 if the last wg_infer on this handle ran on it. */
+int wg_debug_pair_info(wg_handle h, int32_t* max_pairs, int32_t* last_used);
+
 /* Runs wg_infer but stops after WN layer `stop_layer` of flow `stop_flow` (flows run 11..0) and
  * copies the residual stream h [B*L, C] (float32) and the pre-coupling accumulator [B*L, 8] to
  * the given DEVICE buffers (either may be NULL). stop_layer == -1: stop right after the start

@@ -24,7 +24,7 @@ ABI_VERSION = 2
 
 # every symbol include/wg_b200.h declares (tests check the library exports all of them)
 EXPORTS = ["wg_abi_version", "wg_create", "wg_destroy", "wg_last_error", "wg_workspace_bytes", "wg_infer",
-           "wg_infer_host", "wg_workspace_bytes_ragged", "wg_infer_ragged", "wg_infer_host_ragged", "wg_last_launch_count", "wg_profile_enable", "wg_profile_read", "wg_debug_read_timing", "wg_debug_infer_prefix", "wg_debug_get_spect",
+           "wg_infer_host", "wg_workspace_bytes_ragged", "wg_infer_ragged", "wg_infer_host_ragged", "wg_last_launch_count", "wg_profile_enable", "wg_profile_read", "wg_debug_read_timing", "wg_debug_pair_info", "wg_debug_infer_prefix", "wg_debug_get_spect",
            "wg_debug_gemm_bf16"]
 # ... and include/wg_mel_b200.h
 MEL_EXPORTS = ["wg_mel_create", "wg_mel_destroy", "wg_mel_last_error", "wg_mel_frames", "wg_mel_spectrogram",
@@ -129,6 +129,8 @@ def load_library():
     lib.wg_profile_read.argtypes = [vp, c.POINTER(c.c_double), c.POINTER(i32)]
     lib.wg_debug_read_timing.restype = c.c_int
     lib.wg_debug_read_timing.argtypes = [vp, c.POINTER(c.c_uint64)]
+    lib.wg_debug_pair_info.restype = c.c_int
+    lib.wg_debug_pair_info.argtypes = [vp, c.POINTER(i32), c.POINTER(i32)]
     lib.wg_debug_infer_prefix.restype = c.c_int
     lib.wg_debug_infer_prefix.argtypes = [vp, vp, vp, c.c_float, i32, i32, i32, vp, c.c_size_t, vp, i32, i32, vp, vp]
     lib.wg_debug_get_spect.restype = c.c_int

@@ -29,7 +29,7 @@ namespace {
 using namespace wg;
 
 #ifndef WG_PAIR_DEFAULT
-#define WG_PAIR_DEFAULT 0        // measured default of the CTA-pair layer kernel
+#define WG_PAIR_DEFAULT 1        // the CTA-pair layer kernel is the default where its wave count allows
 #endif
 constexpr int HOP = 256;         // upsample stride (waveglow_arch.py:197)
 constexpr int UPSAMPLE_K = 1024; // upsample kernel size
@@ -102,6 +102,8 @@ struct wg_engine {
   unsigned long long* timing = nullptr;   // WG_LAYER_TIMING=1: in-kernel cycle counters (debug)
   int dbg_flags = 0;                      // WG_DEBUG_FLAGS, honoured only by a -DWG_PROBES build (WnLayerParams::flags)
   int pair_policy = -1;                   // WG_PAIR: 1 = CTA-pair (cta_group::2) layer kernel, 0 = single-CTA kernel, -1 = default
+  int pair_max = 0;                       // CTA pairs that can be resident at once on this device (tc_pair_init)
+  int last_pair = 0;                      // the last wg_infer ran its layers on the CTA-pair kernel
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;   // pairs: [2i] start, [2i+1] stop
   std::vector<int> ev_count;          // per pair: layer launches bracketed by it
@@ -202,11 +204,18 @@ bool use_pm(const wg_engine* e, int B, int T) {
   return cost_pm <= cost_pos;
 }
 
-// CTA-pair layer kernel (phase-major, C = 256): needs at least one full wave of pair tiles to pay off; WG_PAIR=0/1 forces.
+// CTA-pair layer kernel (phase-major, C = 256; tc_pair_kernels.cuh): same bits, 3-4 % less time per tile (same-box A/B,
+// profiles/r02_pair_ab.jsonl) -- chosen when its wave count (pairs of row tiles on pairs of SMs; an odd tile count per phase
+// block leaves a ghost tile) does not eat that gain. WG_PAIR=0/1 forces either kernel.
 bool use_pair(const wg_engine* e, const TcPlan& pl) {
-  if (e->pair_policy == 0) return false;
+  if (e->pair_policy == 0 || e->pair_max < 1) return false;
   if (e->pair_policy == 1) return true;
-  return WG_PAIR_DEFAULT && ((pl.tiles_per_row + 1) / 2) * pl.R >= e->sm_count / 2;
+  if (!WG_PAIR_DEFAULT) return false;
+  // a device whose complete TPCs are fewer than sm_count / 2 leaves SMs idle under the pair kernel: the wave count decides
+  const long sm = e->sm_count > 0 ? e->sm_count : 148, pairs = e->pair_max;
+  const long tiles = (long)pl.tiles_per_row * pl.R, pair_tiles = (long)((pl.tiles_per_row + 1) / 2) * pl.R;
+  const double cost_single = (double)((tiles + sm - 1) / sm), cost_pair = 0.966 * (double)((pair_tiles + pairs - 1) / pairs);
+  return cost_pair < cost_single;
 }
 
 Ws carve(const wg_engine* e, int B, int T, const Ragged* rg = nullptr) {
@@ -390,8 +399,9 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
                e->Wup16, R * S, e->W1, e->W2, aup16, spect16, h16[0], h16[1], hlo, pm, R, e->V,
                fold0 ? a0 : nullptr, e->W0, e->H0, c.n_flows, pm ? pm_gap(e) : 0, rg ? &geo : nullptr);
     if (const char* to = std::getenv("WG_TILE_ORDER")) plan.tile_order = to[0] != '0';
+    e->last_pair = 0;
     if (pm && C == 256 && use_pair(e, plan))
-      tc_pair_prepare(pmaps, plan, c.n_flows * c.n_layers, c.n_flows, R, e->W1, e->W2, e->V, e->W0, e->H0);
+      tc_pair_prepare(pmaps, plan, c.n_flows * c.n_layers, c.n_flows, R, e->W1, e->W2, e->V, e->W0, e->H0, e->pair_max);
     if (C == 512) make_map_4d(&m_acts512, acts16, 1, pm ? (uint64_t)R : (uint64_t)B, plan.Trows, C, WL_BM);
     e->launches += tc_upsample(plan, mel, e->bup, st);
   }
@@ -498,7 +508,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
         if (C == 512)
           e->launches += tc512_wn_layer(plan, m_acts512, k * c.n_layers + i, d, last, hcur, acc8, pm ? lw.b1_pm : lw.b1,
                                         lw.b2, lw.wse_p.data(), st, fold0 && i == 0);
-        else if (pmaps.ready)
+        else if (pmaps.ready && (e->last_pair = 1))
           e->launches += tc_wn_layer_pair(plan, pmaps, k * c.n_layers + i, d, last, hcur, acc8, lw.b1_pm, lw.b2,
                                           lw.wse_p.data(), st, fold0 && i == 0, e->timing);
         else
@@ -945,7 +955,7 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
       if (const char* pmv = std::getenv("WG_PM")) e->pm_policy = std::atoi(pmv);
     }
     tc512_init();
-    tc_pair_init();
+    e->pair_max = std::min(tc_pair_init(), e->sm_count / 2);
     if (const char* pr = std::getenv("WG_PAIR")) e->pair_policy = std::atoi(pr);
 #ifdef WG_PROBES
     // A/B probes that deliberately BREAK the result to isolate a cost (profiles/r01_probes.md): compiled only into a
@@ -1201,6 +1211,13 @@ int wg_profile_read(wg_handle h, double* layer_ms_sum, int32_t* layer_launches) 
     h->ev_used = 0;
     h->ev_count.clear();
   });
+}
+
+int wg_debug_pair_info(wg_handle h, int32_t* max_pairs, int32_t* last_used) {
+  if (!h || !max_pairs || !last_used) return WG_ERR_INVALID;
+  *max_pairs = h->pair_max;
+  *last_used = h->last_pair;
+  return WG_OK;
 }
 
 int wg_debug_read_timing(wg_handle h, uint64_t* out128) {

@@ -544,21 +544,39 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
   }
 }
 
-inline void tc_pair_init() {
+// Returns how many CTA pairs (clusters of 2) of the layer kernel can be resident at once on this device. A pair needs
+// both SMs of one TPC; a part whose disabled SMs are spread over TPCs has fewer complete TPCs than sm_count / 2, and a
+// persistent grid larger than that would run its last clusters as a second round.
+inline int tc_pair_init() {
   WG_CK(cudaFuncSetAttribute(tc_wn_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WpGeom<false>::SMEM));
   WG_CK(cudaFuncSetAttribute(tc_wn_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WpGeom<true>::SMEM));
   WG_CK(cudaFuncSetAttribute(tc_wn_pair_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WpGeom<false>::SMEM));
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.gridDim = dim3(2 * 1024); cfg.blockDim = dim3(WL_THREADS); cfg.dynamicSmemBytes = WpGeom<false>::SMEM;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, tc_wn_pair_kernel<false>, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  return n;
 }
 
 // 128-row boxes (one CTA's half of a 256-row B chunk) over the stacked weight matrices
 struct TcPairMaps {
   CUtensorMap m_w1, m_wc, m_w2, m_w0, m_h0;
+  int max_pairs = 0;     // resident clusters of 2 on this device (tc_pair_init)
   bool ready = false;
 };
 
 inline void tc_pair_prepare(TcPairMaps& pm, const TcPlan& pl, int n_layers_total, int n_flows, int R, const __nv_bfloat16* W1,
-                            const __nv_bfloat16* W2, const __nv_bfloat16* V, const __nv_bfloat16* W0, const __nv_bfloat16* H0) {
+                            const __nv_bfloat16* W2, const __nv_bfloat16* V, const __nv_bfloat16* W0, const __nv_bfloat16* H0,
+                            int max_pairs) {
   const int C = pl.C;
+  pm.max_pairs = max_pairs;
   make_map_2d(&pm.m_w1, W1, (uint64_t)n_layers_total * 2 * C, 3 * C + pl.S, 128);
   make_map_2d(&pm.m_w2, W2, (uint64_t)n_layers_total * C, C, 128);
   make_map_2d(&pm.m_wc, V, (uint64_t)n_layers_total * R * 2 * C, pl.Kup, 128);
@@ -580,7 +598,7 @@ inline int tc_wn_layer_pair(const TcPlan& pl, const TcPairMaps& pm, int layer, i
   tc_fill_params(pl, p, layer, dilation, hcur, acc8, b1, b2, timing, 0);
   WnLayerConst cw;
   std::memcpy(cw.wse, wse_host, sizeof cw.wse);
-  const int max_pairs = pl.sm_count / 2;
+  const int max_pairs = pm.max_pairs;
   const int need_pairs = ((pl.tiles_per_row + 1) / 2) * pl.R;
   const int grid = 2 * (need_pairs < max_pairs ? need_pairs : max_pairs);
   if (first && (!pl.fold0 || last || dilation != 1)) fail(WG_ERR_INVALID, "start fold requested for a layer it does not apply to");

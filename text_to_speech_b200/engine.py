@@ -99,6 +99,12 @@ class WaveGlowEngine:
         self._check(self._lib.wg_profile_read(self._h, ctypes.byref(ms), ctypes.byref(n)), "wg_profile_read")
         return ms.value, n.value
 
+    def pair_info(self):
+        """(CTA pairs resident at once on this device, whether the last infer used the CTA-pair layer kernel)."""
+        a, b = ctypes.c_int32(), ctypes.c_int32()
+        self._check(self._lib.wg_debug_pair_info(self._h, ctypes.byref(a), ctypes.byref(b)), "wg_debug_pair_info")
+        return a.value, bool(b.value)
+
     def read_layer_timing(self):
         buf = (ctypes.c_uint64 * 128)()
         self._check(self._lib.wg_debug_read_timing(self._h, buf), "wg_debug_read_timing")

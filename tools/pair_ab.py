@@ -52,4 +52,5 @@ for name, eng in (("single", single), ("pair", pair)) * 2:
     e1.record()
     torch.cuda.synchronize()
     res[name].append(e0.elapsed_time(e1) / reps)
-print(json.dumps({"k2_ms_single": res["single"], "k2_ms_pair": res["pair"], "all_bitwise_equal": ok}), flush=True)
+print(json.dumps({"k2_ms_single": res["single"], "k2_ms_pair": res["pair"], "all_bitwise_equal": ok,
+                  "resident_cta_pairs": pair.pair_info()[0], "sm_count": torch.cuda.get_device_properties(0).multi_processor_count}), flush=True)
