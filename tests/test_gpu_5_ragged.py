@@ -225,3 +225,27 @@ def test_output_ring_views_and_copies(lib_built, tmp_path):
     for _ in range(3):
         rc(mel, z=-z, sigma=0.6)
     assert np.array_equal(c, keep)
+
+
+def test_pipelined_sweep_equals_the_plain_one(lib_built, tmp_path):
+    """sharding.run_rank_pipelined (pinned rings, copy stream, preallocated device buffers, runtime(out=...)) must return
+    exactly what the plain batch-by-batch loop returns, sweep after sweep."""
+    from text_to_speech_b200 import sharding
+    from text_to_speech_b200.runtime import B200WaveGlowRuntime
+    hp = WaveGlowHParams()
+    path = str(tmp_path / "wg.npz")
+    save_weights(path, hp, generate_weights(hp, 1234))
+    rng = np.random.default_rng(9)
+    lengths = [int(x) for x in rng.integers(4, 60, size=11)]
+    mels = [synthetic_inputs(300 + i, 1, n, hp)[0][0] for i, n in enumerate(lengths)]
+    plan = sharding.plan_batches(lengths, 1, max_frames=120, max_batch=4, ragged=True)[0]
+    rt = B200WaveGlowRuntime(path, mode="bf16", device=0)
+    want = sharding.run_rank(rt, mels, plan, ragged=True, sigma=0.6, deterministic=True)
+    for _ in range(2):
+        got, stats = sharding.run_rank_pipelined(rt, mels, plan, sigma=0.6, deterministic=True)
+        assert sorted(got) == sorted(want) and all(np.array_equal(got[i], want[i]) for i in want)
+        assert stats["h2d_bytes"] > 0 and stats["d2h_bytes"] == sum(len(b.indices) * b.T * 256 * 4 for b in plan)
+    d = torch.empty(2, 8 * 256, device="cuda")
+    mel, z = synthetic_inputs(1, 2, 8, hp)
+    r = rt(torch.from_numpy(mel).cuda(), z=torch.from_numpy(z).cuda(), sigma=0.6, out=d)      # graph path + out=
+    assert r.data_ptr() == d.data_ptr() and np.array_equal(d.cpu().numpy(), rt(mel, z=z, sigma=0.6))

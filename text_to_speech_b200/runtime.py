@@ -119,6 +119,7 @@ class B200WaveGlowRuntime(Runtime):
                           runtime-owned pinned buffer that stays valid for `output_ring - 1` further calls (the
                           TensorRT runtime precedent returns views that the very next call overwrites,
                           tensorrt_runtime.py:208-210).
+      out=tensor          device path: write the waveform into this caller-owned [B, 256*T] float32 CUDA tensor.
       graph_max_frames    calls with B*T <= this many frames replay a CUDA graph captured per (B, T, sigma,
                           deterministic, lengths) instead of launching ~120 kernels one by one; 0 disables.
                           `precompile()` captures them ahead of time (the analogue of
@@ -239,7 +240,7 @@ class B200WaveGlowRuntime(Runtime):
         torch.cuda.synchronize(torch.device("cuda", eng.device))
         return done
 
-    def __call__(self, inputs, z=None, sigma=1.0, deterministic=False, lengths=None, **_ignored):
+    def __call__(self, inputs, z=None, sigma=1.0, deterministic=False, lengths=None, out=None, **_ignored):
         import torch
         eng = self.engine
         dev = torch.device("cuda", eng.device)
@@ -279,6 +280,7 @@ class B200WaveGlowRuntime(Runtime):
                 z_src.copy_(torch.from_numpy(z_np))
         if lengths is not None:
             lengths = [int(x) for x in lengths]
+        _out_arg = out          # device path only: caller-owned [B, 256 T] float32 CUDA tensor to write into
         g = self._graph_for(B, T, sigma, deterministic, lengths)
         if g is not None:
             g.mel.copy_(mel_src, non_blocking=True)
@@ -290,9 +292,12 @@ class B200WaveGlowRuntime(Runtime):
         else:
             mel = mel_src if mel_src.is_cuda else mel_src.to(dev, non_blocking=True)
             z_dev = None if z_src is None else (z_src if z_src.is_cuda else z_src.to(dev, non_blocking=True))
-            out = eng.infer_device(mel, z_dev, sigma=float(sigma), deterministic=bool(deterministic), lengths=lengths)
+            out = eng.infer_device(mel, z_dev, sigma=float(sigma), deterministic=bool(deterministic), lengths=lengths,
+                                   out=out if on_device else None)
         if on_device:
-            return out.clone() if g is not None else out     # a graph's output buffer is overwritten by its next replay
+            if g is not None:       # a graph's output buffer is overwritten by its next replay
+                return out.clone() if _out_arg is None else _out_arg.copy_(out)
+            return out
         po = self._pin_out((B, T * HOP))
         po.copy_(out, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()

@@ -165,9 +165,13 @@ def run_rank_pipelined(runtime, mels, plan_for_rank, pad_mel_value=-11.0, hop=25
     if st is None or st["cap_in"] < cap_in or st["cap_out"] < cap_out:
         st = {"cap_in": cap_in, "cap_out": cap_out, "copy_stream": torch.cuda.Stream(device=dev),
               "pin_in": [torch.empty(cap_in, dtype=torch.float32, pin_memory=True) for _ in range(2)],
-              "pin_out": [torch.empty(cap_out, dtype=torch.float32, pin_memory=True) for _ in range(2)]}
+              "pin_out": [torch.empty(cap_out, dtype=torch.float32, pin_memory=True) for _ in range(2)],
+              # device-side rings too: no allocator traffic (and none of its implicit synchronisations) inside the loop
+              "dev_in": [torch.empty(cap_in, dtype=torch.float32, device=dev) for _ in range(2)],
+              "dev_out": [torch.empty(cap_out, dtype=torch.float32, device=dev) for _ in range(2)]}
         runtime._sweep_state = st
     copy_stream, pin_in, pin_out = st["copy_stream"], st["pin_in"], st["pin_out"]
+    dev_in, dev_out, out_free = st["dev_in"], st["dev_out"], [None, None]
     in_free = [None, None]        # event: the H2D copy that read pin_in[i] has finished
     if z_seed is not None:
         runtime._seed, runtime._gen = int(z_seed), None
@@ -199,13 +203,17 @@ def run_rank_pipelined(runtime, mels, plan_for_rank, pad_mel_value=-11.0, hop=25
             n = mels[i].shape[0]
             xn[j, :n] = mels[i]
             xn[j, n:] = pad_mel_value
-        x_d = x.to(dev, non_blocking=True)
+        x_d = dev_in[slot][:B * T * n_mel].view(B, T, n_mel)
+        x_d.copy_(x, non_blocking=True)
         in_free[slot] = torch.cuda.Event()
         in_free[slot].record(main)
         stats["h2d_bytes"] += x.numel() * 4
         t1 = time.perf_counter()
         lengths = [int(mels[i].shape[0]) for i in batch.indices] if ragged else None
-        y_d = runtime(x_d, sigma=sigma, deterministic=deterministic, lengths=lengths)
+        if out_free[slot] is not None:
+            main.wait_event(out_free[slot])           # the D2H copy that read dev_out[slot] two batches ago
+        y_d = runtime(x_d, sigma=sigma, deterministic=deterministic, lengths=lengths,
+                      out=dev_out[slot][:B * T * hop].view(B, T * hop))
         done = torch.cuda.Event()
         done.record(main)
         t2 = time.perf_counter()
@@ -216,9 +224,9 @@ def run_rank_pipelined(runtime, mels, plan_for_rank, pad_mel_value=-11.0, hop=25
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(done)
             view.copy_(y_d, non_blocking=True)
-            y_d.record_stream(copy_stream)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
+        out_free[slot] = ev
         pending.append((batch, view, ev))
         stats["d2h_bytes"] += B * T * hop * 4
     drain(0)
