@@ -104,6 +104,7 @@ struct wg_engine {
   int pair_policy = -1;                   // WG_PAIR: 1 = CTA-pair (cta_group::2) layer kernel, 0 = single-CTA kernel, -1 = default
   int pair_max = 0;                       // CTA pairs that can be resident at once on this device (tc_pair_init)
   int last_pair = 0;                      // the last wg_infer ran its layers on the CTA-pair kernel
+  int pair_epi_warps = 8;                 // WG_PAIR_EPI=16: 16 epilogue warps in the pair kernel
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;   // pairs: [2i] start, [2i+1] stop
   std::vector<int> ev_count;          // per pair: layer launches bracketed by it
@@ -510,7 +511,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
                                         lw.b2, lw.wse_p.data(), st, fold0 && i == 0);
         else if (pmaps.ready && (e->last_pair = 1))
           e->launches += tc_wn_layer_pair(plan, pmaps, k * c.n_layers + i, d, last, hcur, acc8, lw.b1_pm, lw.b2,
-                                          lw.wse_p.data(), st, fold0 && i == 0, e->timing);
+                                          lw.wse_p.data(), st, fold0 && i == 0, e->timing, e->pair_epi_warps);
         else
           e->launches += tc_wn_layer(plan, k * c.n_layers + i, d, last, hcur, acc8, pm ? lw.b1_pm : lw.b1, lw.b2,
                                      lw.wse_p.data(), e->timing, e->dbg_flags, st, fold0 && i == 0);
@@ -957,6 +958,7 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
     tc512_init();
     e->pair_max = std::min(tc_pair_init(), e->sm_count / 2);
     if (const char* pr = std::getenv("WG_PAIR")) e->pair_policy = std::atoi(pr);
+    if (const char* pw = std::getenv("WG_PAIR_EPI")) e->pair_epi_warps = std::atoi(pw) == 16 ? 16 : 8;
 #ifdef WG_PROBES
     // A/B probes that deliberately BREAK the result to isolate a cost (profiles/r01_probes.md): compiled only into a
     // -DWG_PROBES build, and even there honoured only when the caller also sets WG_ALLOW_PROBES=1.

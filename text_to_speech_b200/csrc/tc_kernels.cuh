@@ -830,9 +830,12 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
       const uint32_t ph = n & 1u;
       const bool valid = wn_row_valid(p, t0 + row);
       const size_t m = (static_cast<size_t>(b) * p.R + r) * p.T + t0 + row;
-      float2 o8p[8];   // (even-channel, odd-channel) partial sums of the eight fold columns
+      // (even-channel, odd-channel) partial sums of the eight fold columns, one accumulator per 16-channel column class
+      // this thread owns ((channel mod 64) / 16 = 2 hf and 2 hf + 1): the classes are summed separately and then pairwise,
+      // ((S0 + S1) + (S2 + S3)), so that every layer-kernel variant (CTA pair, 8 or 16 epilogue warps) produces the same bits
+      float2 o8p[8], o8q[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o8p[j] = make_float2(0.f, 0.f);
+      for (int j = 0; j < 8; ++j) o8p[j] = o8q[j] = make_float2(0.f, 0.f);
 
       // ---- gate epilogue: chunk q holds gate channels [128 q, 128 q + 128) ---------------------
       // (loops deliberately NOT fully unrolled: the kernel must stay inside the instruction cache)
@@ -867,7 +870,7 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
             tmem_ld16(taddr + 64, t0r);
             tmem_ld16(taddr + 128 + 64, g0r);
           }
-          gate_step2<LAST>(t1r, g1r, bT0 + 16, wse0 + 64, kblk, hf * 2 + 1, row, o8p);
+          gate_step2<LAST>(t1r, g1r, bT0 + 16, wse0 + 64, kblk, hf * 2 + 1, row, o8q);
           if (!LAST && q == 1 && blk == 0) {
             fence_proxy_async_smem();
             mbar_arrive(acts2_bar);
@@ -885,7 +888,10 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
       // fold accumulator: even + odd channels, then the two column halves of a row, in a fixed order (bit-reproducible)
       float o8[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o8[j] = o8p[j].x + o8p[j].y;
+      for (int j = 0; j < 8; ++j) {
+        o8[j] = o8p[j].x + o8p[j].y;
+        o8[j] += o8q[j].x + o8q[j].y;
+      }
       if (hf == 1) {
         *reinterpret_cast<float4*>(s_o8 + row * 8) = make_float4(o8[0], o8[1], o8[2], o8[3]);
         *reinterpret_cast<float4*>(s_o8 + row * 8 + 4) = make_float4(o8[4], o8[5], o8[6], o8[7]);

@@ -81,22 +81,26 @@ constexpr int WP_A_BYTES = WL_BM * WL_BK * 2;          // 16 KB: own 128 rows x 
 constexpr int WP_B_BYTES = 128 * WL_BK * 2;            // 16 KB: own half (128 of 256 N rows) x 64 K
 constexpr int WP_STAGE_BYTES = WP_A_BYTES + WP_B_BYTES;
 // The LAST layer of a flow has no GEMM2 / residual, hence no acts tile, identity tile or staging: its ring can be 6 deep.
-template <bool LAST>
+// EW = epilogue warps (8 or 16): NQ = EW / 4 warps share a TMEM lane quarter and split the accumulator columns.
+template <bool LAST, int EW = 8>
 struct WpGeom {
+  static constexpr int NQ = EW / 4;
+  static constexpr int EPI_THREADS = EW * 32, THREADS = 64 + EPI_THREADS;
   static constexpr int STAGES = LAST ? 6 : 4;
   static constexpr int OFF_ACTS = STAGES * WP_STAGE_BYTES;
   static constexpr int OFF_I64 = OFF_ACTS + (LAST ? 0 : WL_ACTS_BYTES);   // own half (32 N rows) of the 64x64 identity
   static constexpr int OFF_B1 = OFF_I64 + (LAST ? 0 : 32 * 128);
   static constexpr int OFF_B2 = OFF_B1 + 2 * WL_C * 4;
   static constexpr int OFF_O8 = OFF_B2 + WL_C * 4;
-  static constexpr int OFF_BARS = OFF_O8 + WL_BM * 8 * 4;
+  static constexpr int OFF_BARS = OFF_O8 + (NQ - 1) * WL_BM * 8 * 4;   // fold partials of column groups 1 .. NQ-1
   static constexpr int NBARS = 2 * STAGES + 3 + 2 + 4;
   static constexpr int SMEM = OFF_BARS + NBARS * 8 + 16;
+  static_assert(EW == 8 || EW == 16, "8 or 16 epilogue warps");
   static_assert(SMEM <= 232448, "shared memory budget");
 };
 
-template <bool LAST, bool FIRST = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WL_THREADS, 1)
+template <bool LAST, bool FIRST = false, int EW = 8>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + EW * 32, 1)
 tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_ho,
                   const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_cond,
                   const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_wc,
@@ -104,8 +108,8 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
                   const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_h0, const WnLayerParams p,
                   const __grid_constant__ WnLayerConst cw) {
   static_assert(!(LAST && FIRST), "the start fold needs a residual layer");
-  using G = WpGeom<LAST>;
-  constexpr int STAGES = G::STAGES;
+  using G = WpGeom<LAST, EW>;
+  constexpr int STAGES = G::STAGES, NQ = G::NQ, EPI_THREADS = G::EPI_THREADS, THREADS = G::THREADS;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
   float* s_b1 = reinterpret_cast<float*>(smem + G::OFF_B1);
@@ -157,26 +161,26 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
       mbar_init(empty_bar(s), 1);
     }
     for (int i = 0; i < 3; ++i) mbar_init(dfull_bar(i), 1);
-    for (int i = 0; i < 2; ++i) mbar_init(drained_bar(i), 2 * WL_EPI_THREADS);
-    mbar_init(actsa_bar, 2 * WL_EPI_THREADS);
-    mbar_init(acts_bar, 2 * WL_EPI_THREADS);
-    mbar_init(epi2_bar, 2 * WL_EPI_THREADS);
-    mbar_init(acts2_bar, 2 * WL_EPI_THREADS);
+    for (int i = 0; i < 2; ++i) mbar_init(drained_bar(i), 2 * EPI_THREADS);
+    mbar_init(actsa_bar, 2 * EPI_THREADS);
+    mbar_init(acts_bar, 2 * EPI_THREADS);
+    mbar_init(epi2_bar, 2 * EPI_THREADS);
+    mbar_init(acts2_bar, 2 * EPI_THREADS);
     fence_barrier_init();
   }
   if (warp == 1) {
     tmem2_alloc(smem_u32(tmem_slot), 512);
     tmem2_relinquish();
   }
-  for (int i = threadIdx.x; i < 2 * WL_C; i += WL_THREADS) s_b1[i] = p.b1[i];
+  for (int i = threadIdx.x; i < 2 * WL_C; i += THREADS) s_b1[i] = p.b1[i];
   if (!LAST) {
-    for (int i = threadIdx.x; i < WL_C; i += WL_THREADS) s_b2[i] = p.b2[i];
+    for (int i = threadIdx.x; i < WL_C; i += THREADS) s_b2[i] = p.b2[i];
   }
   if (!LAST && !FIRST) {
     // own half of the identity B tile: local row nl is N row n = 32 * rank + nl; element (n, k) = [n == k]
     // (K-major SWIZZLE_128B: 16-byte chunk c of row nl sits at c ^ (nl & 7))
     uint32_t* i64w = reinterpret_cast<uint32_t*>(smem + G::OFF_I64);
-    for (int i = threadIdx.x; i < 32 * 32; i += WL_THREADS) {
+    for (int i = threadIdx.x; i < 32 * 32; i += THREADS) {
       const int nl = i >> 5, w = i & 31;
       const int n = 32 * static_cast<int>(rank) + nl;
       const int chunk_log = (w >> 2) ^ (nl & 7);
@@ -394,9 +398,12 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
     }
   } else {
     // ======================================= epilogue (both CTAs) ==============================
+    // NQ warps share a TMEM lane quarter; column group cq handles, of every 64-channel block, the 64 / NQ channels
+    // [cq * 64 / NQ, ...) in STEPS steps of 16 ("column class" = step index st = (channel mod 64) / 16).
+    constexpr int STEPS = 4 / NQ;
     const int we = warp - 2;
     const int quarter = warp & 3;       // TMEM lane quarter this warp may access
-    const int hf = we >> 2;             // which half of the columns this warp handles
+    const int cq = we >> 2;             // column group of this warp
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     uint8_t* acts = smem + G::OFF_ACTS;
@@ -414,9 +421,13 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
       const uint32_t ph = n & 1u;
       const bool valid = wn_row_valid(p, t0 + row);
       const size_t m = static_cast<size_t>(r) * p.T + t0 + row;
-      float2 o8p[8];
+      // one fold accumulator per column class this thread owns (summed per class, then pairwise: the same order
+      // whatever NQ is, so every layer-kernel variant produces the same bits)
+      float2 o8p[STEPS][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o8p[j] = make_float2(0.f, 0.f);
+      for (int i = 0; i < STEPS; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o8p[i][j] = make_float2(0.f, 0.f);
 
 #pragma unroll 1
       for (int q = 0; q < 2; ++q) {
@@ -425,29 +436,47 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
         mbar_wait(dfull_bar(q), ph);
         tc_fence_after();
         if (tmr) { tw1 = clock64(); (q == 0 ? t_w0 : t_w1) += tw1 - tw0; }
-        const uint32_t taddr = tmem_base + lane_addr + 256u * (q == 0 ? par : (par ^ 1u)) + hf * 32;
-        uint32_t t0r[16], g0r[16], t1r[16], g1r[16];
-        tmem_ld16(taddr, t0r);
-        tmem_ld16(taddr + 128, g0r);
+        const uint32_t taddr = tmem_base + lane_addr + 256u * (q == 0 ? par : (par ^ 1u)) + cq * (64 / NQ);
+        if constexpr (NQ == 2) {
+          uint32_t t0r[16], g0r[16], t1r[16], g1r[16];
+          tmem_ld16(taddr, t0r);
+          tmem_ld16(taddr + 128, g0r);
 #pragma unroll 1
-        for (int blk = 0; blk < 2; ++blk) {
-          uint8_t* kblk = acts + (q * 2 + blk) * WL_A_BYTES + row * 128;
-          const int ch0 = blk * 64 + hf * 32;
-          const float* bT0 = s_b1 + q * 256 + ch0;
-          const float2* wse0 = reinterpret_cast<const float2*>(cw.wse) + (q * 128 + ch0) * 4;
-          tmem_ld_wait();
-          tmem_ld16(taddr + blk * 64 + 16, t1r);
-          tmem_ld16(taddr + 128 + blk * 64 + 16, g1r);
-          gate_step2<LAST>(t0r, g0r, bT0, wse0, kblk, hf * 2, row, o8p);
-          tmem_ld_wait();
-          if (blk == 0) {
-            tmem_ld16(taddr + 64, t0r);
-            tmem_ld16(taddr + 128 + 64, g0r);
+          for (int blk = 0; blk < 2; ++blk) {
+            uint8_t* kblk = acts + (q * 2 + blk) * WL_A_BYTES + row * 128;
+            const int ch0 = blk * 64 + cq * 32;
+            const float* bT0 = s_b1 + q * 256 + ch0;
+            const float2* wse0 = reinterpret_cast<const float2*>(cw.wse) + (q * 128 + ch0) * 4;
+            tmem_ld_wait();
+            tmem_ld16(taddr + blk * 64 + 16, t1r);
+            tmem_ld16(taddr + 128 + blk * 64 + 16, g1r);
+            gate_step2<LAST>(t0r, g0r, bT0, wse0, kblk, cq * 2, row, o8p[0]);
+            tmem_ld_wait();
+            if (blk == 0) {
+              tmem_ld16(taddr + 64, t0r);
+              tmem_ld16(taddr + 128 + 64, g0r);
+            }
+            gate_step2<LAST>(t1r, g1r, bT0 + 16, wse0 + 64, kblk, cq * 2 + 1, row, o8p[STEPS - 1]);
+            if (!LAST && q == 1 && blk == 0) {
+              fence_proxy_async_smem();
+              mbar_arrive_cluster(r_acts2);
+            }
           }
-          gate_step2<LAST>(t1r, g1r, bT0 + 16, wse0 + 64, kblk, hf * 2 + 1, row, o8p);
-          if (!LAST && q == 1 && blk == 0) {
-            fence_proxy_async_smem();
-            mbar_arrive_cluster(r_acts2);
+        } else {
+          uint32_t tr[16], gr[16];
+#pragma unroll 1
+          for (int blk = 0; blk < 2; ++blk) {
+            uint8_t* kblk = acts + (q * 2 + blk) * WL_A_BYTES + row * 128;
+            const int ch0 = blk * 64 + cq * 16;
+            tmem_ld16(taddr + blk * 64, tr);
+            tmem_ld16(taddr + 128 + blk * 64, gr);
+            tmem_ld_wait();
+            gate_step2<LAST>(tr, gr, s_b1 + q * 256 + ch0, reinterpret_cast<const float2*>(cw.wse) + (q * 128 + ch0) * 4, kblk, cq,
+                             row, o8p[0]);
+            if (!LAST && q == 1 && blk == 0) {
+              fence_proxy_async_smem();
+              mbar_arrive_cluster(r_acts2);
+            }
           }
         }
         tc_fence_before();
@@ -459,74 +488,97 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
         }
         if (tmr) t_e1 += clock64() - tw1;
       }
+      // fold: per class even + odd channel lanes, then the classes pairwise ((S0 + S1) + (S2 + S3)), in a fixed order
       float o8[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o8[j] = o8p[j].x + o8p[j].y;
-      if (hf == 1) {
-        *reinterpret_cast<float4*>(s_o8 + row * 8) = make_float4(o8[0], o8[1], o8[2], o8[3]);
-        *reinterpret_cast<float4*>(s_o8 + row * 8 + 4) = make_float4(o8[4], o8[5], o8[6], o8[7]);
+      for (int j = 0; j < 8; ++j) {
+        o8[j] = o8p[0][j].x + o8p[0][j].y;
+        if (STEPS == 2) o8[j] += o8p[STEPS - 1][j].x + o8p[STEPS - 1][j].y;
       }
-      asm volatile("bar.sync 2, %0;" ::"n"(WL_EPI_THREADS) : "memory");
-      if (hf == 0 && valid) {
-        const float4 p0 = *reinterpret_cast<const float4*>(s_o8 + row * 8);
-        const float4 p1 = *reinterpret_cast<const float4*>(s_o8 + row * 8 + 4);
+      if (cq > 0) {
+        float* dst = s_o8 + ((cq - 1) * WL_BM + row) * 8;
+        *reinterpret_cast<float4*>(dst) = make_float4(o8[0], o8[1], o8[2], o8[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(o8[4], o8[5], o8[6], o8[7]);
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(EPI_THREADS) : "memory");
+      if (cq == 0 && valid) {
+        float tot[8];
+        if constexpr (NQ == 2) {
+          const float* p1 = s_o8 + row * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) tot[j] = o8[j] + p1[j];
+        } else {
+          const float* p1 = s_o8 + row * 8;
+          const float* p2 = s_o8 + (WL_BM + row) * 8;
+          const float* p3 = s_o8 + (2 * WL_BM + row) * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) tot[j] = (o8[j] + p1[j]) + (p2[j] + p3[j]);
+        }
         float4* o = reinterpret_cast<float4*>(p.acc8 + m * 8);
         float4 a0 = o[0], a1 = o[1];
-        a0.x += o8[0] + p0.x; a0.y += o8[1] + p0.y; a0.z += o8[2] + p0.z; a0.w += o8[3] + p0.w;
-        a1.x += o8[4] + p1.x; a1.y += o8[5] + p1.y; a1.z += o8[6] + p1.z; a1.w += o8[7] + p1.w;
+        a0.x += tot[0]; a0.y += tot[1]; a0.z += tot[2]; a0.w += tot[3];
+        a1.x += tot[4]; a1.y += tot[5]; a1.z += tot[6]; a1.w += tot[7];
         o[0] = a0; o[1] = a1;
       }
 
+      // ---- residual epilogue: column group cq owns 256 / NQ accumulator columns = 4 / NQ blocks of 64 ----
       if (!LAST) {
+        constexpr int NBLK = 4 / NQ, NG = 16 / NQ;     // 64-column blocks and 16-column groups per column group
         long long tw0 = 0, tw1 = 0;
         if (tmr) tw0 = clock64();
         mbar_wait(dfull_bar(2), ph);
         tc_fence_after();
         if (tmr) { tw1 = clock64(); t_w2 += tw1 - tw0; }
-        const uint32_t taddr = tmem_base + lane_addr + 256u * par + hf * 128;
-        uint8_t* stg = acts + (hf * 2) * WL_A_BYTES + row * 128;
-        const uint32_t stg_addr = smem_base + G::OFF_ACTS + (hf * 2) * WL_A_BYTES;
-        const bool issuer = (we == hf * 4) && lane == 0;
+        const uint32_t taddr = tmem_base + lane_addr + 256u * par + cq * (256 / NQ);
+        uint8_t* stg = acts + (cq * NBLK) * WL_A_BYTES + row * 128;
+        const uint32_t stg_addr = smem_base + G::OFF_ACTS + (cq * NBLK) * WL_A_BYTES;
+        const bool issuer = (we == cq * 4) && lane == 0;
+        auto group_sync = [&]() {      // the 128 threads of this column group
+          if (cq == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
+          else if (cq == 1) asm volatile("bar.sync 4, 128;" ::: "memory");
+          else if (cq == 2) asm volatile("bar.sync 5, 128;" ::: "memory");
+          else asm volatile("bar.sync 6, 128;" ::: "memory");
+        };
         auto resid_pass = [&](auto pass_tag) {
           constexpr int pass = decltype(pass_tag)::value;
           if (pass == 1) {
-            if (issuer) bulk_wait_read0();
-            if (hf == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
-            else asm volatile("bar.sync 4, 128;" ::: "memory");
+            if (issuer) bulk_wait_read0();   // the hi store has finished reading the staging tile
+            group_sync();
           }
           uint32_t r0[16], r1[16];
           tmem_ld16(taddr, r0);
 #pragma unroll 1
-          for (int gp = 0; gp < 4; ++gp) {
+          for (int gp = 0; gp < NG / 2; ++gp) {          // two groups of 16 columns per iteration
             tmem_ld_wait();
             tmem_ld16(taddr + (2 * gp + 1) * 16, r1);
-            resid_step2<pass>(r0, s_b2 + hf * 128 + (2 * gp) * 16, stg, 2 * gp, row, valid);
+            resid_step2<pass>(r0, s_b2 + cq * (256 / NQ) + (2 * gp) * 16, stg, 2 * gp, row, valid);
             tmem_ld_wait();
-            if (gp < 3) tmem_ld16(taddr + (2 * gp + 2) * 16, r0);
+            if (gp < NG / 2 - 1) tmem_ld16(taddr + (2 * gp + 2) * 16, r0);
             else if (pass == 1) {
               tc_fence_before();
               mbar_arrive_cluster(r_epi2);   // all TMEM reads of this tile are done
             }
-            resid_step2<pass>(r1, s_b2 + hf * 128 + (2 * gp + 1) * 16, stg, 2 * gp + 1, row, valid);
+            resid_step2<pass>(r1, s_b2 + cq * (256 / NQ) + (2 * gp + 1) * 16, stg, 2 * gp + 1, row, valid);
           }
           fence_proxy_async_smem();
-          if (hf == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
-          else asm volatile("bar.sync 4, 128;" ::: "memory");
+          group_sync();
           if (issuer) {
             const CUtensorMap* om = pass == 0 ? &map_ho : &map_lo;
-            tma_store_4d(om, stg_addr, (hf * 2) * WL_BK, t0, r, 0);
-            tma_store_4d(om, stg_addr + WL_A_BYTES, (hf * 2 + 1) * WL_BK, t0, r, 0);
+#pragma unroll
+            for (int bk = 0; bk < NBLK; ++bk)
+              tma_store_4d(om, stg_addr + bk * WL_A_BYTES, (cq * NBLK + bk) * WL_BK, t0, r, 0);
             bulk_commit();
           }
         };
         resid_pass(std::integral_constant<int, 0>{});
         resid_pass(std::integral_constant<int, 1>{});
-        if (issuer) bulk_wait_read0();
+        if (issuer) bulk_wait_read0();   // staging tile may be overwritten by the next gate epilogue
         if (tmr) t_e2 += clock64() - tw1;
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(WL_EPI_THREADS) : "memory");
+      // s_o8 and the staging tile are reused by the next tile: no epilogue warp may run ahead
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
     }
-    if (!LAST && lane == 0 && (we == 0 || we == 4)) bulk_wait0();
+    if (!LAST && lane == 0 && (we & 3) == 0) bulk_wait0();   // all TMA stores of this CTA have landed
     if (tmr) {
       atomicAdd(p.timing + 3, static_cast<unsigned long long>(t_w0));
       atomicAdd(p.timing + 4, static_cast<unsigned long long>(t_w1));
@@ -547,18 +599,28 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
 // Returns how many CTA pairs (clusters of 2) of the layer kernel can be resident at once on this device. A pair needs
 // both SMs of one TPC; a part whose disabled SMs are spread over TPCs has fewer complete TPCs than sm_count / 2, and a
 // persistent grid larger than that would run its last clusters as a second round.
+template <int EW>
+inline void tc_pair_set_attrs() {
+  WG_CK(cudaFuncSetAttribute(tc_wn_pair_kernel<false, false, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, WpGeom<false, EW>::SMEM));
+  WG_CK(cudaFuncSetAttribute(tc_wn_pair_kernel<true, false, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, WpGeom<true, EW>::SMEM));
+  WG_CK(cudaFuncSetAttribute(tc_wn_pair_kernel<false, true, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, WpGeom<false, EW>::SMEM));
+}
+// The 16-epilogue-warp instantiation (EW = 16, four warps per TMEM lane quarter) is a measured probe: bit-identical, no
+// faster (K2 55.3 ms vs 54.6-54.8 ms with 8 warps on the same box) -- the step is power-capped, not epilogue-bound. It is
+// compiled only into a -DWG_PROBES build (WG_PAIR_EPI=16 selects it there).
 inline int tc_pair_init() {
-  WG_CK(cudaFuncSetAttribute(tc_wn_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WpGeom<false>::SMEM));
-  WG_CK(cudaFuncSetAttribute(tc_wn_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WpGeom<true>::SMEM));
-  WG_CK(cudaFuncSetAttribute(tc_wn_pair_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WpGeom<false>::SMEM));
+  tc_pair_set_attrs<8>();
+#ifdef WG_PROBES
+  tc_pair_set_attrs<16>();
+#endif
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr{};
   attr.id = cudaLaunchAttributeClusterDimension;
   attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-  cfg.gridDim = dim3(2 * 1024); cfg.blockDim = dim3(WL_THREADS); cfg.dynamicSmemBytes = WpGeom<false>::SMEM;
+  cfg.gridDim = dim3(2 * 1024); cfg.blockDim = dim3(WpGeom<false, 8>::THREADS); cfg.dynamicSmemBytes = WpGeom<false, 8>::SMEM;
   cfg.attrs = &attr; cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, tc_wn_pair_kernel<false>, &cfg) != cudaSuccess) {
+  if (cudaOccupancyMaxActiveClusters(&n, tc_wn_pair_kernel<false, false, 8>, &cfg) != cudaSuccess) {
     cudaGetLastError();
     n = 0;
   }
@@ -590,9 +652,20 @@ inline void tc_pair_prepare(TcPairMaps& pm, const TcPlan& pl, int n_layers_total
   pm.ready = true;
 }
 
+template <int EW>
+inline void tc_pair_launch(const TcPlan& pl, const TcPairMaps& pm, const WnLayerParams& p, const WnLayerConst& cw, int grid, bool last,
+                           bool first, int hcur, cudaStream_t st) {
+  if (last)
+    tc_wn_pair_kernel<true, false, EW><<<grid, WpGeom<true, EW>::THREADS, WpGeom<true, EW>::SMEM, st>>>(pl.m4_h[hcur], pl.m4_h[hcur ^ 1], pl.m4_lo, pl.m4_cond, pm.m_w1, pm.m_wc, pm.m_w2, pl.m4_a0, pm.m_w0, pm.m_h0, p, cw);
+  else if (first)
+    tc_wn_pair_kernel<false, true, EW><<<grid, WpGeom<false, EW>::THREADS, WpGeom<false, EW>::SMEM, st>>>(pl.m4_h[hcur], pl.m4_h[hcur ^ 1], pl.m4_lo, pl.m4_cond, pm.m_w1, pm.m_wc, pm.m_w2, pl.m4_a0, pm.m_w0, pm.m_h0, p, cw);
+  else
+    tc_wn_pair_kernel<false, false, EW><<<grid, WpGeom<false, EW>::THREADS, WpGeom<false, EW>::SMEM, st>>>(pl.m4_h[hcur], pl.m4_h[hcur ^ 1], pl.m4_lo, pl.m4_cond, pm.m_w1, pm.m_wc, pm.m_w2, pl.m4_a0, pm.m_w0, pm.m_h0, p, cw);
+}
+
 inline int tc_wn_layer_pair(const TcPlan& pl, const TcPairMaps& pm, int layer, int dilation, bool last, int hcur,
                             float* acc8, const float* b1, const float* b2, const float* wse_host, cudaStream_t st,
-                            bool first = false, unsigned long long* timing = nullptr) {
+                            bool first = false, unsigned long long* timing = nullptr, int epi_warps = 8) {
   if (!pl.pm || pl.C != 256) fail(WG_ERR_UNSUPPORTED, "the CTA-pair kernel is built for the phase-major layout, C = 256");
   WnLayerParams p{};
   tc_fill_params(pl, p, layer, dilation, hcur, acc8, b1, b2, timing, 0);
@@ -602,12 +675,15 @@ inline int tc_wn_layer_pair(const TcPlan& pl, const TcPairMaps& pm, int layer, i
   const int need_pairs = ((pl.tiles_per_row + 1) / 2) * pl.R;
   const int grid = 2 * (need_pairs < max_pairs ? need_pairs : max_pairs);
   if (first && (!pl.fold0 || last || dilation != 1)) fail(WG_ERR_INVALID, "start fold requested for a layer it does not apply to");
-  if (last)
-    tc_wn_pair_kernel<true><<<grid, WL_THREADS, WpGeom<true>::SMEM, st>>>(pl.m4_h[hcur], pl.m4_h[hcur ^ 1], pl.m4_lo, pl.m4_cond, pm.m_w1, pm.m_wc, pm.m_w2, pl.m4_a0, pm.m_w0, pm.m_h0, p, cw);
-  else if (first)
-    tc_wn_pair_kernel<false, true><<<grid, WL_THREADS, WpGeom<false>::SMEM, st>>>(pl.m4_h[hcur], pl.m4_h[hcur ^ 1], pl.m4_lo, pl.m4_cond, pm.m_w1, pm.m_wc, pm.m_w2, pl.m4_a0, pm.m_w0, pm.m_h0, p, cw);
-  else
-    tc_wn_pair_kernel<false><<<grid, WL_THREADS, WpGeom<false>::SMEM, st>>>(pl.m4_h[hcur], pl.m4_h[hcur ^ 1], pl.m4_lo, pl.m4_cond, pm.m_w1, pm.m_wc, pm.m_w2, pl.m4_a0, pm.m_w0, pm.m_h0, p, cw);
+#ifdef WG_PROBES
+  if (epi_warps == 16) {
+    tc_pair_launch<16>(pl, pm, p, cw, grid, last, first, hcur, st);
+    WG_CK(cudaGetLastError());
+    return 1;
+  }
+#endif
+  (void)epi_warps;
+  tc_pair_launch<8>(pl, pm, p, cw, grid, last, first, hcur, st);
   WG_CK(cudaGetLastError());
   return 1;
 }

@@ -20,6 +20,8 @@ os.environ["WG_PAIR"] = "0"
 single = WaveGlowEngine(hp, w, mode="bf16")
 os.environ["WG_PAIR"] = "1"
 pair = WaveGlowEngine(hp, w, mode="bf16")
+os.environ["WG_PAIR_EPI"] = "16"
+wide = WaveGlowEngine(hp, w, mode="bf16")      # CTA pairs with 16 epilogue warps (a -DWG_PROBES build; else the same as `pair`)
 
 
 def run(eng, mel, z, lengths=None):
@@ -31,17 +33,17 @@ def run(eng, mel, z, lengths=None):
 ok = True
 for (B, T, lengths) in [(1, 12, None), (2, 150, None), (3, 300, None), (1, 200, None), (4, 97, [97, 5, 33, 64]), (16, 860, None)]:
     mel, z = synthetic_inputs(B * 1000 + T, B, T, hp)
-    a, b = run(single, mel, z, lengths), run(pair, mel, z, lengths)
-    same = bool(np.array_equal(a, b))
+    a, b, c = run(single, mel, z, lengths), run(pair, mel, z, lengths), run(wide, mel, z, lengths)
+    same = bool(np.array_equal(a, b)) and bool(np.array_equal(a, c))
     ok &= same
     print(json.dumps({"B": B, "T": T, "ragged": lengths is not None, "bitwise_equal": same,
-                      "max_abs_diff": float(np.abs(a - b).max()), "finite": bool(np.isfinite(b).all()),
+                      "max_abs_diff": float(max(np.abs(a - b).max(), np.abs(a - c).max())), "finite": bool(np.isfinite(c).all()),
                       "launches": pair.last_launch_count}), flush=True)
 mel, z = synthetic_inputs(2024, 16, 860, hp)
 md, zd = torch.from_numpy(mel).cuda(), torch.from_numpy(z).cuda()
 out = torch.empty(16, 860 * 256, device="cuda")
-res = {"single": [], "pair": []}
-for name, eng in (("single", single), ("pair", pair)) * 2:
+res = {"single": [], "pair": [], "pair16": []}
+for name, eng in (("single", single), ("pair", pair), ("pair16", wide)) * 2:
     for _ in range(2):
         eng.infer_device(md, zd, 0.6, out=out)
     torch.cuda.synchronize()
@@ -52,5 +54,5 @@ for name, eng in (("single", single), ("pair", pair)) * 2:
     e1.record()
     torch.cuda.synchronize()
     res[name].append(e0.elapsed_time(e1) / reps)
-print(json.dumps({"k2_ms_single": res["single"], "k2_ms_pair": res["pair"], "all_bitwise_equal": ok,
+print(json.dumps({"k2_ms_single": res["single"], "k2_ms_pair": res["pair"], "k2_ms_pair_16_epilogue_warps": res["pair16"], "all_bitwise_equal": ok,
                   "resident_cta_pairs": pair.pair_info()[0], "sm_count": torch.cuda.get_device_properties(0).multi_processor_count}), flush=True)
