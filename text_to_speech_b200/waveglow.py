@@ -13,22 +13,57 @@ from .runtime import build_runtime
 PAD_MEL_VALUE = -11.0   # models/tts/waveglow.py:29
 
 
-def _get_steps(length, win_len, hop_len):
-    """models/tts/waveglow.py:156-164."""
-    num_steps = int(math.ceil((length - win_len) / hop_len)) + 1
-    if num_steps == 1:
+def window_starts(n_frames, window, hop):
+    """First frame of every window: evenly spread so that the last one ends exactly at `n_frames`
+    (behaviour of `_get_steps`, models/tts/waveglow.py:156-164)."""
+    count = int(math.ceil((n_frames - window) / hop)) + 1
+    if count == 1:
         return [0]
-    max_step = length - win_len
-    actual_step_size = max_step / (num_steps - 1)
-    return np.round(np.arange(num_steps) * actual_step_size).astype(np.int32)
+    stride = (n_frames - window) / (count - 1)
+    return np.round(np.arange(count) * stride).astype(np.int32)
+
+
+_get_steps = window_starts      # the reference's name for it
 
 
 def _to_numpy(x):
     return x.detach().cpu().numpy() if hasattr(x, "detach") else np.asarray(x)
 
 
+def _window_length(n_frames, win_len, use_slice, max_win_len):
+    """A float `win_len` means "a multiple of this many frames": rounded up to cover the mel, or (use_slice) down to
+    whole slices; `max_win_len` caps either (waveglow.py:84-90)."""
+    if isinstance(win_len, float):
+        if use_slice:
+            win_len = max(1, n_frames // win_len) * int(win_len)
+        else:
+            win_len = int(math.ceil(n_frames / win_len) * win_len)
+    return win_len if max_win_len is None else min(max_win_len, win_len)
+
+
+def _stitch(pieces, starts, window, hop_samples=256):
+    """Joins per-window waveforms at the midpoints of their overlaps (waveglow.py:136-142)."""
+    overlap = ((starts[:-1] + window) - starts[1:]) * hop_samples
+    last = len(pieces) - 1
+    kept = []
+    for i, piece in enumerate(pieces):
+        head = overlap[i - 1] // 2 if i else 0
+        tail = -overlap[i] // 2 if i < last else None
+        kept.append(piece[head:tail])
+    return np.concatenate(kept, axis=-1)
+
+
 class WaveGlow:
-    """`WaveGlow(path=..., runtime='b200', mode='bf16')(mel, sigma=0.6, z=z)` -> waveform [B, 256*T]."""
+    """`WaveGlow(path=..., runtime='b200', mode='bf16')(mel, sigma=0.6, z=z)` -> waveform [B, 256*T].
+
+    Behaviour of `models.tts.WaveGlow.infer` (waveglow.py:61-144), case by case:
+      no `win_len`                 one call on the whole mel, trimmed to 256*T samples
+      mel not longer than a window one call; WITHOUT the caller's kwargs and untrimmed unless `force_pad` (the reference
+                                   pads only for the keras runtime, :95-96), else padded with `pad_mel_value` and trimmed
+      several utterances           one direct call, untrimmed (:108-112)
+      one long utterance           windows of `win_len` frames every `hop_len` (negative = overlap, float = fraction),
+                                   vocoded one by one or as one batch, stitched at the overlap midpoints
+    """
 
     def __init__(self, *, path, runtime="b200", pad_mel_value=PAD_MEL_VALUE, **runtime_kwargs):
         if runtime == "keras":
@@ -44,53 +79,34 @@ class WaveGlow:
 
     def infer(self, mel, *, win_len=None, hop_len=-64, force_pad=None, batch=False, use_slice=False,
               max_win_len=None, **kwargs):
-        if isinstance(mel, str):
-            mel = np.load(mel)
-        if len(mel.shape) == 2:
-            mel = mel[None]
-        seq_len = mel.shape[1]
-        audio_len = seq_len * 256
+        vocode = self.compiled_infer
+        mel = np.load(mel) if isinstance(mel, str) else mel
+        mel = mel[None] if len(mel.shape) == 2 else mel
+        n_frames = mel.shape[1]
+        n_samples = 256 * n_frames
         if win_len is None:
-            return self.compiled_infer(mel, **kwargs)[:, :audio_len]
+            return vocode(mel, **kwargs)[:, :n_samples]
 
-        if isinstance(win_len, float):
-            if not use_slice:
-                win_len = int(math.ceil(seq_len / win_len) * win_len)
-            else:
-                win_len = max(1, seq_len // win_len) * int(win_len)
-        if max_win_len is not None:
-            win_len = min(max_win_len, win_len)
-        kwargs['padding_multiple'] = win_len
+        window = _window_length(n_frames, win_len, use_slice, max_win_len)
+        kwargs["padding_multiple"] = window
+        if n_frames <= window:
+            pad = (self.runtime == "keras") if force_pad is None else force_pad
+            if not pad:
+                return vocode(mel)
+            extra = max(window, n_frames) - n_frames
+            padded = np.pad(_to_numpy(mel), [(0, 0), (0, extra), (0, 0)], constant_values=self.pad_mel_value)
+            return vocode(padded, **kwargs)[:, :n_samples]
+        if mel.shape[0] > 1:
+            return vocode(mel, **kwargs)
 
-        if seq_len <= win_len:
-            if force_pad is None:
-                force_pad = self.runtime == 'keras'
-            if not force_pad:
-                return self.compiled_infer(mel)     # reference drops kwargs here (waveglow.py:96)
-            win_len = max(win_len, seq_len)
-            mel_np = _to_numpy(mel)
-            padded = np.pad(mel_np, [(0, 0), (0, win_len - seq_len), (0, 0)], constant_values=self.pad_mel_value)
-            return self.compiled_infer(padded, **kwargs)[:, :audio_len]
-        elif mel.shape[0] > 1:
-            return self.compiled_infer(mel, **kwargs)
-
-        if isinstance(hop_len, float):
-            hop_len = int(win_len * hop_len)
-        if hop_len < 0:
-            hop_len = win_len + hop_len
-        starts = _get_steps(seq_len, win_len, hop_len)
-        parts = [mel[:, start: start + win_len] for start in starts]
-        overlaps = ((starts[:-1] + win_len) - starts[1:]) * 256
+        hop = int(window * hop_len) if isinstance(hop_len, float) else hop_len
+        hop = window + hop if hop < 0 else hop
+        starts = window_starts(n_frames, window, hop)
+        windows = [mel[:, s: s + window] for s in starts]
         if batch:
-            stacked = np.concatenate([_to_numpy(p) for p in parts], axis=0)
-            audio_parts = _to_numpy(self.compiled_infer(stacked, **kwargs))
+            pieces = _to_numpy(vocode(np.concatenate([_to_numpy(w) for w in windows], axis=0), **kwargs))
         else:
-            audio_parts = [_to_numpy(self.compiled_infer(p, **kwargs)[0]) for p in parts]
-        audio = []
-        for i, part in enumerate(audio_parts):
-            start = 0 if i == 0 else overlaps[i - 1] // 2
-            end = None if i == len(audio_parts) - 1 else -overlaps[i] // 2
-            audio.append(part[start:end])
-        return np.concatenate(audio, axis=-1)
+            pieces = [_to_numpy(vocode(w, **kwargs)[0]) for w in windows]
+        return _stitch(pieces, starts, window)
 
     __call__ = infer
