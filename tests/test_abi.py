@@ -40,6 +40,16 @@ def test_sass_is_blackwell_native(lib_built):
     for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG"):     # tcgen05.mma, tcgen05.ld, TMA
         assert mnemonic in sass, f"{mnemonic} missing from SASS"
     assert "HGMMA" not in sass
+    # per kernel: the BF16 layer kernels (single CTA and CTA pair), the WaveGlow-512 pair and the fp32-grade tf32x3 pair
+    # all issue tcgen05.mma (UTCHMMA) fed by TMA (UTMALDG) and read their accumulators with tcgen05.ld (LDTM)
+    bodies = {}
+    for chunk in sass.split("Function : ")[1:]:
+        bodies[chunk.split("\n", 1)[0].strip()] = chunk
+    for frag in ("tc_wn_layer_kernel", "tc_wn_pair_kernel", "tc512_gate_kernel", "tc512_res_kernel", "tf32_gate_kernel", "tf32_res_kernel"):
+        hits = [b for name, b in bodies.items() if frag in name]
+        assert hits, f"no kernel named *{frag}* in the library"
+        for b in hits:
+            assert "UTCHMMA" in b and "UTMALDG" in b and "LDTM" in b, f"{frag}: not a tcgen05/TMA kernel"
 
 
 def test_null_arguments_are_rejected(lib_built):

@@ -249,3 +249,40 @@ def test_pipelined_sweep_equals_the_plain_one(lib_built, tmp_path):
     mel, z = synthetic_inputs(1, 2, 8, hp)
     r = rt(torch.from_numpy(mel).cuda(), z=torch.from_numpy(z).cuda(), sigma=0.6, out=d)      # graph path + out=
     assert r.data_ptr() == d.data_ptr() and np.array_equal(d.cpu().numpy(), rt(mel, z=z, sigma=0.6))
+
+
+@pytest.mark.parametrize("C,mode,pair", [(256, "bf16", "0"), (256, "bf16", "1"), (256, "tf32x3", "0"), (512, "bf16", "0"), (256, "fp32", "0")])
+def test_no_write_outside_the_workspace_or_the_output(lib_built, monkeypatch, C, mode, pair):
+    """Canary check through the raw C ABI (compute-sanitizer is not available on this pool): the scratch the engine asks
+    for and the caller's waveform buffer sit between guard bands; after uniform and ragged infers on every kernel path
+    (single-CTA, CTA pair incl. a ghost tile, tf32x3, WaveGlow-512, FFMA) the bands must be untouched."""
+    monkeypatch.setenv("WG_PM", "1")
+    monkeypatch.setenv("WG_PAIR", pair)
+    hp = WaveGlowHParams(n_channels=C, n_flows=4 if C == 512 else 12)
+    eng = _engine(hp, generate_weights(hp, 7), mode)
+    lib, h = eng._lib, eng._h
+    B, T, lens = 3, 40, [40, 7, 33]
+    mel, z = synthetic_inputs(3, B, T, hp)
+    mel_d, z_d = torch.from_numpy(mel).cuda(), torch.from_numpy(z).cuda()
+    arr = (ctypes.c_int32 * B)(*lens)
+    n1, n2 = ctypes.c_size_t(), ctypes.c_size_t()
+    assert lib.wg_workspace_bytes(h, B, T, ctypes.byref(n1)) == 0
+    assert lib.wg_workspace_bytes_ragged(h, B, T, arr, ctypes.byref(n2)) == 0
+    G = 1 << 20
+    for ragged, need in ((False, n1.value), (True, n2.value)):
+        need_al = (need + 1023) // 1024 * 1024
+        ws = torch.full((G + need_al + G + 1024,), 0xA5, dtype=torch.uint8, device="cuda")
+        off = (-ws.data_ptr()) % 1024 + G
+        out = torch.full((G // 4 + B * T * 256 + G // 4,), 7.5, dtype=torch.float32, device="cuda")
+        out_ptr = out.data_ptr() + G
+        if ragged:
+            rc = lib.wg_infer_ragged(h, mel_d.data_ptr(), z_d.data_ptr(), 0.6, 0, B, T, arr, out_ptr, ws.data_ptr() + off, need, 0)
+        else:
+            rc = lib.wg_infer(h, mel_d.data_ptr(), z_d.data_ptr(), 0.6, 0, B, T, out_ptr, ws.data_ptr() + off, need, 0)
+        assert rc == 0, lib.wg_last_error(h)
+        torch.cuda.synchronize()
+        assert bool((ws[:off] == 0xA5).all()) and bool((ws[off + need_al:] == 0xA5).all()), "write outside the workspace"
+        assert bool((out[:G // 4] == 7.5).all()) and bool((out[G // 4 + B * T * 256:] == 7.5).all()), "write outside the waveform"
+        body = out[G // 4:G // 4 + B * T * 256]
+        assert bool(torch.isfinite(body).all()) and float(body.abs().max()) > 0
+    eng.close()

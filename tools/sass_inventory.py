@@ -12,6 +12,8 @@ COLS = ["UTCHMMA", "UTCBAR", "UTMALDG", "UTMASTG", "UTMAPF", "LDTM", "STTM", "SY
 LISTINGS = {   # demangled-name fragment -> file suffix
     "wg::tc_wn_layer_kernel<false, false>": "tc_wn_layer_kernel_0",
     "wg::tc_wn_layer_kernel<false, true>": "tc_wn_layer_kernel_first",
+    "wg::tc_wn_pair_kernel<false, false, 8>": "tc_wn_pair_kernel_0",
+    "wg::tf32_gate_kernel<false>": "tf32_gate_kernel_0",
     "wg::flow_boundary_kernel": "flow_boundary_kernel",
     "mel_frames_kernel": "mel_frames_kernel",
     "lstm_mma_kernel": "lstm_mma_kernel",
