@@ -105,6 +105,7 @@ struct wg_engine {
   int pair_max = 0;                       // CTA pairs that can be resident at once on this device (tc_pair_init)
   int last_pair = 0;                      // the last wg_infer ran its layers on the CTA-pair kernel
   int pair_epi_warps = 8;                 // WG_PAIR_EPI=16: 16 epilogue warps in the pair kernel
+  int t3_gate_bk = 16;                    // WG_TF32_BK=32: 2-stage SWIZZLE_128B ring in the tf32x3 gate kernel (A/B)
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;   // pairs: [2i] start, [2i+1] stop
   std::vector<int> ev_count;          // per pair: layer launches bracketed by it
@@ -385,7 +386,8 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
     tf32_prepare(plan3, e->sm_count, C, R, e->Kup, c.n_mel_channels, c.n_flows * c.n_layers, geo.rows_per_phase(), geo1,
                  rg ? 0 : geo.Tp, geo.T, e->t3, t3_hhi[0], t3_hhi[1], t3_hlo[0], t3_hlo[1],
                  reinterpret_cast<float*>(base + w.t3_chi), reinterpret_cast<float*>(base + w.t3_clo),
-                 reinterpret_cast<float*>(base + w.t3_ahi), reinterpret_cast<float*>(base + w.t3_alo), acc8, t3_acc_stride);
+                 reinterpret_cast<float*>(base + w.t3_ahi), reinterpret_cast<float*>(base + w.t3_alo), acc8, t3_acc_stride,
+                 e->t3_gate_bk);
     e->launches += tf32_upsample(plan3, mel, st);
   } else if (ffma) {
     GemmArgs g{};
@@ -877,6 +879,7 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
     e->t3.W2h = upload(e, t3w2h); e->t3.W2l = upload(e, t3w2l);
     tc_init();
     tf32_init();
+    if (const char* bk = std::getenv("WG_TF32_BK")) e->t3_gate_bk = std::atoi(bk) == 32 ? 32 : 16;
     // folded conditioning weights as an fp32 (hi, lo) pair: V[(layer*R + r)*2C + n][k] = sum_s Wup_r[k][s] * Wcond[s][n]
     const int Kw = e->Kup;
     float *d_wup = nullptr, *d_wc = nullptr, *d_tmp = nullptr, *vh = nullptr, *vl = nullptr;

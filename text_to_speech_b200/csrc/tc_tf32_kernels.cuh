@@ -11,14 +11,15 @@
 //
 // Two kernels per layer (the fp32 acts tile, 128 x C x 2 x 4 B, does not fit beside the operand ring):
 //   tf32_gate_kernel   item = (128-row tile, 256-column chunk q of the gate pre-activation = 128 tanh + 128 sigmoid
-//                      channels).  GEMM1 [128 x (3C + 320)] @ [(3C + 320) x 256], K-blocks of 32 floats (128-byte
-//                      swizzled rows), 2-stage TMA ring of {A_hi, A_lo, B_hi, B_lo} = 96 KB, 12 MMAs per stage;
+//                      channels).  GEMM1 [128 x (3C + 320)] @ [(3C + 320) x 256], K-blocks of 16 floats (64-byte
+//                      swizzled rows), 4-stage TMA ring of {A_hi, A_lo, B_hi, B_lo} = 48 KB, 6 MMAs per stage
+//                      (WG_TF32_BK=32: K-blocks of 32 floats, 2 stages of 96 KB -- measured 7.5 % slower at K1);
 //                      epilogue: gate, acts -> (hi, lo) in HBM, skip/end fold into this chunk's OWN partial
 //                      accumulator acc8[q] (no cross-CTA race: the flow boundary sums the partials in a fixed order).
 //   tf32_res_kernel    item = (128-row tile, 128-column chunk of the residual half).  GEMM2 acts[128 x C] @ Wres,
 //                      3-stage ring of 64 KB; epilogue: h = acc + b + (h_hi + h_lo) -> (hi, lo) for the next layer.
 // Both are persistent (static schedule) with a double-buffered TMEM accumulator so the epilogue of one item overlaps
-// the MMAs of the next. K1 (1 x 200 frames) has 50 tiles -> 100 items: one item per CTA on 100 of the 148 SMs.
+// the MMAs of the next. K1 (1 x 200 frames) is 32 phases x 2 tiles = 64 tiles -> 128 gate items: one item per CTA, one wave.
 #pragma once
 #include "tc_kernels.cuh"
 
@@ -57,14 +58,37 @@ __host__ __device__ inline float tf32_rna_host(float x) {   // same rounding on 
 constexpr int T3_BM = 128, T3_BK = 32;                 // 32 floats = one 128-byte swizzle row
 constexpr int T3_A_BYTES = T3_BM * T3_BK * 4;          // 16 KB
 constexpr int T3_EPI_WARPS = 8, T3_EPI_THREADS = T3_EPI_WARPS * 32, T3_THREADS = 64 + T3_EPI_THREADS;
-// gate kernel: N = 256 per item
-constexpr int T3G_BN = 256, T3G_B_BYTES = T3G_BN * T3_BK * 4;                 // 32 KB
-constexpr int T3G_STAGES = 2, T3G_STAGE_BYTES = 2 * T3_A_BYTES + 2 * T3G_B_BYTES;   // 96 KB
-constexpr int T3G_OFF_B1 = T3G_STAGES * T3G_STAGE_BYTES;
-constexpr int T3G_OFF_O8 = T3G_OFF_B1 + 256 * 4;
-constexpr int T3G_OFF_BARS = T3G_OFF_O8 + T3_BM * 8 * 4;
-constexpr int T3G_NBARS = 2 * T3G_STAGES + 4;
-constexpr int T3G_SMEM = T3G_OFF_BARS + T3G_NBARS * 8 + 16;
+// gate kernel: N = 256 per item. K-block width BK floats per stage: 32 (one 128-byte swizzle row, 2 stages of 96 KB) or
+// 16 (64-byte swizzle rows, 4 stages of 48 KB): the same 192 KB ring in finer slices keeps more bytes in flight while the
+// MMA works on a stage -- the kernel is bound by the latency of its operand feed (8 B per operand element for the fp32 pairs).
+constexpr int T3G_BN = 256;
+template <int BK>
+struct T3G {
+  static_assert(BK == 32 || BK == 16, "K-block of 32 floats (SWIZZLE_128B) or 16 floats (SWIZZLE_64B)");
+  static constexpr int A_BYTES = T3_BM * BK * 4, B_BYTES = T3G_BN * BK * 4;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;                // 96 KB / 48 KB
+  static constexpr int STAGES = BK == 32 ? 2 : 4;
+  static constexpr int OFF_B1 = STAGES * STAGE_BYTES;
+  static constexpr int OFF_O8 = OFF_B1 + 256 * 4;
+  static constexpr int OFF_BARS = OFF_O8 + T3_BM * 8 * 4;
+  static constexpr int NBARS = 2 * STAGES + 4;
+  static constexpr int SMEM = OFF_BARS + NBARS * 8 + 16;
+  static_assert(SMEM <= 232448, "shared memory budget");
+};
+// K-major SWIZZLE_64B shared-memory matrix descriptor: 8-row groups of 64-byte rows (SBO = 512 B), layout type 4
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;
+  return d;
+}
+template <int BK>
+__device__ __forceinline__ uint64_t t3_desc(uint32_t smem_addr) {
+  return BK == 32 ? umma_desc_sw128(smem_addr) : umma_desc_sw64(smem_addr);
+}
 // residual kernel: N = 128 per item
 constexpr int T3R_BN = 128, T3R_B_BYTES = T3R_BN * T3_BK * 4;                 // 16 KB
 constexpr int T3R_STAGES = 3, T3R_STAGE_BYTES = 2 * T3_A_BYTES + 2 * T3R_B_BYTES;   // 64 KB
@@ -72,7 +96,7 @@ constexpr int T3R_OFF_B2 = T3R_STAGES * T3R_STAGE_BYTES;
 constexpr int T3R_OFF_BARS = T3R_OFF_B2 + T3R_BN * 4;
 constexpr int T3R_NBARS = 2 * T3R_STAGES + 4;
 constexpr int T3R_SMEM = T3R_OFF_BARS + T3R_NBARS * 8 + 16;
-static_assert(T3G_SMEM <= 232448 && T3R_SMEM <= 232448, "shared memory budget");
+static_assert(T3R_SMEM <= 232448, "shared memory budget");
 
 struct Tf32Params {
   int T, R, tiles_per_row, n_tiles;   // phase-block rows, phases, 128-row tiles per phase block, tiles in all
@@ -110,13 +134,16 @@ __device__ __forceinline__ void t3_item_coords(const Tf32Params& p, int item, in
   t0 = (tile / p.R) * T3_BM;
 }
 
-template <bool LAST>
+template <bool LAST, int BK = 32>
 __global__ void __launch_bounds__(T3_THREADS, 1)
 tf32_gate_kernel(const __grid_constant__ CUtensorMap map_hh, const __grid_constant__ CUtensorMap map_hl,
                  const __grid_constant__ CUtensorMap map_ch, const __grid_constant__ CUtensorMap map_cl,
                  const __grid_constant__ CUtensorMap map_w1h, const __grid_constant__ CUtensorMap map_w1l,
                  const __grid_constant__ CUtensorMap map_vh, const __grid_constant__ CUtensorMap map_vl,
                  const Tf32Params p) {
+  using G = T3G<BK>;
+  constexpr int T3G_STAGES = G::STAGES, T3G_STAGE_BYTES = G::STAGE_BYTES, T3G_B_BYTES = G::B_BYTES, T3G_A_BYTES = G::A_BYTES;
+  constexpr int T3G_OFF_B1 = G::OFF_B1, T3G_OFF_O8 = G::OFF_O8, T3G_OFF_BARS = G::OFF_BARS, T3G_NBARS = G::NBARS;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
   float* s_b1 = reinterpret_cast<float*>(smem + T3G_OFF_B1);
@@ -154,7 +181,7 @@ tf32_gate_kernel(const __grid_constant__ CUtensorMap map_hh, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
   const int n_items = p.n_tiles * p.n_chunks;
   const int kb1 = p.kb_conv + p.kb_cond;
-  const int cblks = p.C / T3_BK;   // K-blocks per tap
+  const int cblks = p.C / BK;   // K-blocks per tap
 
   if (warp == 0) {
     // ===================================== TMA producer ======================================
@@ -167,23 +194,23 @@ tf32_gate_kernel(const __grid_constant__ CUtensorMap map_hh, const __grid_consta
         mbar_wait(empty_bar(s), ((it / T3G_STAGES) & 1) ^ 1);
         if (elect_one()) {
           mbar_expect_tx(full_bar(s), T3G_STAGE_BYTES);
-          const uint32_t a_hi = smem_base + s * T3G_STAGE_BYTES, a_lo = a_hi + T3_A_BYTES;
-          const uint32_t b_hi = a_lo + T3_A_BYTES, b_lo = b_hi + T3G_B_BYTES;
+          const uint32_t a_hi = smem_base + s * T3G_STAGE_BYTES, a_lo = a_hi + T3G_A_BYTES;
+          const uint32_t b_hi = a_lo + T3G_A_BYTES, b_lo = b_hi + T3G_B_BYTES;
           if (kb < p.kb_conv) {
             // tap shifted by (tap-1)*dilation positions: phase (r+sh) mod R, frames moved by floor((r+sh)/R)
             const int tap = kb / cblks, cblk = kb - tap * cblks;
             const int rs = r + (tap - 1) * p.dilation;
             const int carry = (rs >= 0) ? rs / p.R : -((-rs + p.R - 1) / p.R);
-            tma_load_4d(a_hi, &map_hh, full_bar(s), cblk * T3_BK, t0 + carry, rs - carry * p.R, 0);
-            tma_load_4d(a_lo, &map_hl, full_bar(s), cblk * T3_BK, t0 + carry, rs - carry * p.R, 0);
-            tma_load_2d(b_hi, &map_w1h, full_bar(s), kb * T3_BK, p.layer * 2 * p.C + q * T3G_BN);
-            tma_load_2d(b_lo, &map_w1l, full_bar(s), kb * T3_BK, p.layer * 2 * p.C + q * T3G_BN);
+            tma_load_4d(a_hi, &map_hh, full_bar(s), cblk * BK, t0 + carry, rs - carry * p.R, 0);
+            tma_load_4d(a_lo, &map_hl, full_bar(s), cblk * BK, t0 + carry, rs - carry * p.R, 0);
+            tma_load_2d(b_hi, &map_w1h, full_bar(s), kb * BK, p.layer * 2 * p.C + q * T3G_BN);
+            tma_load_2d(b_lo, &map_w1l, full_bar(s), kb * BK, p.layer * 2 * p.C + q * T3G_BN);
           } else {
             const int kc = kb - p.kb_conv;
-            tma_load_4d(a_hi, &map_ch, full_bar(s), kc * T3_BK, t0, 0, 0);
-            tma_load_4d(a_lo, &map_cl, full_bar(s), kc * T3_BK, t0, 0, 0);
-            tma_load_2d(b_hi, &map_vh, full_bar(s), kc * T3_BK, p.wc_row0 + r * p.wc_rstride + q * T3G_BN);
-            tma_load_2d(b_lo, &map_vl, full_bar(s), kc * T3_BK, p.wc_row0 + r * p.wc_rstride + q * T3G_BN);
+            tma_load_4d(a_hi, &map_ch, full_bar(s), kc * BK, t0, 0, 0);
+            tma_load_4d(a_lo, &map_cl, full_bar(s), kc * BK, t0, 0, 0);
+            tma_load_2d(b_hi, &map_vh, full_bar(s), kc * BK, p.wc_row0 + r * p.wc_rstride + q * T3G_BN);
+            tma_load_2d(b_lo, &map_vl, full_bar(s), kc * BK, p.wc_row0 + r * p.wc_rstride + q * T3G_BN);
           }
         }
         __syncwarp();
@@ -203,16 +230,16 @@ tf32_gate_kernel(const __grid_constant__ CUtensorMap map_hh, const __grid_consta
         mbar_wait(full_bar(s), (it / T3G_STAGES) & 1);
         tc_fence_after();
         const uint32_t base = smem_base + s * T3G_STAGE_BYTES;
-        const uint64_t ahi = umma_desc_sw128(base), alo = umma_desc_sw128(base + T3_A_BYTES);
-        const uint64_t bhi = umma_desc_sw128(base + 2 * T3_A_BYTES), blo = umma_desc_sw128(base + 2 * T3_A_BYTES + T3G_B_BYTES);
+        const uint64_t ahi = t3_desc<BK>(base), alo = t3_desc<BK>(base + T3G_A_BYTES);
+        const uint64_t bhi = t3_desc<BK>(base + 2 * T3G_A_BYTES), blo = t3_desc<BK>(base + 2 * T3G_A_BYTES + T3G_B_BYTES);
         if (elect_one()) {
           // small cross terms first, then the main product (K = 8 floats = 32 bytes per instruction: +2 in the descriptor)
 #pragma unroll
-          for (int k = 0; k < T3_BK / 8; ++k) umma_tf32(d_tmem, alo + 2 * k, bhi + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < BK / 8; ++k) umma_tf32(d_tmem, alo + 2 * k, bhi + 2 * k, idesc, (kb | k) ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < T3_BK / 8; ++k) umma_tf32(d_tmem, ahi + 2 * k, blo + 2 * k, idesc, 1u);
+          for (int k = 0; k < BK / 8; ++k) umma_tf32(d_tmem, ahi + 2 * k, blo + 2 * k, idesc, 1u);
 #pragma unroll
-          for (int k = 0; k < T3_BK / 8; ++k) umma_tf32(d_tmem, ahi + 2 * k, bhi + 2 * k, idesc, 1u);
+          for (int k = 0; k < BK / 8; ++k) umma_tf32(d_tmem, ahi + 2 * k, bhi + 2 * k, idesc, 1u);
           tc_commit(empty_bar(s));
           if (kb == kb1 - 1) tc_commit(accfull_bar(as));
         }
@@ -497,6 +524,7 @@ __global__ void fold_store_tf32_kernel(const float* __restrict__ in, float* __re
 
 // ---- host side --------------------------------------------------------------------------------------------------
 inline void make_map_f32(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint32_t* box) {
+  const CUtensorMapSwizzle swz = box[0] == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;   // 64- or 128-byte rows
   cuuint64_t gdim[4], gstr[3];
   cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
   uint64_t stride = 4;
@@ -507,24 +535,26 @@ inline void make_map_f32(CUtensorMap* m, const void* ptr, int rank, const uint64
     if (i < rank - 1) gstr[i] = stride;
   }
   CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) fail(WG_ERR_CUDA, "cuTensorMapEncodeTiled (fp32) failed with CUresult %d", (int)r);
 }
-inline void make_map_f32_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+inline void make_map_f32_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, int bk = T3_BK) {
   const uint64_t dims[2] = {cols, rows};
-  const uint32_t box[2] = {T3_BK, box_rows};
+  const uint32_t box[2] = {(uint32_t)bk, box_rows};
   make_map_f32(m, ptr, 2, dims, box);
 }
-inline void make_map_f32_4d(CUtensorMap* m, const void* ptr, uint64_t phases, uint64_t rows, uint64_t cols) {
+inline void make_map_f32_4d(CUtensorMap* m, const void* ptr, uint64_t phases, uint64_t rows, uint64_t cols, int bk = T3_BK) {
   const uint64_t dims[4] = {cols, rows, phases, 1};
-  const uint32_t box[4] = {T3_BK, T3_BM, 1, 1};
+  const uint32_t box[4] = {(uint32_t)bk, T3_BM, 1, 1};
   make_map_f32(m, ptr, 4, dims, box);
 }
 
 inline void tf32_init() {
-  WG_CK(cudaFuncSetAttribute(tf32_gate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3G_SMEM));
-  WG_CK(cudaFuncSetAttribute(tf32_gate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3G_SMEM));
+  WG_CK(cudaFuncSetAttribute(tf32_gate_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3G<32>::SMEM));
+  WG_CK(cudaFuncSetAttribute(tf32_gate_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3G<32>::SMEM));
+  WG_CK(cudaFuncSetAttribute(tf32_gate_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3G<16>::SMEM));
+  WG_CK(cudaFuncSetAttribute(tf32_gate_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3G<16>::SMEM));
   WG_CK(cudaFuncSetAttribute(tf32_res_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T3R_SMEM));
 }
 
@@ -533,6 +563,7 @@ struct Tf32Plan {
   Tf32Params base{};
   RowGeom geo1{};
   int sm_count = 0, n_mel = 0, Kup = 0;
+  int gate_bk = 16;      // K-block width of the gate kernel (WG_TF32_BK=32 selects the 2-stage SWIZZLE_128B variant)
   float *h_hi[2] = {nullptr, nullptr}, *h_lo[2] = {nullptr, nullptr}, *aup_hi = nullptr, *aup_lo = nullptr;
 };
 
@@ -546,8 +577,10 @@ struct Tf32Weights {   // device pointers, stacked over all layers
 inline void tf32_prepare(Tf32Plan& pl, int sm_count, int C, int R, int Kup, int n_mel, int n_layers_total, int rows1,
                          const RowGeom& geo1, int Tp, int Tv, const Tf32Weights& w, float* h_hi0, float* h_hi1,
                          float* h_lo0, float* h_lo1, float* aup_hi, float* aup_lo, float* acts_hi, float* acts_lo,
-                         float* acc8, size_t acc8_stride) {
+                         float* acc8, size_t acc8_stride, int gate_bk = 16) {
   if (C % 128 || Kup % T3_BK) fail(WG_ERR_UNSUPPORTED, "tf32x3 path needs n_channels %% 128 == 0 (got %d)", C);
+  pl.gate_bk = gate_bk == 32 ? 32 : 16;
+  const int gbk = pl.gate_bk;
   pl.sm_count = sm_count; pl.n_mel = n_mel; pl.Kup = Kup; pl.geo1 = geo1;
   pl.h_hi[0] = h_hi0; pl.h_hi[1] = h_hi1; pl.h_lo[0] = h_lo0; pl.h_lo[1] = h_lo1; pl.aup_hi = aup_hi; pl.aup_lo = aup_lo;
   Tf32Params& p = pl.base;
@@ -555,17 +588,17 @@ inline void tf32_prepare(Tf32Plan& pl, int sm_count, int C, int R, int Kup, int 
   p.C = C; p.Tp = Tp; p.Tv = Tv; p.row_b = geo1.row_b;
   p.acts_hi = acts_hi; p.acts_lo = acts_lo; p.acc8 = acc8; p.acc8_stride = acc8_stride;
   for (int i = 0; i < 2; ++i) {
-    make_map_f32_4d(&pl.m_h_hi[i], pl.h_hi[i], R, rows1, C);
-    make_map_f32_4d(&pl.m_h_lo[i], pl.h_lo[i], R, rows1, C);
+    make_map_f32_4d(&pl.m_h_hi[i], pl.h_hi[i], R, rows1, C, gbk);
+    make_map_f32_4d(&pl.m_h_lo[i], pl.h_lo[i], R, rows1, C, gbk);
   }
-  make_map_f32_4d(&pl.m_c_hi, aup_hi, 1, rows1, Kup);
-  make_map_f32_4d(&pl.m_c_lo, aup_lo, 1, rows1, Kup);
+  make_map_f32_4d(&pl.m_c_hi, aup_hi, 1, rows1, Kup, gbk);
+  make_map_f32_4d(&pl.m_c_lo, aup_lo, 1, rows1, Kup, gbk);
   make_map_f32_4d(&pl.m_a_hi, acts_hi, R, rows1, C);
   make_map_f32_4d(&pl.m_a_lo, acts_lo, R, rows1, C);
-  make_map_f32_2d(&pl.m_w1h, w.W1h, (uint64_t)n_layers_total * 2 * C, 3 * C, T3G_BN);
-  make_map_f32_2d(&pl.m_w1l, w.W1l, (uint64_t)n_layers_total * 2 * C, 3 * C, T3G_BN);
-  make_map_f32_2d(&pl.m_vh, w.Vh, (uint64_t)n_layers_total * R * 2 * C, Kup, T3G_BN);
-  make_map_f32_2d(&pl.m_vl, w.Vl, (uint64_t)n_layers_total * R * 2 * C, Kup, T3G_BN);
+  make_map_f32_2d(&pl.m_w1h, w.W1h, (uint64_t)n_layers_total * 2 * C, 3 * C, T3G_BN, gbk);
+  make_map_f32_2d(&pl.m_w1l, w.W1l, (uint64_t)n_layers_total * 2 * C, 3 * C, T3G_BN, gbk);
+  make_map_f32_2d(&pl.m_vh, w.Vh, (uint64_t)n_layers_total * R * 2 * C, Kup, T3G_BN, gbk);
+  make_map_f32_2d(&pl.m_vl, w.Vl, (uint64_t)n_layers_total * R * 2 * C, Kup, T3G_BN, gbk);
   make_map_f32_2d(&pl.m_w2h, w.W2h, (uint64_t)n_layers_total * C, C, T3R_BN);
   make_map_f32_2d(&pl.m_w2l, w.W2l, (uint64_t)n_layers_total * C, C, T3R_BN);
 }
@@ -582,17 +615,22 @@ inline int tf32_wn_layer(const Tf32Plan& pl, int layer, int dilation, bool last,
                          const float* wse, cudaStream_t st) {
   Tf32Params g = pl.base;
   g.layer = layer; g.dilation = dilation;
-  g.n_chunks = 2 * g.C / T3G_BN; g.kb_conv = 3 * g.C / T3_BK; g.kb_cond = pl.Kup / T3_BK;
+  g.n_chunks = 2 * g.C / T3G_BN; g.kb_conv = 3 * g.C / pl.gate_bk; g.kb_cond = pl.Kup / pl.gate_bk;
   g.wc_row0 = layer * g.R * 2 * g.C; g.wc_rstride = 2 * g.C;
   g.bias = b1; g.wse = wse;
   const int items_g = g.n_tiles * g.n_chunks;
   const int grid_g = items_g < pl.sm_count ? items_g : pl.sm_count;
-  if (last)
-    tf32_gate_kernel<true><<<grid_g, T3_THREADS, T3G_SMEM, st>>>(pl.m_h_hi[hcur], pl.m_h_lo[hcur], pl.m_c_hi, pl.m_c_lo,
-                                                                 pl.m_w1h, pl.m_w1l, pl.m_vh, pl.m_vl, g);
-  else
-    tf32_gate_kernel<false><<<grid_g, T3_THREADS, T3G_SMEM, st>>>(pl.m_h_hi[hcur], pl.m_h_lo[hcur], pl.m_c_hi, pl.m_c_lo,
-                                                                  pl.m_w1h, pl.m_w1l, pl.m_vh, pl.m_vl, g);
+#define WG_T3G_LAUNCH(LASTV, BKV)                                                                                          \
+  tf32_gate_kernel<LASTV, BKV><<<grid_g, T3_THREADS, T3G<BKV>::SMEM, st>>>(pl.m_h_hi[hcur], pl.m_h_lo[hcur], pl.m_c_hi, pl.m_c_lo, \
+                                                                           pl.m_w1h, pl.m_w1l, pl.m_vh, pl.m_vl, g)
+  if (pl.gate_bk == 32) {
+    if (last) WG_T3G_LAUNCH(true, 32);
+    else WG_T3G_LAUNCH(false, 32);
+  } else {
+    if (last) WG_T3G_LAUNCH(true, 16);
+    else WG_T3G_LAUNCH(false, 16);
+  }
+#undef WG_T3G_LAUNCH
   WG_CK(cudaGetLastError());
   if (last) return 1;
   Tf32Params r = pl.base;
