@@ -7,7 +7,8 @@ channels-last, op for op in the reference's order:
   architectures/waveglow_arch.py:105-141   WaveglowBlock.call              -> wn_block()
   architectures/waveglow_arch.py:244-306   WaveGlow.infer                  -> infer()
   architectures/layers/invertible_conv.py:41-51  build_inverse / call(reverse=True) -> w_inverse(), infer()
-  models/tts/waveglow.py:61-142, 156-164   wrapper glue / windowing        -> wrapper_infer(), get_steps()
+  models/tts/waveglow.py:61-142, 156-164   wrapper glue / windowing        -> not restated: pinned by the reference's own source
+                                           (oracle/run_reference_wrapper.py) and its golden outputs (oracle/gen_golden_wrapper.py)
 
 The arithmetic itself lives in Keras 3 (un-vendored, un-pinned third party: `keras` on a
 tensorflow/torch/jax backend; not even listed in the reference's requirements.txt). Keras layer
@@ -173,64 +174,6 @@ class OracleWaveGlow:
         return audio.reshape(B, -1)
 
     __call__ = infer
-
-
-# -- models/tts/waveglow.py:156-164 -------------------------------------------------------------
-def get_steps(length, win_len, hop_len):
-    num_steps = int(math.ceil((length - win_len) / hop_len)) + 1
-    if num_steps == 1:
-        return [0]
-    max_step = length - win_len
-    actual = max_step / (num_steps - 1)
-    return np.round(np.arange(num_steps) * actual).astype(np.int32)
-
-
-def wrapper_infer(engine, mel, *, win_len=None, hop_len=-64, force_pad=None, batch=False,
-                  use_slice=False, max_win_len=None, pad_mel_value=-11.0, runtime="b200", **kwargs):
-    """models/tts/waveglow.py:61-142 restated over any callable ``engine(mel, **kw) -> [B, 256 T]``
-    (numpy in / numpy out). Used to check the product wrapper's windowing/stitching."""
-    mel = np.asarray(mel, dtype=np.float32)
-    if mel.ndim == 2:
-        mel = mel[None]
-    seq_len = mel.shape[1]
-    audio_len = seq_len * 256
-    if win_len is None:
-        return np.asarray(engine(mel, **kwargs))[:, :audio_len]
-    if isinstance(win_len, float):
-        if not use_slice:
-            win_len = int(math.ceil(seq_len / win_len) * win_len)
-        else:
-            win_len = max(1, seq_len // win_len) * int(win_len)
-    if max_win_len is not None:
-        win_len = min(max_win_len, win_len)
-    kwargs["padding_multiple"] = win_len
-    if seq_len <= win_len:
-        if force_pad is None:
-            force_pad = runtime == "keras"
-        if not force_pad:
-            return np.asarray(engine(mel))
-        win_len = max(win_len, seq_len)
-        padded = np.pad(mel, [(0, 0), (0, win_len - seq_len), (0, 0)], constant_values=pad_mel_value)
-        return np.asarray(engine(padded, **kwargs))[:, :audio_len]
-    elif mel.shape[0] > 1:
-        return np.asarray(engine(mel, **kwargs))
-    if isinstance(hop_len, float):
-        hop_len = int(win_len * hop_len)
-    if hop_len < 0:
-        hop_len = win_len + hop_len
-    starts = get_steps(seq_len, win_len, hop_len)
-    parts = [mel[:, s: s + win_len] for s in starts]
-    overlaps = ((starts[:-1] + win_len) - starts[1:]) * 256
-    if batch:
-        audio_parts = np.asarray(engine(np.concatenate(parts, axis=0), **kwargs))
-    else:
-        audio_parts = [np.asarray(engine(p, **kwargs))[0] for p in parts]
-    audio = []
-    for i, part in enumerate(audio_parts):
-        start = 0 if i == 0 else overlaps[i - 1] // 2
-        end = None if i == len(audio_parts) - 1 else -overlaps[i] // 2
-        audio.append(part[start:end])
-    return np.concatenate(audio, axis=-1)
 
 
 # -- independent second implementation (NVIDIA channels-first formulation via torch conv ops) ----

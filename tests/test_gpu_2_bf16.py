@@ -274,14 +274,16 @@ def test_runtime_plugin_end_to_end(lib_built, tmp_path):
     # device-resident call returns a CUDA tensor
     d = voc.model(torch.from_numpy(mel).cuda(), z=torch.from_numpy(z).cuda(), sigma=0.6)
     assert d.is_cuda and np.abs(d.cpu().numpy() - ref).max() <= TOL_BF16_ABS
-    # windowed inference, stitched exactly like models/tts/waveglow.py:114-142
-    from oracle.waveglow_oracle import wrapper_infer
+    # windowed inference: the SAME wrapper (pinned to the reference's wrapper source by tests/test_host_logic.py) over the
+    # B200 fp32 runtime and over a CPU-oracle vocoder -- windows, per-window calls and stitching included
     fp = WaveGlow(path=path, runtime="b200", mode="fp32")
     long_mel, _ = synthetic_inputs(12, 1, 100, hp)
     got = fp(long_mel, win_len=64, hop_len=-16, deterministic=True)
-    want = wrapper_infer(lambda m, **kw: OracleWaveGlow(hp, w)(m, None, kw.get("sigma", 1.0), deterministic=True).numpy(),
-                         long_mel, win_len=64, hop_len=-16, deterministic=True)
-    assert got.shape == want.shape and np.abs(got - want).max() <= 1e-4
+    cpu = WaveGlow.__new__(WaveGlow)
+    cpu.runtime, cpu.pad_mel_value = "b200", -11.0
+    cpu.model = lambda m, **kw: OracleWaveGlow(hp, w)(np.asarray(m), None, kw.get("sigma", 1.0), deterministic=True).numpy()
+    want = cpu(long_mel, win_len=64, hop_len=-16, deterministic=True)
+    assert got.shape == want.shape == (1, 100 * 256) and np.abs(got - want).max() <= 1e-4
 
 
 def test_wg_infer_is_cuda_graph_capturable(lib_built):
