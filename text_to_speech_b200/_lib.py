@@ -11,7 +11,8 @@ import shutil
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwg_b200.so")
+# WG_LIB_PATH: load another build of the library (development: a -DWG_PROBES build made with tools/build_probes.sh)
+LIB_PATH = os.environ.get("WG_LIB_PATH") or os.path.join(_HERE, "libwg_b200.so")
 SOURCES = [os.path.join(_HERE, "csrc", "engine.cu"), os.path.join(_HERE, "csrc", "mel.cu"),
            os.path.join(_HERE, "csrc", "taco.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", f) for f in ("common.cuh", "simt_kernels.cuh", "tc_kernels.cuh", "tc_pair_kernels.cuh", "tc_c512_kernels.cuh", "tc_tf32_kernels.cuh")] + \
@@ -58,10 +59,10 @@ class WgTensor(ctypes.Structure):
                 ("ndim", ctypes.c_int32), ("shape", ctypes.c_int64 * 4)]
 
 
-def nvcc_command(out=LIB_PATH):
+def nvcc_command(out=LIB_PATH, extra=()):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-            "-Xcompiler", "-fPIC", "-shared", "-o", out] + SOURCES
+            "-Xcompiler", "-fPIC", "-shared", *extra, "-o", out] + SOURCES
 
 
 def needs_build():

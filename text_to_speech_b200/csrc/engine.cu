@@ -511,10 +511,11 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
         if (C == 512)
           e->launches += tc512_wn_layer(plan, m_acts512, k * c.n_layers + i, d, last, hcur, acc8, pm ? lw.b1_pm : lw.b1,
                                         lw.b2, lw.wse_p.data(), st, fold0 && i == 0);
-        else if (pmaps.ready && !(fold0 && i == 0) && (e->last_pair = 1))   // FIRST layers: the single-CTA kernel is faster (348 vs 370 us)
+        else if (pmaps.ready && !(fold0 && i == 0 && e->pair_epi_warps == 8)) {   // FIRST layers: the single-CTA kernel is faster (348 vs 370 us)
+          e->last_pair = 1;
           e->launches += tc_wn_layer_pair(plan, pmaps, k * c.n_layers + i, d, last, hcur, acc8, lw.b1_pm, lw.b2,
                                           lw.wse_p.data(), st, fold0 && i == 0, e->timing, e->pair_epi_warps);
-        else
+        } else
           e->launches += tc_wn_layer(plan, k * c.n_layers + i, d, last, hcur, acc8, pm ? lw.b1_pm : lw.b1, lw.b2,
                                      lw.wse_p.data(), e->timing, e->dbg_flags, st, fold0 && i == 0);
         if (last || (k == stop_flow && i == stop_layer)) prof_mark();
