@@ -15,20 +15,30 @@ from text_to_speech_b200.weights import WaveGlowHParams, generate_weights, synth
 n_wg = int(sys.argv[1]) if len(sys.argv) > 1 else 300
 n_taco = int(sys.argv[2]) if len(sys.argv) > 2 else 100
 hp = WaveGlowHParams()
-eng = WaveGlowEngine(hp, generate_weights(hp, 1234), mode="bf16", device=0)
+weights = generate_weights(hp, 1234)
 bad = 0
-for B, T in ((16, 860), (3, 333), (1, 37)):
-    mel, z = synthetic_inputs(1, B, T, hp)
-    mel_d, z_d = torch.from_numpy(mel).cuda(), torch.from_numpy(z).cuda()
-    ref = eng.infer_device(mel_d, z_d, 0.6).clone()
-    n = n_wg if B == 16 else 3 * n_wg
-    for i in range(n):
-        out = eng.infer_device(mel_d, z_d, 0.6)
-        if not torch.equal(out, ref):
-            bad += 1
-            print(f"WaveGlow {B}x{T}: run {i} differs, max {float((out - ref).abs().max()):.3e}")
-    torch.cuda.synchronize()
-    print(f"WaveGlow {B}x{T}: {n} runs, finite {bool(torch.isfinite(ref).all())}")
+# (engine mode, WG_PAIR, shapes): the BF16 layer kernel as the engine picks it (CTA pairs for the big batch), the single-CTA
+# kernel forced, a ragged batch on either, and the tf32x3 kernels
+for mode, pair, cases in (("bf16", "-1", ((16, 860, None), (3, 333, None), (1, 37, None), (12, 300, "ragged"))),
+                          ("bf16", "0", ((16, 860, None), (12, 300, "ragged"))),
+                          ("tf32x3", "-1", ((2, 150, None), (5, 90, "ragged")))):
+    os.environ["WG_PAIR"] = pair
+    eng = WaveGlowEngine(hp, weights, mode=mode, device=0)
+    for B, T, ragged in cases:
+        mel, z = synthetic_inputs(1, B, T, hp)
+        lengths = [max(1, T - 23 * b) for b in range(B)] if ragged else None
+        mel_d, z_d = torch.from_numpy(mel).cuda(), torch.from_numpy(z).cuda()
+        ref = eng.infer_device(mel_d, z_d, 0.6, lengths=lengths).clone()
+        n = (n_wg if B * T > 5000 else 3 * n_wg) // (1 if mode == "bf16" else 6)
+        for i in range(n):
+            out = eng.infer_device(mel_d, z_d, 0.6, lengths=lengths)
+            if not torch.equal(out, ref):
+                bad += 1
+                print(f"WaveGlow {mode} {B}x{T}: run {i} differs, max {float((out - ref).abs().max()):.3e}")
+        torch.cuda.synchronize()
+        print(f"WaveGlow {mode} WG_PAIR={pair} {B}x{T}{' ragged' if ragged else ''}: {n} runs, pair kernel {eng.pair_info()[1]}, "
+              f"finite {bool(torch.isfinite(ref).all())}", flush=True)
+    eng.close()
 thp = Tacotron2HParams()
 tw = generate_tacotron2_weights(thp, 77)
 tw["decoder/gate_output/bias"][:] = -10.0
