@@ -206,8 +206,8 @@ bool use_pm(const wg_engine* e, int B, int T) {
   return cost_pm <= cost_pos;
 }
 
-// CTA-pair layer kernel (phase-major, C = 256; tc_pair_kernels.cuh): same bits, 3-4 % less time per tile (same-box A/B,
-// profiles/r02_pair_ab.jsonl) -- chosen when its wave count (pairs of row tiles on pairs of SMs; an odd tile count per phase
+// CTA-pair layer kernels (phase-major; C = 256: tc_pair_kernels.cuh, C = 512: tc512_gate_pair_kernel): same bits, 0-3.4 % /
+// 7 % less time per tile (same-box A/Bs, profiles/r02_pair_ab*.jsonl) -- chosen when the wave count (pairs of row tiles on pairs of SMs; an odd tile count per phase
 // block leaves a ghost tile) does not eat that gain. WG_PAIR=0/1 forces either kernel.
 bool use_pair(const wg_engine* e, const TcPlan& pl) {
   if (e->pair_policy == 0 || e->pair_max < 1) return false;
@@ -216,7 +216,8 @@ bool use_pair(const wg_engine* e, const TcPlan& pl) {
   // a device whose complete TPCs are fewer than sm_count / 2 leaves SMs idle under the pair kernel: the wave count decides
   const long sm = e->sm_count > 0 ? e->sm_count : 148, pairs = e->pair_max;
   const long tiles = (long)pl.tiles_per_row * pl.R, pair_tiles = (long)((pl.tiles_per_row + 1) / 2) * pl.R;
-  const double cost_single = (double)((tiles + sm - 1) / sm), cost_pair = 0.966 * (double)((pair_tiles + pairs - 1) / pairs);
+  const double gain = pl.C == 512 ? 0.93 : 0.966;      // measured per-wave time of the pair kernel relative to the single-CTA one
+  const double cost_single = (double)((tiles + sm - 1) / sm), cost_pair = gain * (double)((pair_tiles + pairs - 1) / pairs);
   return cost_pair < cost_single;
 }
 
@@ -378,6 +379,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
 
   TcPlan plan;
   TcPairMaps pmaps;
+  Tc512PairMaps pmaps512;
   Tf32Plan plan3;
   // ---- (1) upsample + trim + regroup: spect[B*L, S]  (waveglow_arch.py:245-253) ---------------
   if (tf32) {
@@ -405,6 +407,10 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
     e->last_pair = 0;
     if (pm && C == 256 && use_pair(e, plan))
       tc_pair_prepare(pmaps, plan, c.n_flows * c.n_layers, c.n_flows, R, e->W1, e->W2, e->V, e->W0, e->H0, e->pair_max);
+    if (pm && C == 512 && use_pair(e, plan)) {
+      tc512_pair_prepare(pmaps512, plan, c.n_flows * c.n_layers, c.n_flows, R, e->W1, e->V, e->W0, e->pair_max);
+      e->last_pair = 1;
+    }
     if (C == 512) make_map_4d(&m_acts512, acts16, 1, pm ? (uint64_t)R : (uint64_t)B, plan.Trows, C, WL_BM);
     e->launches += tc_upsample(plan, mel, e->bup, st);
   }
@@ -510,7 +516,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
         if (e->profiling) e->ev_count.back() += 1;
         if (C == 512)
           e->launches += tc512_wn_layer(plan, m_acts512, k * c.n_layers + i, d, last, hcur, acc8, pm ? lw.b1_pm : lw.b1,
-                                        lw.b2, lw.wse_p.data(), st, fold0 && i == 0);
+                                        lw.b2, lw.wse_p.data(), st, fold0 && i == 0, &pmaps512);
         else if (pmaps.ready && !(fold0 && i == 0 && e->pair_epi_warps == 8)) {   // FIRST layers: the single-CTA kernel is faster (348 vs 370 us)
           e->last_pair = 1;
           e->launches += tc_wn_layer_pair(plan, pmaps, k * c.n_layers + i, d, last, hcur, acc8, lw.b1_pm, lw.b2,
