@@ -1,3 +1,4 @@
+# The round-end check on a B200 box: `gpurun -- bash tools/gpu_check.sh` -> GPU tests, parity prints, default bench line, reference arm (outputs in gpurun_out/).
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
