@@ -14,12 +14,9 @@ variable-length or compound types) raises `H5FormatError` with the name of the m
 """
 from __future__ import annotations
 
-import struct
-
 import numpy as np
 
 SIGNATURE = b"\x89HDF\r\n\x1a\n"
-UNDEF = 0xFFFFFFFFFFFFFFFF
 
 
 class H5FormatError(ValueError):
@@ -43,10 +40,6 @@ class H5File:
     # ---- low level ------------------------------------------------------------------------------------------------
     def _u(self, off, n):
         return int.from_bytes(self.buf[off:off + n], "little")
-
-    def _addr(self, off):
-        v = self._u(off, self.so)
-        return None if v == (1 << (8 * self.so)) - 1 else v + self.base
 
     def _find_superblock(self):
         off = 0
