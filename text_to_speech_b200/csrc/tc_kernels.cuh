@@ -142,7 +142,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// One lane of a fully converged warp (see tc_pair_kernel.cuh for why the issue loops keep the whole warp).
+// One lane of a fully converged warp. The producer / MMA issue loops keep the WHOLE warp in the loop and elect only around
+// the asm: ptxas then keeps descriptors and coordinates in uniform registers; a loop entered by `if (lane == 0)` made every
+// UTCHMMA / UTMALDG pay an ELECT + R2UR.BROADCAST waterfall (profiles/r01_probes.md).
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
