@@ -2,6 +2,7 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log; tail -7 gpurun_out/smoke.log
 timeout 1800 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -8 gpurun_out/pytest_gpu.log
 timeout 300 python -m pytest tests/test_gpu_6_tf32x3.py tests/test_gpu_5_ragged.py -q -s 2>&1 | grep -E "err|max-abs|passed|failed" > gpurun_out/pytest_prints.log
