@@ -105,6 +105,7 @@ struct wg_engine {
   int pair_max = 0;                       // CTA pairs that can be resident at once on this device (tc_pair_init)
   int last_pair = 0;                      // the last wg_infer ran its layers on the CTA-pair kernel
   int pair_epi_warps = 8;                 // WG_PAIR_EPI=16: 16 epilogue warps in the pair kernel
+  bool pdl = true;                        // WG_PDL=0: no programmatic dependent launch of the BF16 layer kernels (A/B)
   int t3_gate_bk = 16;                    // WG_TF32_BK=32: 2-stage SWIZZLE_128B ring in the tf32x3 gate kernel (A/B)
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;   // pairs: [2i] start, [2i+1] stop
@@ -404,6 +405,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
                e->Wup16, R * S, e->W1, e->W2, aup16, spect16, h16[0], h16[1], hlo, pm, R, e->V,
                fold0 ? a0 : nullptr, e->W0, e->H0, c.n_flows, pm ? pm_gap(e) : 0, rg ? &geo : nullptr);
     if (const char* to = std::getenv("WG_TILE_ORDER")) plan.tile_order = to[0] != '0';
+    plan.pdl = e->pdl;
     e->last_pair = 0;
     if (pm && C == 256 && use_pair(e, plan))
       tc_pair_prepare(pmaps, plan, c.n_flows * c.n_layers, c.n_flows, R, e->W1, e->W2, e->V, e->W0, e->H0, e->pair_max);
@@ -969,6 +971,7 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
     e->pair_max = std::min(tc_pair_init(), e->sm_count / 2);
     if (const char* pr = std::getenv("WG_PAIR")) e->pair_policy = std::atoi(pr);
     if (const char* pw = std::getenv("WG_PAIR_EPI")) e->pair_epi_warps = std::atoi(pw) == 16 ? 16 : 8;
+    if (const char* pd = std::getenv("WG_PDL")) e->pdl = pd[0] != '0';
 #ifdef WG_PROBES
     // A/B probes that deliberately BREAK the result to isolate a cost (profiles/r01_probes.md): compiled only into a
     // -DWG_PROBES build, and even there honoured only when the caller also sets WG_ALLOW_PROBES=1.

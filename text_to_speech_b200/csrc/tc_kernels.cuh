@@ -142,6 +142,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Programmatic dependent launch: the trigger lets the next kernel of the stream start launching once every CTA of this grid
+// has issued it; the wait blocks until the previous grid has COMPLETED and its memory is visible.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // One lane of a fully converged warp. The producer / MMA issue loops keep the WHOLE warp in the loop and elect only around
 // the asm: ptxas then keeps descriptors and coordinates in uniform registers; a loop entered by `if (lane == 0)` made every
 // UTCHMMA / UTMALDG pay an ELECT + R2UR.BROADCAST waterfall (profiles/r01_probes.md).
@@ -360,6 +365,8 @@ struct WnLayerParams {
   __nv_bfloat16* lo;       // [B*L, 256] bf16(h - hi), updated in place (rows are tile-private)
   float* acc8;       // [B*L, 8] folded skip/end accumulator (read-modify-write, one thread per row)
   unsigned long long* timing;   // optional [16] cycle counters (debug), may be null
+  int pdl;     // launched with the programmatic-dependent-launch attribute: run the griddepcontrol instructions (small grids:
+               // the next layer's CTAs start on idle SMs and run their prologue while this grid is still working)
   int flags;   // only read when compiled with -DWG_PROBES (result-breaking A/B probes, profiles/r01_probes.md):
                //   1 = skip every other W1 tile load, 2 = skip every other activation tile load
 };
@@ -533,6 +540,7 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((smem_base & 1023u) != 0u) __trap();   // SWIZZLE_128B tiles need 1024-byte aligned bases
+  if (p.pdl) pdl_trigger();
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_h);
@@ -585,6 +593,8 @@ tc_wn_layer_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // everything above touched only weights / kernel parameters; from here on the previous kernel's results are read
+  if (p.pdl) pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
   const bool timing = p.timing != nullptr;
   const bool pm = p.R > 1;   // phase-major: maps are (channels, frames, phases, batch); else (channels, rows, batch, 1)
@@ -1102,6 +1112,7 @@ struct TcPlan {
   // start-conv fold (FIRST layer variant, phase-major only): a0 [M, 64], W0 [n_flows*2C, 64], H0 [n_flows*C, 64]
   CUtensorMap m4_a0{}, m_w0{}, m_h0{};
   bool fold0 = false;
+  bool pdl = true;          // WG_PDL=0 switches programmatic dependent launch of the layer kernels off (A/B)
   int n_layers = 0;
   int tile_order = 1;
   int Breal = 0, Treal = 0, Tp = 0;   // gap layout: B utterances of T frames, Tp rows apart inside a phase block (pm only)
@@ -1201,6 +1212,21 @@ inline void tc_fill_params(const TcPlan& pl, WnLayerParams& p, int layer, int di
   p.b1 = b1; p.b2 = b2; p.hi_out = pl.h16[hcur ^ 1]; p.lo = pl.hlo; p.acc8 = acc8; p.timing = timing; p.flags = flags;
 }
 
+template <typename... KArgs, typename... Args>
+inline void tc_launch(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, bool pdl, const Args&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  WG_CK(cudaLaunchKernelEx(&cfg, kernel, args...));
+}
+
 inline int tc_wn_layer(const TcPlan& pl, int layer, int dilation, bool last, int hcur, float* acc8, const float* b1,
                        const float* b2, const float* wse_host, unsigned long long* timing, int flags, cudaStream_t st,
                        bool first = false) {
@@ -1210,12 +1236,14 @@ inline int tc_wn_layer(const TcPlan& pl, int layer, int dilation, bool last, int
   std::memcpy(cw.wse, wse_host, sizeof cw.wse);
   const int grid = pl.n_tiles < pl.sm_count ? pl.n_tiles : pl.sm_count;
   if (first && (!pl.fold0 || last || dilation != 1)) fail(WG_ERR_INVALID, "start fold requested for a layer it does not apply to");
+  // programmatic dependent launch only where it can pay: a grid that leaves SMs idle (single-utterance calls)
+  p.pdl = pl.pdl && grid < pl.sm_count ? 1 : 0;
   if (last)
-    tc_wn_layer_kernel<true><<<grid, WL_THREADS, WL_SMEM, st>>>(pl.m4_h[hcur], pl.m4_h[hcur ^ 1], pl.m4_lo, pl.m4_cond, pl.m_w1, pl.m_wc, pl.m_w2, pl.m4_a0, pl.m_w0, pl.m_h0, p, cw);
+    tc_launch(tc_wn_layer_kernel<true, false>, grid, WL_THREADS, WL_SMEM, st, p.pdl, pl.m4_h[hcur], pl.m4_h[hcur ^ 1], pl.m4_lo, pl.m4_cond, pl.m_w1, pl.m_wc, pl.m_w2, pl.m4_a0, pl.m_w0, pl.m_h0, p, cw);
   else if (first)
-    tc_wn_layer_kernel<false, true><<<grid, WL_THREADS, WL_SMEM, st>>>(pl.m4_h[hcur], pl.m4_h[hcur ^ 1], pl.m4_lo, pl.m4_cond, pl.m_w1, pl.m_wc, pl.m_w2, pl.m4_a0, pl.m_w0, pl.m_h0, p, cw);
+    tc_launch(tc_wn_layer_kernel<false, true>, grid, WL_THREADS, WL_SMEM, st, p.pdl, pl.m4_h[hcur], pl.m4_h[hcur ^ 1], pl.m4_lo, pl.m4_cond, pl.m_w1, pl.m_wc, pl.m_w2, pl.m4_a0, pl.m_w0, pl.m_h0, p, cw);
   else
-    tc_wn_layer_kernel<false><<<grid, WL_THREADS, WL_SMEM, st>>>(pl.m4_h[hcur], pl.m4_h[hcur ^ 1], pl.m4_lo, pl.m4_cond, pl.m_w1, pl.m_wc, pl.m_w2, pl.m4_a0, pl.m_w0, pl.m_h0, p, cw);
+    tc_launch(tc_wn_layer_kernel<false, false>, grid, WL_THREADS, WL_SMEM, st, p.pdl, pl.m4_h[hcur], pl.m4_h[hcur ^ 1], pl.m4_lo, pl.m4_cond, pl.m_w1, pl.m_wc, pl.m_w2, pl.m4_a0, pl.m_w0, pl.m_h0, p, cw);
   WG_CK(cudaGetLastError());
   return 1;
 }

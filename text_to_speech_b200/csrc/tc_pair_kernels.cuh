@@ -131,6 +131,7 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   if ((smem_base & 1023u) != 0u) __trap();
+  if (p.pdl) pdl_trigger();
 
   // pair-tile pt -> phase r (fastest, as in the single-CTA kernel's tile order) and the pair's row range; this CTA's
   // tile is the rank-th 128-row tile of it. With an odd tile count per phase block the last pair has a GHOST tile
@@ -196,6 +197,7 @@ tc_wn_pair_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
   __syncthreads();
   cluster_sync_all();   // both CTAs' barriers / TMEM / constant tiles exist before anyone signals across
   tc_fence_after();
+  if (p.pdl) pdl_wait();   // from here on the previous kernel's results are read
   const uint32_t tmem_base = *tmem_slot;
   const bool timing = p.timing != nullptr;   // WG_LAYER_TIMING=1: in-kernel cycle counters (same slots as the single-CTA kernel)
   constexpr int KB_CONV = FIRST ? 1 : WL_KB_CONV;
@@ -655,12 +657,13 @@ inline void tc_pair_prepare(TcPairMaps& pm, const TcPlan& pl, int n_layers_total
 template <int EW>
 inline void tc_pair_launch(const TcPlan& pl, const TcPairMaps& pm, const WnLayerParams& p, const WnLayerConst& cw, int grid, bool last,
                            bool first, int hcur, cudaStream_t st) {
+  const bool pdl = p.pdl != 0;
   if (last)
-    tc_wn_pair_kernel<true, false, EW><<<grid, WpGeom<true, EW>::THREADS, WpGeom<true, EW>::SMEM, st>>>(pl.m4_h[hcur], pl.m4_h[hcur ^ 1], pl.m4_lo, pl.m4_cond, pm.m_w1, pm.m_wc, pm.m_w2, pl.m4_a0, pm.m_w0, pm.m_h0, p, cw);
+    tc_launch(tc_wn_pair_kernel<true, false, EW>, grid, WpGeom<true, EW>::THREADS, WpGeom<true, EW>::SMEM, st, pdl, pl.m4_h[hcur], pl.m4_h[hcur ^ 1], pl.m4_lo, pl.m4_cond, pm.m_w1, pm.m_wc, pm.m_w2, pl.m4_a0, pm.m_w0, pm.m_h0, p, cw);
   else if (first)
-    tc_wn_pair_kernel<false, true, EW><<<grid, WpGeom<false, EW>::THREADS, WpGeom<false, EW>::SMEM, st>>>(pl.m4_h[hcur], pl.m4_h[hcur ^ 1], pl.m4_lo, pl.m4_cond, pm.m_w1, pm.m_wc, pm.m_w2, pl.m4_a0, pm.m_w0, pm.m_h0, p, cw);
+    tc_launch(tc_wn_pair_kernel<false, true, EW>, grid, WpGeom<false, EW>::THREADS, WpGeom<false, EW>::SMEM, st, pdl, pl.m4_h[hcur], pl.m4_h[hcur ^ 1], pl.m4_lo, pl.m4_cond, pm.m_w1, pm.m_wc, pm.m_w2, pl.m4_a0, pm.m_w0, pm.m_h0, p, cw);
   else
-    tc_wn_pair_kernel<false, false, EW><<<grid, WpGeom<false, EW>::THREADS, WpGeom<false, EW>::SMEM, st>>>(pl.m4_h[hcur], pl.m4_h[hcur ^ 1], pl.m4_lo, pl.m4_cond, pm.m_w1, pm.m_wc, pm.m_w2, pl.m4_a0, pm.m_w0, pm.m_h0, p, cw);
+    tc_launch(tc_wn_pair_kernel<false, false, EW>, grid, WpGeom<false, EW>::THREADS, WpGeom<false, EW>::SMEM, st, pdl, pl.m4_h[hcur], pl.m4_h[hcur ^ 1], pl.m4_lo, pl.m4_cond, pm.m_w1, pm.m_wc, pm.m_w2, pl.m4_a0, pm.m_w0, pm.m_h0, p, cw);
 }
 
 inline int tc_wn_layer_pair(const TcPlan& pl, const TcPairMaps& pm, int layer, int dilation, bool last, int hcur,
@@ -675,6 +678,7 @@ inline int tc_wn_layer_pair(const TcPlan& pl, const TcPairMaps& pm, int layer, i
   const int need_pairs = ((pl.tiles_per_row + 1) / 2) * pl.R;
   const int grid = 2 * (need_pairs < max_pairs ? need_pairs : max_pairs);
   if (first && (!pl.fold0 || last || dilation != 1)) fail(WG_ERR_INVALID, "start fold requested for a layer it does not apply to");
+  p.pdl = pl.pdl && grid < pl.sm_count ? 1 : 0;
 #ifdef WG_PROBES
   if (epi_warps == 16) {
     tc_pair_launch<16>(pl, pm, p, cw, grid, last, first, hcur, st);
