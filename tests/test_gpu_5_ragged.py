@@ -303,3 +303,19 @@ def test_ragged_batch_of_hundreds_of_short_utterances(lib_built):
         n = lengths[b]
         assert np.array_equal(out[b, :n * 256], _alone(eng, mel, z, b, n)) and not out[b, n * 256:].any()
     eng.close()
+
+
+def test_engine_from_keras_weights_h5_equals_engine_from_npz(lib_built, tmp_path):
+    """`WaveGlow(path='<name>.weights.h5')`: the reference's checkpoint format (checkpoint_manager.py:169-216) through
+    h5lite / convert.from_keras_weights_h5 gives the same engine as the .npz of the same weights, bit for bit."""
+    from oracle.h5_writer import write_h5, keras3_waveglow_layout
+    from text_to_speech_b200.waveglow import WaveGlow
+    hp = WaveGlowHParams()
+    w = generate_weights(hp, 1234)
+    npz, h5 = str(tmp_path / "wg.npz"), str(tmp_path / "waveglow.weights.h5")
+    save_weights(npz, hp, w)
+    write_h5(h5, keras3_waveglow_layout(hp, w))
+    mel, z = synthetic_inputs(6, 2, 20, hp)
+    a = np.array(WaveGlow(path=npz, runtime="b200", mode="bf16")(mel, z=z, sigma=0.6))
+    b = np.array(WaveGlow(path=h5, runtime="b200", mode="bf16")(mel, z=z, sigma=0.6))
+    assert a.shape == (2, 20 * 256) and np.array_equal(a, b)
