@@ -102,3 +102,30 @@ def test_tf32x3_refuses_what_it_cannot_run(lib_built):
     hp = WaveGlowHParams(n_channels=64)
     with pytest.raises(WaveGlowError, match="TF32X3"):
         WaveGlowEngine(hp, generate_weights(hp, 1), mode="tf32x3")
+
+
+@pytest.mark.parametrize("B,T,lengths", [(1, 12, None), (3, 300, None), (1, 200, None), (4, 97, [97, 5, 33, 64])])
+def test_tf32x3_kernel_variants_give_the_same_bits(lib_built, monkeypatch, B, T, lengths):
+    """The CTA-pair kernels (cta_group::2 kind::tf32, an odd tile count per phase block = a ghost tile included) against
+    the single-CTA kernels, and 8 against 16 epilogue warps: the engine picks among them by shape, so a ragged batch is
+    bit-identical to its stand-alone utterances only if all of them produce the same bits."""
+    hp = WaveGlowHParams()
+    w = generate_weights(hp, 1234)
+    mel, z = synthetic_inputs(B * 1000 + T, B, T, hp)
+    outs = {}
+    for pair in ("0", "1"):
+        for ew in ("8", "16"):
+            monkeypatch.setenv("WG_PAIR", pair)
+            monkeypatch.setenv("WG_TF32_EPI", ew)
+            eng = _engine(hp, w)
+            outs[(pair, ew)] = _run(eng, mel, z, 0.6, lengths=lengths)
+            assert eng.pair_info()[1] == (pair == "1")
+            eng.close()
+    monkeypatch.delenv("WG_PAIR")
+    monkeypatch.delenv("WG_TF32_EPI")
+    eng = _engine(hp, w)
+    ref = _run(eng, mel, z, 0.6, lengths=lengths)
+    eng.close()
+    assert np.isfinite(ref).all()
+    for k, o in outs.items():
+        assert np.array_equal(ref, o), k

@@ -106,7 +106,9 @@ struct wg_engine {
   int last_pair = 0;                      // the last wg_infer ran its layers on the CTA-pair kernel
   int pair_epi_warps = 8;                 // WG_PAIR_EPI=16: 16 epilogue warps in the pair kernel
   bool pdl = true;                        // WG_PDL=0: no programmatic dependent launch of the BF16 layer kernels (A/B)
-  int t3_gate_bk = 16;                    // WG_TF32_BK=32: 2-stage SWIZZLE_128B ring in the tf32x3 gate kernel (A/B)
+  int t3_gate_bk = 32;                    // WG_TF32_BK=16: SWIZZLE_64B ring of 16-float K-blocks in the tf32x3 gate kernel (A/B)
+  int t3_epi_warps = 0;                   // WG_TF32_EPI=8 / 16: force the epilogue warp count of the tf32x3 kernels (A/B)
+  int t3_max_pairs = 0;                   // resident CTA pairs of the tf32x3 kernels (tf32_init)
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;   // pairs: [2i] start, [2i+1] stop
   std::vector<int> ev_count;          // per pair: layer launches bracketed by it
@@ -390,7 +392,8 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
                  rg ? 0 : geo.Tp, geo.T, e->t3, t3_hhi[0], t3_hhi[1], t3_hlo[0], t3_hlo[1],
                  reinterpret_cast<float*>(base + w.t3_chi), reinterpret_cast<float*>(base + w.t3_clo),
                  reinterpret_cast<float*>(base + w.t3_ahi), reinterpret_cast<float*>(base + w.t3_alo), acc8, t3_acc_stride,
-                 e->t3_gate_bk);
+                 e->t3_gate_bk, e->t3_max_pairs, e->pair_policy, e->t3_epi_warps);
+    e->last_pair = plan3.pair ? 1 : 0;
     e->launches += tf32_upsample(plan3, mel, st);
   } else if (ffma) {
     GemmArgs g{};
@@ -483,7 +486,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
           if (e->profiling) e->ev_count.push_back(0);
         }
         if (e->profiling) e->ev_count.back() += 1;
-        e->launches += tf32_wn_layer(plan3, k * c.n_layers + i, d, last, hcur, lw.b1_pm, lw.b2, lw.wse_d, st);
+        e->launches += tf32_wn_layer(plan3, k * c.n_layers + i, d, last, hcur, lw.b1_pm, lw.b2, lw.wse_d, st, e->timing);
         if (last || (k == stop_flow && i == stop_layer)) prof_mark();
         if (!last) hcur ^= 1;
       } else if (ffma) {
@@ -887,8 +890,10 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
     e->t3.W1h = upload(e, t3w1h); e->t3.W1l = upload(e, t3w1l);
     e->t3.W2h = upload(e, t3w2h); e->t3.W2l = upload(e, t3w2l);
     tc_init();
-    tf32_init();
-    if (const char* bk = std::getenv("WG_TF32_BK")) e->t3_gate_bk = std::atoi(bk) == 32 ? 32 : 16;
+    e->t3_max_pairs = std::min(tf32_init(), e->sm_count / 2);
+    if (const char* pr = std::getenv("WG_PAIR")) e->pair_policy = std::atoi(pr);
+    if (const char* bk = std::getenv("WG_TF32_BK")) e->t3_gate_bk = std::atoi(bk) == 16 ? 16 : 32;
+    if (const char* ew = std::getenv("WG_TF32_EPI")) e->t3_epi_warps = std::atoi(ew) == 16 ? 16 : (std::atoi(ew) == 8 ? 8 : 0);
     // folded conditioning weights as an fp32 (hi, lo) pair: V[(layer*R + r)*2C + n][k] = sum_s Wup_r[k][s] * Wcond[s][n]
     const int Kw = e->Kup;
     float *d_wup = nullptr, *d_wc = nullptr, *d_tmp = nullptr, *vh = nullptr, *vl = nullptr;
@@ -978,12 +983,12 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
     if (const char* f = std::getenv("WG_DEBUG_FLAGS"))
       if (const char* ok = std::getenv("WG_ALLOW_PROBES")) e->dbg_flags = ok[0] == '1' ? std::atoi(f) : 0;
 #endif
-    if (const char* t = std::getenv("WG_LAYER_TIMING")) {
-      if (t[0] == '1') {
-        CK(cudaMalloc(&e->timing, 128 * sizeof(unsigned long long)));
-        e->allocs.push_back(e->timing);
-        CK(cudaMemset(e->timing, 0, 128 * sizeof(unsigned long long)));
-      }
+  }
+  if (const char* t = std::getenv("WG_LAYER_TIMING")) {
+    if (t[0] == '1' && c.mode != WG_MODE_FP32) {
+      CK(cudaMalloc(&e->timing, 128 * sizeof(unsigned long long)));
+      e->allocs.push_back(e->timing);
+      CK(cudaMemset(e->timing, 0, 128 * sizeof(unsigned long long)));
     }
   }
   CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
@@ -1230,7 +1235,7 @@ int wg_profile_read(wg_handle h, double* layer_ms_sum, int32_t* layer_launches) 
 
 int wg_debug_pair_info(wg_handle h, int32_t* max_pairs, int32_t* last_used) {
   if (!h || !max_pairs || !last_used) return WG_ERR_INVALID;
-  *max_pairs = h->pair_max;
+  *max_pairs = h->cfg.mode == WG_MODE_TF32X3 ? h->t3_max_pairs : h->pair_max;
   *last_used = h->last_pair;
   return WG_OK;
 }
@@ -1238,7 +1243,7 @@ int wg_debug_pair_info(wg_handle h, int32_t* max_pairs, int32_t* last_used) {
 int wg_debug_read_timing(wg_handle h, uint64_t* out128) {
   if (!h || !out128) return WG_ERR_INVALID;
   return guarded(h, [&] {
-    if (!h->timing) fail(WG_ERR_INVALID, "layer timing is off (set WG_LAYER_TIMING=1 before wg_create, BF16 mode)");
+    if (!h->timing) fail(WG_ERR_INVALID, "layer timing is off (set WG_LAYER_TIMING=1 before wg_create; BF16 / TF32X3 modes)");
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(out128, h->timing, 128 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     CK(cudaMemset(h->timing, 0, 128 * sizeof(unsigned long long)));

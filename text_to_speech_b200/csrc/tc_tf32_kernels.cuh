@@ -21,10 +21,20 @@
 // Both are persistent (static schedule) with a double-buffered TMEM accumulator so the epilogue of one item overlaps
 // the MMAs of the next. K1 (1 x 200 frames) is 32 phases x 2 tiles = 64 tiles -> 128 gate items: one item per CTA, one wave.
 #pragma once
-#include "tc_kernels.cuh"
+#include "tc_pair_kernels.cuh"
 
 namespace wg {
 
+// cta_group::2 form: ONE instruction drives both tensor cores of a CTA pair (M = 256: 128 rows per CTA; each CTA's shared
+// memory holds its own A rows and its own HALF of the B rows -- see tc_pair_kernels.cuh for the protocol)
+__device__ __forceinline__ void umma2_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -57,20 +67,26 @@ __host__ __device__ inline float tf32_rna_host(float x) {   // same rounding on 
 
 constexpr int T3_BM = 128, T3_BK = 32;                 // 32 floats = one 128-byte swizzle row
 constexpr int T3_A_BYTES = T3_BM * T3_BK * 4;          // 16 KB
-constexpr int T3_EPI_WARPS = 8, T3_EPI_THREADS = T3_EPI_WARPS * 32, T3_THREADS = 64 + T3_EPI_THREADS;
+// Epilogue warps EW (template parameter, 8 or 16): NCG = EW / 4 warps share a TMEM lane quarter and split the accumulator
+// columns. A single utterance runs ONE item per CTA, so the epilogue is not hidden behind the next item's MMAs and its
+// latency (accurate tanhf / expf; 2 warps per scheduler with EW = 8) is paid per layer: 16 warps there (K1 7.8 -> 7.1 ms);
+// with several items per CTA the epilogue is hidden and 8 warps are faster (8 x 860: 141 vs 150 ms). Same bits either way:
+// the skip/end fold has one canonical order.
+constexpr int t3_threads(int ew) { return 64 + ew * 32; }
 // gate kernel: N = 256 per item. K-block width BK floats per stage: 32 (one 128-byte swizzle row, 2 stages of 96 KB) or
 // 16 (64-byte swizzle rows, 4 stages of 48 KB): the same 192 KB ring in finer slices keeps more bytes in flight while the
 // MMA works on a stage -- the kernel is bound by the latency of its operand feed (8 B per operand element for the fp32 pairs).
 constexpr int T3G_BN = 256;
-template <int BK>
+template <int BK, bool PAIR = false>
 struct T3G {
   static_assert(BK == 32 || BK == 16, "K-block of 32 floats (SWIZZLE_128B) or 16 floats (SWIZZLE_64B)");
-  static constexpr int A_BYTES = T3_BM * BK * 4, B_BYTES = T3G_BN * BK * 4;
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;                // 96 KB / 48 KB
-  static constexpr int STAGES = BK == 32 ? 2 : 4;
+  // PAIR: this CTA holds its own 128 A rows and 128 of the chunk's 256 B rows (the other half sits in the peer CTA)
+  static constexpr int A_BYTES = T3_BM * BK * 4, B_BYTES = (PAIR ? T3G_BN / 2 : T3G_BN) * BK * 4;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;                // 96 / 48 KB;  pair: 64 / 32 KB
+  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;                    // 2 / 4;  pair: 3 / 6
   static constexpr int OFF_B1 = STAGES * STAGE_BYTES;
   static constexpr int OFF_O8 = OFF_B1 + 256 * 4;
-  static constexpr int OFF_BARS = OFF_O8 + T3_BM * 8 * 4;
+  static constexpr int OFF_BARS = OFF_O8 + 3 * T3_BM * 8 * 4;   // fold partials of column groups 1 .. NCG-1 (NCG <= 4)
   static constexpr int NBARS = 2 * STAGES + 4;
   static constexpr int SMEM = OFF_BARS + NBARS * 8 + 16;
   static_assert(SMEM <= 232448, "shared memory budget");
@@ -90,13 +106,18 @@ __device__ __forceinline__ uint64_t t3_desc(uint32_t smem_addr) {
   return BK == 32 ? umma_desc_sw128(smem_addr) : umma_desc_sw64(smem_addr);
 }
 // residual kernel: N = 128 per item
-constexpr int T3R_BN = 128, T3R_B_BYTES = T3R_BN * T3_BK * 4;                 // 16 KB
-constexpr int T3R_STAGES = 3, T3R_STAGE_BYTES = 2 * T3_A_BYTES + 2 * T3R_B_BYTES;   // 64 KB
-constexpr int T3R_OFF_B2 = T3R_STAGES * T3R_STAGE_BYTES;
-constexpr int T3R_OFF_BARS = T3R_OFF_B2 + T3R_BN * 4;
-constexpr int T3R_NBARS = 2 * T3R_STAGES + 4;
-constexpr int T3R_SMEM = T3R_OFF_BARS + T3R_NBARS * 8 + 16;
-static_assert(T3R_SMEM <= 232448, "shared memory budget");
+constexpr int T3R_BN = 128;
+template <bool PAIR = false>
+struct T3RG {
+  static constexpr int B_BYTES = (PAIR ? T3R_BN / 2 : T3R_BN) * T3_BK * 4;     // 16 KB;  pair: 8 KB (64 of the 128 B rows)
+  static constexpr int STAGE_BYTES = 2 * T3_A_BYTES + 2 * B_BYTES;             // 64 KB;  pair: 48 KB
+  static constexpr int STAGES = PAIR ? 4 : 3;
+  static constexpr int OFF_B2 = STAGES * STAGE_BYTES;
+  static constexpr int OFF_BARS = OFF_B2 + T3R_BN * 4;
+  static constexpr int NBARS = 2 * STAGES + 4;
+  static constexpr int SMEM = OFF_BARS + NBARS * 8 + 16;
+  static_assert(SMEM <= 232448, "shared memory budget");
+};
 
 struct Tf32Params {
   int T, R, tiles_per_row, n_tiles;   // phase-block rows, phases, 128-row tiles per phase block, tiles in all
@@ -118,6 +139,11 @@ struct Tf32Params {
   const float* h_lo;
   float* ho_hi;        // residual epilogue: the next layer's stream (written; gap rows as zeros)
   float* ho_lo;
+  // WG_LAYER_TIMING=1 (debug): cycle counters, summed over CTAs. Gate kernel slots 16..: [16] MMA warp first wait -> last
+  // accumulator complete, [17] MMA waiting for TMA data, [18] MMA waiting for the epilogue, [19] epilogue waiting for an
+  // accumulator, [20] epilogue work, [21] kernel entry -> MMA loop entry, [22] producer waiting for a free stage,
+  // [23] MMA-issuing CTAs; residual kernel: the same at 32..
+  unsigned long long* timing;
 };
 
 __device__ __forceinline__ bool t3_row_valid(const Tf32Params& p, int t) {
@@ -126,22 +152,52 @@ __device__ __forceinline__ bool t3_row_valid(const Tf32Params& p, int t) {
   return p.Tp == 0 || t % p.Tp < p.Tv;
 }
 
-// item -> (tile, chunk); tile -> (phase r, first row t0): phase fastest, as in the BF16 kernel's tile order
-__device__ __forceinline__ void t3_item_coords(const Tf32Params& p, int item, int& q, int& r, int& t0) {
+// item -> (tile, chunk); tile -> (phase r, first row t0): phase fastest, as in the BF16 kernel's tile order.
+// PAIR: an item belongs to a CTA pair and covers two adjacent 128-row tiles of one phase, this CTA's being the rank-th;
+// with an odd tile count per phase block the last pair has a GHOST tile (t0 >= T: zeros in, nothing out).
+template <bool PAIR>
+__device__ __forceinline__ void t3_item_coords(const Tf32Params& p, int item, uint32_t rank, int& q, int& r, int& t0) {
   q = item % p.n_chunks;
   const int tile = item / p.n_chunks;
   r = tile % p.R;
-  t0 = (tile / p.R) * T3_BM;
+  t0 = PAIR ? (2 * (tile / p.R) + static_cast<int>(rank)) * T3_BM : (tile / p.R) * T3_BM;
+}
+template <bool PAIR>
+__device__ __forceinline__ int t3_n_items(const Tf32Params& p) {
+  return (PAIR ? ((p.tiles_per_row + 1) / 2) * p.R : p.n_tiles) * p.n_chunks;
+}
+// TMA loads whose bytes complete on `bar`: the CTA's own barrier, or (PAIR) the LEADER CTA's barrier at the same offset
+template <bool PAIR>
+__device__ __forceinline__ void t3_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  if (PAIR) tma2_load_2d(dst, m, bar & kPeerBitMask, c0, c1);
+  else tma_load_2d(dst, m, bar, c0, c1);
+}
+template <bool PAIR>
+__device__ __forceinline__ void t3_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+  if (PAIR) tma2_load_4d(dst, m, bar & kPeerBitMask, c0, c1, c2, c3);
+  else tma_load_4d(dst, m, bar, c0, c1, c2, c3);
+}
+template <bool PAIR>
+__device__ __forceinline__ void t3_mma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if (PAIR) umma2_tf32(d, a, b, idesc, acc);
+  else umma_tf32(d, a, b, idesc, acc);
+}
+template <bool PAIR>
+__device__ __forceinline__ void t3_commit(uint32_t bar) {   // PAIR: arrives at this offset in BOTH CTAs
+  if (PAIR) tc2_commit(bar);
+  else tc_commit(bar);
 }
 
-template <bool LAST, int BK = 32>
-__global__ void __launch_bounds__(T3_THREADS, 1)
+template <bool LAST, int BK = 32, bool PAIR = false, int EW = 8>
+__global__ void __launch_bounds__(t3_threads(EW), 1)
 tf32_gate_kernel(const __grid_constant__ CUtensorMap map_hh, const __grid_constant__ CUtensorMap map_hl,
                  const __grid_constant__ CUtensorMap map_ch, const __grid_constant__ CUtensorMap map_cl,
                  const __grid_constant__ CUtensorMap map_w1h, const __grid_constant__ CUtensorMap map_w1l,
                  const __grid_constant__ CUtensorMap map_vh, const __grid_constant__ CUtensorMap map_vl,
                  const Tf32Params p) {
-  using G = T3G<BK>;
+  using G = T3G<BK, PAIR>;
+  static_assert(EW == 8 || EW == 16, "8 or 16 epilogue warps");
+  constexpr int T3_EPI_THREADS = EW * 32, T3_NCG = EW / 4;
   constexpr int T3G_STAGES = G::STAGES, T3G_STAGE_BYTES = G::STAGE_BYTES, T3G_B_BYTES = G::B_BYTES, T3G_A_BYTES = G::A_BYTES;
   constexpr int T3G_OFF_B1 = G::OFF_B1, T3G_OFF_O8 = G::OFF_O8, T3G_OFF_BARS = G::OFF_BARS, T3G_NBARS = G::NBARS;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -156,7 +212,12 @@ tf32_gate_kernel(const __grid_constant__ CUtensorMap map_hh, const __grid_consta
   auto accfull_bar = [&](int s) { return bar_base + 8u * (2 * T3G_STAGES + s); };
   auto accempty_bar = [&](int s) { return bar_base + 8u * (2 * T3G_STAGES + 2 + s); };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;     // PAIR: full / accempty barriers are used in the leader only, the MMA warp too
+  const int item0 = PAIR ? blockIdx.x >> 1 : blockIdx.x, item_step = PAIR ? gridDim.x >> 1 : gridDim.x;
   if ((smem_base & 1023u) != 0u) __trap();
+  const bool timing = p.timing != nullptr;
+  const long long t_entry = timing ? clock64() : 0;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_hh); prefetch_tmap(&map_hl); prefetch_tmap(&map_ch); prefetch_tmap(&map_cl);
@@ -167,33 +228,43 @@ tf32_gate_kernel(const __grid_constant__ CUtensorMap map_hh, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(accfull_bar(s), 1);
-      mbar_init(accempty_bar(s), T3_EPI_THREADS);
+      mbar_init(accempty_bar(s), (PAIR ? 2 : 1) * T3_EPI_THREADS);
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(tmem_slot), 512);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem2_alloc(smem_u32(tmem_slot), 512);
+      tmem2_relinquish();
+    } else {
+      tmem_alloc(smem_u32(tmem_slot), 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // both CTAs' barriers and TMEM exist before anyone signals across
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int n_items = p.n_tiles * p.n_chunks;
+  const int n_items = t3_n_items<PAIR>(p);
   const int kb1 = p.kb_conv + p.kb_cond;
   const int cblks = p.C / BK;   // K-blocks per tap
 
   if (warp == 0) {
     // ===================================== TMA producer ======================================
     uint32_t it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    long long t_wait = 0;
+    for (int item = item0; item < n_items; item += item_step) {
       int q, r, t0;
-      t3_item_coords(p, item, q, r, t0);
+      t3_item_coords<PAIR>(p, item, rank, q, r, t0);
       for (int kb = 0; kb < kb1; ++kb, ++it) {
         const int s = it % T3G_STAGES;
+        const long long tq = timing ? clock64() : 0;
         mbar_wait(empty_bar(s), ((it / T3G_STAGES) & 1) ^ 1);
+        if (timing) t_wait += clock64() - tq;
         if (elect_one()) {
-          mbar_expect_tx(full_bar(s), T3G_STAGE_BYTES);
+          if (leader) mbar_expect_tx(full_bar(s), (PAIR ? 2 : 1) * T3G_STAGE_BYTES);   // PAIR: the bytes of both CTAs
+          const int bq = q * T3G_BN + (PAIR ? static_cast<int>(rank) * (T3G_BN / 2) : 0);   // first B row this CTA loads
           const uint32_t a_hi = smem_base + s * T3G_STAGE_BYTES, a_lo = a_hi + T3G_A_BYTES;
           const uint32_t b_hi = a_lo + T3G_A_BYTES, b_lo = b_hi + T3G_B_BYTES;
           if (kb < p.kb_conv) {
@@ -201,33 +272,40 @@ tf32_gate_kernel(const __grid_constant__ CUtensorMap map_hh, const __grid_consta
             const int tap = kb / cblks, cblk = kb - tap * cblks;
             const int rs = r + (tap - 1) * p.dilation;
             const int carry = (rs >= 0) ? rs / p.R : -((-rs + p.R - 1) / p.R);
-            tma_load_4d(a_hi, &map_hh, full_bar(s), cblk * BK, t0 + carry, rs - carry * p.R, 0);
-            tma_load_4d(a_lo, &map_hl, full_bar(s), cblk * BK, t0 + carry, rs - carry * p.R, 0);
-            tma_load_2d(b_hi, &map_w1h, full_bar(s), kb * BK, p.layer * 2 * p.C + q * T3G_BN);
-            tma_load_2d(b_lo, &map_w1l, full_bar(s), kb * BK, p.layer * 2 * p.C + q * T3G_BN);
+            t3_load_4d<PAIR>(a_hi, &map_hh, full_bar(s), cblk * BK, t0 + carry, rs - carry * p.R, 0);
+            t3_load_4d<PAIR>(a_lo, &map_hl, full_bar(s), cblk * BK, t0 + carry, rs - carry * p.R, 0);
+            t3_load_2d<PAIR>(b_hi, &map_w1h, full_bar(s), kb * BK, p.layer * 2 * p.C + bq);
+            t3_load_2d<PAIR>(b_lo, &map_w1l, full_bar(s), kb * BK, p.layer * 2 * p.C + bq);
           } else {
             const int kc = kb - p.kb_conv;
-            tma_load_4d(a_hi, &map_ch, full_bar(s), kc * BK, t0, 0, 0);
-            tma_load_4d(a_lo, &map_cl, full_bar(s), kc * BK, t0, 0, 0);
-            tma_load_2d(b_hi, &map_vh, full_bar(s), kc * BK, p.wc_row0 + r * p.wc_rstride + q * T3G_BN);
-            tma_load_2d(b_lo, &map_vl, full_bar(s), kc * BK, p.wc_row0 + r * p.wc_rstride + q * T3G_BN);
+            t3_load_4d<PAIR>(a_hi, &map_ch, full_bar(s), kc * BK, t0, 0, 0);
+            t3_load_4d<PAIR>(a_lo, &map_cl, full_bar(s), kc * BK, t0, 0, 0);
+            t3_load_2d<PAIR>(b_hi, &map_vh, full_bar(s), kc * BK, p.wc_row0 + r * p.wc_rstride + bq);
+            t3_load_2d<PAIR>(b_lo, &map_vl, full_bar(s), kc * BK, p.wc_row0 + r * p.wc_rstride + bq);
           }
         }
         __syncwarp();
       }
     }
+    if (timing && lane == 0) atomicAdd(p.timing + 22, static_cast<unsigned long long>(t_wait));
   } else if (warp == 1) {
-    // ====================================== MMA issuer =======================================
-    constexpr uint32_t idesc = umma_idesc_tf32(T3_BM, T3G_BN);
+    // =========================== MMA issuer (PAIR: the leader CTA only) ========================
+    constexpr uint32_t idesc = umma_idesc_tf32(PAIR ? 2 * T3_BM : T3_BM, T3G_BN);
     uint32_t it = 0, n = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+    long long t_full = 0, t_epi = 0;
+    const long long t_begin = timing ? clock64() : 0;
+    for (int item = item0; leader && item < n_items; item += item_step, ++n) {
       const uint32_t as = n & 1u;
-      mbar_wait(accempty_bar(as), ((n >> 1) & 1u) ^ 1u);   // the epilogue has read this accumulator out (2 items ago)
+      long long tq = timing ? clock64() : 0;
+      mbar_wait(accempty_bar(as), ((n >> 1) & 1u) ^ 1u);
+      if (timing) t_epi += clock64() - tq;   // the epilogue has read this accumulator out (2 items ago)
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + 256u * as;
       for (int kb = 0; kb < kb1; ++kb, ++it) {
         const int s = it % T3G_STAGES;
+        tq = timing ? clock64() : 0;
         mbar_wait(full_bar(s), (it / T3G_STAGES) & 1);
+        if (timing) t_full += clock64() - tq;
         tc_fence_after();
         const uint32_t base = smem_base + s * T3G_STAGE_BYTES;
         const uint64_t ahi = t3_desc<BK>(base), alo = t3_desc<BK>(base + T3G_A_BYTES);
@@ -235,28 +313,40 @@ tf32_gate_kernel(const __grid_constant__ CUtensorMap map_hh, const __grid_consta
         if (elect_one()) {
           // small cross terms first, then the main product (K = 8 floats = 32 bytes per instruction: +2 in the descriptor)
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k) umma_tf32(d_tmem, alo + 2 * k, bhi + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < BK / 8; ++k) t3_mma<PAIR>(d_tmem, alo + 2 * k, bhi + 2 * k, idesc, (kb | k) ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k) umma_tf32(d_tmem, ahi + 2 * k, blo + 2 * k, idesc, 1u);
+          for (int k = 0; k < BK / 8; ++k) t3_mma<PAIR>(d_tmem, ahi + 2 * k, blo + 2 * k, idesc, 1u);
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k) umma_tf32(d_tmem, ahi + 2 * k, bhi + 2 * k, idesc, 1u);
-          tc_commit(empty_bar(s));
-          if (kb == kb1 - 1) tc_commit(accfull_bar(as));
+          for (int k = 0; k < BK / 8; ++k) t3_mma<PAIR>(d_tmem, ahi + 2 * k, bhi + 2 * k, idesc, 1u);
+          t3_commit<PAIR>(empty_bar(s));
+          if (kb == kb1 - 1) t3_commit<PAIR>(accfull_bar(as));
         }
         __syncwarp();
+      }
+    }
+    if (timing && leader && n > 0) {
+      // the last accumulator is complete when its accfull barrier flips (this CTA's copy; waiting does not consume it)
+      mbar_wait(accfull_bar((n - 1) & 1u), ((n - 1) >> 1) & 1u);
+      if (lane == 0) {
+        atomicAdd(p.timing + 16, static_cast<unsigned long long>(clock64() - t_begin));
+        atomicAdd(p.timing + 17, static_cast<unsigned long long>(t_full));
+        atomicAdd(p.timing + 18, static_cast<unsigned long long>(t_epi));
+        atomicAdd(p.timing + 21, static_cast<unsigned long long>(t_begin - t_entry));
+        atomicAdd(p.timing + 23, 1ull);
       }
     }
   } else {
     // ======================================= epilogue ========================================
     const int we = warp - 2;
     const int quarter = warp & 3;       // TMEM lane quarter this warp may access
-    const int hf = we >> 2;             // which half of the 128 gate channels this warp handles
+    const int cg = we >> 2;             // column group: CH of the chunk's 128 gate channels
+    constexpr int CH = 128 / T3_NCG, NP = CH / 32;   // channels per thread; 32-channel fold partials per thread
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     uint32_t n = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+    for (int item = item0; item < n_items; item += item_step, ++n) {
       int q, r, t0;
-      t3_item_coords(p, item, q, r, t0);
+      t3_item_coords<PAIR>(p, item, rank, q, r, t0);
       const uint32_t as = n & 1u;
       const bool valid = t3_row_valid(p, t0 + row);
       const size_t m = static_cast<size_t>(r) * p.T + t0 + row;
@@ -264,80 +354,110 @@ tf32_gate_kernel(const __grid_constant__ CUtensorMap map_hh, const __grid_consta
       asm volatile("bar.sync 1, %0;" ::"n"(T3_EPI_THREADS) : "memory");   // previous item's s_b1 / s_o8 readers are done
       for (int i = threadIdx.x - 64; i < 256; i += T3_EPI_THREADS) s_b1[i] = p.bias[q * 256 + i];
       asm volatile("bar.sync 1, %0;" ::"n"(T3_EPI_THREADS) : "memory");
+      const long long tq = timing ? clock64() : 0;
       mbar_wait(accfull_bar(as), (n >> 1) & 1u);
+      const long long tw = timing ? clock64() : 0;
       tc_fence_after();
-      float o8[8];
+      // skip/end fold: one partial sum per 32 channels, P0..P3, combined as (P0 + P1) + (P2 + P3) whatever the warp count
+      float o8[NP][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o8[j] = 0.f;
-      const uint32_t taddr = tmem_base + lane_addr + 256u * as + hf * 64;
+      for (int pi = 0; pi < NP; ++pi)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o8[pi][j] = 0.f;
+      const uint32_t taddr = tmem_base + lane_addr + 256u * as + cg * CH;
+#pragma unroll
+      for (int pi = 0; pi < NP; ++pi) {
 #pragma unroll 1
-      for (int g = 0; g < 4; ++g) {       // 16 gate channels per step
-        uint32_t tr[16], gr[16];
-        tmem_ld16(taddr + g * 16, tr);
-        tmem_ld16(taddr + 128 + g * 16, gr);
-        tmem_ld_wait();
-        const int ch0 = hf * 64 + g * 16;                 // first channel inside the chunk
-        const float* wse = p.wse + static_cast<size_t>(q * 128 + ch0) * 8;
-        float a[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float xt = __uint_as_float(tr[j]) + s_b1[ch0 + j];
-          const float xg = __uint_as_float(gr[j]) + s_b1[128 + ch0 + j];
-          a[j] = tanhf(xt) * (1.0f / (1.0f + expf(-xg)));          // waveglow_arch.py:19-24
-          const float4 w0 = __ldg(reinterpret_cast<const float4*>(wse + j * 8));
-          const float4 w1 = __ldg(reinterpret_cast<const float4*>(wse + j * 8 + 4));
-          o8[0] = fmaf(a[j], w0.x, o8[0]); o8[1] = fmaf(a[j], w0.y, o8[1]);
-          o8[2] = fmaf(a[j], w0.z, o8[2]); o8[3] = fmaf(a[j], w0.w, o8[3]);
-          o8[4] = fmaf(a[j], w1.x, o8[4]); o8[5] = fmaf(a[j], w1.y, o8[5]);
-          o8[6] = fmaf(a[j], w1.z, o8[6]); o8[7] = fmaf(a[j], w1.w, o8[7]);
-        }
-        if (!LAST && (t0 + row) < p.T) {
-          float hi[16], lo[16];
+        for (int g2 = 0; g2 < 2; ++g2) {       // 16 gate channels per step
+          const int g = pi * 2 + g2;
+          uint32_t tr[16], gr[16];
+          tmem_ld16(taddr + g * 16, tr);
+          tmem_ld16(taddr + 128 + g * 16, gr);
+          tmem_ld_wait();
+          const int ch0 = cg * CH + g * 16;                 // first channel inside the chunk
+          const float* wse = p.wse + static_cast<size_t>(q * 128 + ch0) * 8;
+          float a[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            hi[j] = valid ? tf32_rna(a[j]) : 0.f;
-            lo[j] = valid ? a[j] - hi[j] : 0.f;
+            const float xt = __uint_as_float(tr[j]) + s_b1[ch0 + j];
+            const float xg = __uint_as_float(gr[j]) + s_b1[128 + ch0 + j];
+            a[j] = tanhf(xt) * (1.0f / (1.0f + expf(-xg)));          // waveglow_arch.py:19-24
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(wse + j * 8));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(wse + j * 8 + 4));
+            o8[pi][0] = fmaf(a[j], w0.x, o8[pi][0]); o8[pi][1] = fmaf(a[j], w0.y, o8[pi][1]);
+            o8[pi][2] = fmaf(a[j], w0.z, o8[pi][2]); o8[pi][3] = fmaf(a[j], w0.w, o8[pi][3]);
+            o8[pi][4] = fmaf(a[j], w1.x, o8[pi][4]); o8[pi][5] = fmaf(a[j], w1.y, o8[pi][5]);
+            o8[pi][6] = fmaf(a[j], w1.z, o8[pi][6]); o8[pi][7] = fmaf(a[j], w1.w, o8[pi][7]);
           }
-          float4* dh = reinterpret_cast<float4*>(p.acts_hi + m * p.C + q * 128 + ch0);
-          float4* dl = reinterpret_cast<float4*>(p.acts_lo + m * p.C + q * 128 + ch0);
+          if (!LAST && (t0 + row) < p.T) {
+            float hi[16], lo[16];
 #pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            dh[v] = make_float4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
-            dl[v] = make_float4(lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
+            for (int j = 0; j < 16; ++j) {
+              hi[j] = valid ? tf32_rna(a[j]) : 0.f;
+              lo[j] = valid ? a[j] - hi[j] : 0.f;
+            }
+            float4* dh = reinterpret_cast<float4*>(p.acts_hi + m * p.C + q * 128 + ch0);
+            float4* dl = reinterpret_cast<float4*>(p.acts_lo + m * p.C + q * 128 + ch0);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              dh[v] = make_float4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
+              dl[v] = make_float4(lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
+            }
           }
         }
       }
       tc_fence_before();
-      mbar_arrive(accempty_bar(as));
-      // fold: the two column halves of a row are summed in a fixed order, then added to this chunk's own partial
-      if (hf == 1) {
-        *reinterpret_cast<float4*>(s_o8 + row * 8) = make_float4(o8[0], o8[1], o8[2], o8[3]);
-        *reinterpret_cast<float4*>(s_o8 + row * 8 + 4) = make_float4(o8[4], o8[5], o8[6], o8[7]);
+      if (timing && threadIdx.x == 64) {
+        atomicAdd(p.timing + 19, static_cast<unsigned long long>(tw - tq));
+        atomicAdd(p.timing + 20, static_cast<unsigned long long>(clock64() - tw));
+      }
+      if (PAIR) mbar_arrive_cluster(mapa_u32(accempty_bar(as), 0));   // the leader counts the epilogue threads of both CTAs
+      else mbar_arrive(accempty_bar(as));
+      float mine[8];      // this thread's partials: P[cg] (16 warps) or P[2cg] + P[2cg+1] (8 warps)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mine[j] = NP == 2 ? o8[0][j] + o8[NP - 1][j] : o8[0][j];
+      if (cg > 0) {
+        float* d = s_o8 + (static_cast<size_t>(cg - 1) * T3_BM + row) * 8;
+        *reinterpret_cast<float4*>(d) = make_float4(mine[0], mine[1], mine[2], mine[3]);
+        *reinterpret_cast<float4*>(d + 4) = make_float4(mine[4], mine[5], mine[6], mine[7]);
       }
       asm volatile("bar.sync 2, %0;" ::"n"(T3_EPI_THREADS) : "memory");
-      if (hf == 0 && valid) {
-        const float4 p0 = *reinterpret_cast<const float4*>(s_o8 + row * 8);
-        const float4 p1 = *reinterpret_cast<const float4*>(s_o8 + row * 8 + 4);
+      if (cg == 0 && valid) {
+        float tot[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float s0 = s_o8[row * 8 + j];
+          if (T3_NCG == 2) tot[j] = mine[j] + s0;
+          else tot[j] = (mine[j] + s0) + (s_o8[(T3_BM + row) * 8 + j] + s_o8[(2 * T3_BM + row) * 8 + j]);
+        }
         float4* o = reinterpret_cast<float4*>(p.acc8 + q * p.acc8_stride + m * 8);
         float4 a0 = o[0], a1 = o[1];
-        a0.x += o8[0] + p0.x; a0.y += o8[1] + p0.y; a0.z += o8[2] + p0.z; a0.w += o8[3] + p0.w;
-        a1.x += o8[4] + p1.x; a1.y += o8[5] + p1.y; a1.z += o8[6] + p1.z; a1.w += o8[7] + p1.w;
+        a0.x += tot[0]; a0.y += tot[1]; a0.z += tot[2]; a0.w += tot[3];
+        a1.x += tot[4]; a1.y += tot[5]; a1.z += tot[6]; a1.w += tot[7];
         o[0] = a0; o[1] = a1;
       }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer may still be reading this CTA's shared memory / signalling its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (PAIR) tmem2_dealloc(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
-__global__ void __launch_bounds__(T3_THREADS, 1)
+template <bool PAIR = false, int EW = 8>
+__global__ void __launch_bounds__(t3_threads(EW), 1)
 tf32_res_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                 const __grid_constant__ CUtensorMap map_w2h, const __grid_constant__ CUtensorMap map_w2l,
                 const Tf32Params p) {
+  using G = T3RG<PAIR>;
+  static_assert(EW == 8 || EW == 16, "8 or 16 epilogue warps");
+  constexpr int T3_EPI_THREADS = EW * 32, T3_NCG = EW / 4;
+  constexpr int T3R_STAGES = G::STAGES, T3R_STAGE_BYTES = G::STAGE_BYTES, T3R_B_BYTES = G::B_BYTES;
+  constexpr int T3R_OFF_B2 = G::OFF_B2, T3R_OFF_BARS = G::OFF_BARS, T3R_NBARS = G::NBARS;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
   float* s_b2 = reinterpret_cast<float*>(smem + T3R_OFF_B2);
@@ -349,7 +469,12 @@ tf32_res_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
   auto accfull_bar = [&](int s) { return bar_base + 8u * (2 * T3R_STAGES + s); };
   auto accempty_bar = [&](int s) { return bar_base + 8u * (2 * T3R_STAGES + 2 + s); };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int item0 = PAIR ? blockIdx.x >> 1 : blockIdx.x, item_step = PAIR ? gridDim.x >> 1 : gridDim.x;
   if ((smem_base & 1023u) != 0u) __trap();
+  const bool timing = p.timing != nullptr;
+  const long long t_entry = timing ? clock64() : 0;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_ah); prefetch_tmap(&map_al); prefetch_tmap(&map_w2h); prefetch_tmap(&map_w2l);
@@ -359,134 +484,197 @@ tf32_res_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(accfull_bar(s), 1);
-      mbar_init(accempty_bar(s), T3_EPI_THREADS);
+      mbar_init(accempty_bar(s), (PAIR ? 2 : 1) * T3_EPI_THREADS);
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(tmem_slot), 256);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem2_alloc(smem_u32(tmem_slot), 256);
+      tmem2_relinquish();
+    } else {
+      tmem_alloc(smem_u32(tmem_slot), 256);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int n_items = p.n_tiles * p.n_chunks;
+  const int n_items = t3_n_items<PAIR>(p);
   const int kb2 = p.kb_conv;
 
   if (warp == 0) {
     uint32_t it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    long long t_wait = 0;
+    for (int item = item0; item < n_items; item += item_step) {
       int q, r, t0;
-      t3_item_coords(p, item, q, r, t0);
+      t3_item_coords<PAIR>(p, item, rank, q, r, t0);
       for (int kb = 0; kb < kb2; ++kb, ++it) {
         const int s = it % T3R_STAGES;
+        const long long tq = timing ? clock64() : 0;
         mbar_wait(empty_bar(s), ((it / T3R_STAGES) & 1) ^ 1);
+        if (timing) t_wait += clock64() - tq;
         if (elect_one()) {
-          mbar_expect_tx(full_bar(s), T3R_STAGE_BYTES);
+          if (leader) mbar_expect_tx(full_bar(s), (PAIR ? 2 : 1) * T3R_STAGE_BYTES);
+          const int bq = q * T3R_BN + (PAIR ? static_cast<int>(rank) * (T3R_BN / 2) : 0);
           const uint32_t a_hi = smem_base + s * T3R_STAGE_BYTES, a_lo = a_hi + T3_A_BYTES;
           const uint32_t b_hi = a_lo + T3_A_BYTES, b_lo = b_hi + T3R_B_BYTES;
-          tma_load_4d(a_hi, &map_ah, full_bar(s), kb * T3_BK, t0, r, 0);
-          tma_load_4d(a_lo, &map_al, full_bar(s), kb * T3_BK, t0, r, 0);
-          tma_load_2d(b_hi, &map_w2h, full_bar(s), kb * T3_BK, p.layer * p.C + q * T3R_BN);
-          tma_load_2d(b_lo, &map_w2l, full_bar(s), kb * T3_BK, p.layer * p.C + q * T3R_BN);
+          t3_load_4d<PAIR>(a_hi, &map_ah, full_bar(s), kb * T3_BK, t0, r, 0);
+          t3_load_4d<PAIR>(a_lo, &map_al, full_bar(s), kb * T3_BK, t0, r, 0);
+          t3_load_2d<PAIR>(b_hi, &map_w2h, full_bar(s), kb * T3_BK, p.layer * p.C + bq);
+          t3_load_2d<PAIR>(b_lo, &map_w2l, full_bar(s), kb * T3_BK, p.layer * p.C + bq);
         }
         __syncwarp();
       }
     }
+    if (timing && lane == 0) atomicAdd(p.timing + 38, static_cast<unsigned long long>(t_wait));
   } else if (warp == 1) {
-    constexpr uint32_t idesc = umma_idesc_tf32(T3_BM, T3R_BN);
+    constexpr uint32_t idesc = umma_idesc_tf32(PAIR ? 2 * T3_BM : T3_BM, T3R_BN);
     uint32_t it = 0, n = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+    long long t_full = 0, t_epi = 0;
+    const long long t_begin = timing ? clock64() : 0;
+    for (int item = item0; leader && item < n_items; item += item_step, ++n) {
       const uint32_t as = n & 1u;
+      long long tq = timing ? clock64() : 0;
       mbar_wait(accempty_bar(as), ((n >> 1) & 1u) ^ 1u);
+      if (timing) t_epi += clock64() - tq;
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + 128u * as;
       for (int kb = 0; kb < kb2; ++kb, ++it) {
         const int s = it % T3R_STAGES;
+        tq = timing ? clock64() : 0;
         mbar_wait(full_bar(s), (it / T3R_STAGES) & 1);
+        if (timing) t_full += clock64() - tq;
         tc_fence_after();
         const uint32_t base = smem_base + s * T3R_STAGE_BYTES;
         const uint64_t ahi = umma_desc_sw128(base), alo = umma_desc_sw128(base + T3_A_BYTES);
         const uint64_t bhi = umma_desc_sw128(base + 2 * T3_A_BYTES), blo = umma_desc_sw128(base + 2 * T3_A_BYTES + T3R_B_BYTES);
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < T3_BK / 8; ++k) umma_tf32(d_tmem, alo + 2 * k, bhi + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < T3_BK / 8; ++k) t3_mma<PAIR>(d_tmem, alo + 2 * k, bhi + 2 * k, idesc, (kb | k) ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < T3_BK / 8; ++k) umma_tf32(d_tmem, ahi + 2 * k, blo + 2 * k, idesc, 1u);
+          for (int k = 0; k < T3_BK / 8; ++k) t3_mma<PAIR>(d_tmem, ahi + 2 * k, blo + 2 * k, idesc, 1u);
 #pragma unroll
-          for (int k = 0; k < T3_BK / 8; ++k) umma_tf32(d_tmem, ahi + 2 * k, bhi + 2 * k, idesc, 1u);
-          tc_commit(empty_bar(s));
-          if (kb == kb2 - 1) tc_commit(accfull_bar(as));
+          for (int k = 0; k < T3_BK / 8; ++k) t3_mma<PAIR>(d_tmem, ahi + 2 * k, bhi + 2 * k, idesc, 1u);
+          t3_commit<PAIR>(empty_bar(s));
+          if (kb == kb2 - 1) t3_commit<PAIR>(accfull_bar(as));
         }
         __syncwarp();
+      }
+    }
+    if (timing && leader && n > 0) {
+      // the last accumulator is complete when its accfull barrier flips (this CTA's copy; waiting does not consume it)
+      mbar_wait(accfull_bar((n - 1) & 1u), ((n - 1) >> 1) & 1u);
+      if (lane == 0) {
+        atomicAdd(p.timing + 32, static_cast<unsigned long long>(clock64() - t_begin));
+        atomicAdd(p.timing + 33, static_cast<unsigned long long>(t_full));
+        atomicAdd(p.timing + 34, static_cast<unsigned long long>(t_epi));
+        atomicAdd(p.timing + 37, static_cast<unsigned long long>(t_begin - t_entry));
+        atomicAdd(p.timing + 39, 1ull);
       }
     }
   } else {
     const int we = warp - 2;
     const int quarter = warp & 3;
-    const int hf = we >> 2;             // which 64 of the item's 128 columns
+    const int cg = we >> 2;             // column group: CH of the item's 128 columns
+    constexpr int CH = T3R_BN / T3_NCG;
+    // With 32 columns per thread the residual stream's old value is fetched BEFORE the accumulator is waited for
+    // (it does not depend on this layer's MMAs): the loads' latency hides behind the MMAs instead of following them.
+    constexpr bool PREFETCH = CH <= 32;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     uint32_t n = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+    for (int item = item0; item < n_items; item += item_step, ++n) {
       int q, r, t0;
-      t3_item_coords(p, item, q, r, t0);
+      t3_item_coords<PAIR>(p, item, rank, q, r, t0);
       const uint32_t as = n & 1u;
       const bool in_range = (t0 + row) < p.T;
       const bool valid = t3_row_valid(p, t0 + row);
       const size_t m = static_cast<size_t>(r) * p.T + t0 + row;
+      const size_t off0 = m * p.C + q * T3R_BN + cg * CH;
       asm volatile("bar.sync 1, %0;" ::"n"(T3_EPI_THREADS) : "memory");
       for (int i = threadIdx.x - 64; i < T3R_BN; i += T3_EPI_THREADS) s_b2[i] = p.bias[q * T3R_BN + i];
       asm volatile("bar.sync 1, %0;" ::"n"(T3_EPI_THREADS) : "memory");
+      // h = h_hi + h_lo exactly
+      auto load_old = [&](size_t off, float* old) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const float4 oh = *reinterpret_cast<const float4*>(p.h_hi + off + 4 * v);
+          const float4 ol = *reinterpret_cast<const float4*>(p.h_lo + off + 4 * v);
+          old[4 * v] = oh.x + ol.x; old[4 * v + 1] = oh.y + ol.y; old[4 * v + 2] = oh.z + ol.z; old[4 * v + 3] = oh.w + ol.w;
+        }
+      };
+      float pre[PREFETCH ? CH : 16];
+      if (PREFETCH && valid) {
+#pragma unroll
+        for (int g = 0; g < CH / 16; ++g) load_old(off0 + g * 16, pre + g * 16);
+      }
+      const long long tq = timing ? clock64() : 0;
       mbar_wait(accfull_bar(as), (n >> 1) & 1u);
+      const long long tw = timing ? clock64() : 0;
       tc_fence_after();
-      const uint32_t taddr = tmem_base + lane_addr + 128u * as + hf * 64;
+      const uint32_t taddr = tmem_base + lane_addr + 128u * as + cg * CH;
+      auto finish = [&](int g, const uint32_t* rr, const float* old) {
+        if (!in_range) return;
+        const size_t off = off0 + g * 16;
+        float hi[16], lo[16];
+        if (valid) {
+          // h_new = (acts @ Wres + b) + h   (waveglow_arch.py:131-133)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float x = (__uint_as_float(rr[j]) + s_b2[cg * CH + g * 16 + j]) + old[j];
+            hi[j] = tf32_rna(x);
+            lo[j] = x - hi[j];
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) hi[j] = lo[j] = 0.f;     // gap row: the next layer's zero padding
+        }
+        float4* dh = reinterpret_cast<float4*>(p.ho_hi + off);
+        float4* dl = reinterpret_cast<float4*>(p.ho_lo + off);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          dh[v] = make_float4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
+          dl[v] = make_float4(lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
+        }
+      };
+      if (PREFETCH) {
+#pragma unroll
+        for (int g = 0; g < CH / 16; ++g) {
+          uint32_t rr[16];
+          tmem_ld16(taddr + g * 16, rr);
+          tmem_ld_wait();
+          finish(g, rr, pre + g * 16);
+        }
+      } else {
 #pragma unroll 1
-      for (int g = 0; g < 4; ++g) {
-        uint32_t rr[16];
-        tmem_ld16(taddr + g * 16, rr);
-        tmem_ld_wait();
-        if (in_range) {
-          const int c0 = q * T3R_BN + hf * 64 + g * 16;
-          const size_t off = m * p.C + c0;
-          float hi[16], lo[16];
-          if (valid) {
-            // h_new = (acts @ Wres + b) + h   with h = h_hi + h_lo exactly (waveglow_arch.py:131-133)
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              const float4 oh = *reinterpret_cast<const float4*>(p.h_hi + off + 4 * v);
-              const float4 ol = *reinterpret_cast<const float4*>(p.h_lo + off + 4 * v);
-              const float old[4] = {oh.x + ol.x, oh.y + ol.y, oh.z + ol.z, oh.w + ol.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float x = (__uint_as_float(rr[4 * v + j]) + s_b2[hf * 64 + g * 16 + 4 * v + j]) + old[j];
-                hi[4 * v + j] = tf32_rna(x);
-                lo[4 * v + j] = x - hi[4 * v + j];
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) hi[j] = lo[j] = 0.f;     // gap row: the next layer's zero padding
-          }
-          float4* dh = reinterpret_cast<float4*>(p.ho_hi + off);
-          float4* dl = reinterpret_cast<float4*>(p.ho_lo + off);
-#pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            dh[v] = make_float4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
-            dl[v] = make_float4(lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
-          }
+        for (int g = 0; g < CH / 16; ++g) {
+          uint32_t rr[16];
+          tmem_ld16(taddr + g * 16, rr);
+          tmem_ld_wait();
+          float old[16];
+          if (in_range && valid) load_old(off0 + g * 16, old);
+          finish(g, rr, old);
         }
       }
       tc_fence_before();
-      mbar_arrive(accempty_bar(as));
+      if (timing && threadIdx.x == 64) {
+        atomicAdd(p.timing + 35, static_cast<unsigned long long>(tw - tq));
+        atomicAdd(p.timing + 36, static_cast<unsigned long long>(clock64() - tw));
+      }
+      if (PAIR) mbar_arrive_cluster(mapa_u32(accempty_bar(as), 0));
+      else mbar_arrive(accempty_bar(as));
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    if (PAIR) tmem2_dealloc(tmem_base, 256);
+    else tmem_dealloc(tmem_base, 256);
   }
 }
 
@@ -550,20 +738,71 @@ inline void make_map_f32_4d(CUtensorMap* m, const void* ptr, uint64_t phases, ui
   make_map_f32(m, ptr, 4, dims, box);
 }
 
-inline void tf32_init() {
-  WG_CK(cudaFuncSetAttribute(tf32_gate_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3G<32>::SMEM));
-  WG_CK(cudaFuncSetAttribute(tf32_gate_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3G<32>::SMEM));
-  WG_CK(cudaFuncSetAttribute(tf32_gate_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3G<16>::SMEM));
-  WG_CK(cudaFuncSetAttribute(tf32_gate_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3G<16>::SMEM));
-  WG_CK(cudaFuncSetAttribute(tf32_res_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T3R_SMEM));
+// launch with an optional cluster of 2 (the CTA-pair variants)
+template <typename... KArgs, typename... Args>
+inline void t3_launch(void (*kernel)(KArgs...), int grid, int ew, size_t smem, cudaStream_t st, bool pair, const Args&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(t3_threads(ew));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pair ? 1 : 0;
+  WG_CK(cudaLaunchKernelEx(&cfg, kernel, args...));
+}
+
+template <typename K>
+inline int t3_max_pairs(K kernel, int ew, size_t smem) {
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.gridDim = dim3(2 * 1024); cfg.blockDim = dim3(t3_threads(ew)); cfg.dynamicSmemBytes = smem;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  return n;
+}
+
+// Returns how many CTA pairs of the tf32 kernels can be resident at once (0: pairs unavailable); see tc_pair_init().
+inline int tf32_init() {
+#define WG_T3_ATTR(K, BYTES) WG_CK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES))
+#define WG_T3_ATTRS(EWV)                                                                   \
+  WG_T3_ATTR((tf32_gate_kernel<false, 32, false, EWV>), (T3G<32, false>::SMEM));           \
+  WG_T3_ATTR((tf32_gate_kernel<true, 32, false, EWV>), (T3G<32, false>::SMEM));            \
+  WG_T3_ATTR((tf32_gate_kernel<false, 16, false, EWV>), (T3G<16, false>::SMEM));           \
+  WG_T3_ATTR((tf32_gate_kernel<true, 16, false, EWV>), (T3G<16, false>::SMEM));            \
+  WG_T3_ATTR((tf32_gate_kernel<false, 32, true, EWV>), (T3G<32, true>::SMEM));             \
+  WG_T3_ATTR((tf32_gate_kernel<true, 32, true, EWV>), (T3G<32, true>::SMEM));              \
+  WG_T3_ATTR((tf32_gate_kernel<false, 16, true, EWV>), (T3G<16, true>::SMEM));             \
+  WG_T3_ATTR((tf32_gate_kernel<true, 16, true, EWV>), (T3G<16, true>::SMEM));              \
+  WG_T3_ATTR((tf32_res_kernel<false, EWV>), T3RG<false>::SMEM);                            \
+  WG_T3_ATTR((tf32_res_kernel<true, EWV>), T3RG<true>::SMEM)
+  WG_T3_ATTRS(8);
+  WG_T3_ATTRS(16);
+#undef WG_T3_ATTRS
+#undef WG_T3_ATTR
+  const int a = t3_max_pairs(tf32_gate_kernel<false, 32, true, 16>, 16, T3G<32, true>::SMEM);
+  const int b = t3_max_pairs(tf32_res_kernel<true, 16>, 16, T3RG<true>::SMEM);
+  return a < b ? a : b;
 }
 
 struct Tf32Plan {
   CUtensorMap m_h_hi[2], m_h_lo[2], m_c_hi, m_c_lo, m_w1h, m_w1l, m_vh, m_vl, m_a_hi, m_a_lo, m_w2h, m_w2l;
+  CUtensorMap p_w1h, p_w1l, p_vh, p_vl, p_w2h, p_w2l;   // CTA-pair variants: boxes of HALF a chunk's B rows
+  int max_pairs = 0;     // resident CTA pairs (tf32_init); 0 = single-CTA kernels only
+  bool pair = false;     // this plan runs the CTA-pair kernels
+  int epi_warps = 0;     // 0 = by shape (16 when every CTA runs one item, else 8); 8 / 16 force (WG_TF32_EPI, A/B)
   Tf32Params base{};
   RowGeom geo1{};
   int sm_count = 0, n_mel = 0, Kup = 0;
-  int gate_bk = 16;      // K-block width of the gate kernel (WG_TF32_BK=32 selects the 2-stage SWIZZLE_128B variant)
+  int gate_bk = 32;      // K-block width of the gate kernel (WG_TF32_BK=16: SWIZZLE_64B ring of twice as many, half-size stages)
   float *h_hi[2] = {nullptr, nullptr}, *h_lo[2] = {nullptr, nullptr}, *aup_hi = nullptr, *aup_lo = nullptr;
 };
 
@@ -577,9 +816,10 @@ struct Tf32Weights {   // device pointers, stacked over all layers
 inline void tf32_prepare(Tf32Plan& pl, int sm_count, int C, int R, int Kup, int n_mel, int n_layers_total, int rows1,
                          const RowGeom& geo1, int Tp, int Tv, const Tf32Weights& w, float* h_hi0, float* h_hi1,
                          float* h_lo0, float* h_lo1, float* aup_hi, float* aup_lo, float* acts_hi, float* acts_lo,
-                         float* acc8, size_t acc8_stride, int gate_bk = 16) {
+                         float* acc8, size_t acc8_stride, int gate_bk = 32, int max_pairs = 0, int pair_policy = -1, int epi_warps = 0) {
   if (C % 128 || Kup % T3_BK) fail(WG_ERR_UNSUPPORTED, "tf32x3 path needs n_channels %% 128 == 0 (got %d)", C);
-  pl.gate_bk = gate_bk == 32 ? 32 : 16;
+  pl.gate_bk = gate_bk == 16 ? 16 : 32;
+  pl.epi_warps = epi_warps;
   const int gbk = pl.gate_bk;
   pl.sm_count = sm_count; pl.n_mel = n_mel; pl.Kup = Kup; pl.geo1 = geo1;
   pl.h_hi[0] = h_hi0; pl.h_hi[1] = h_hi1; pl.h_lo[0] = h_lo0; pl.h_lo[1] = h_lo1; pl.aup_hi = aup_hi; pl.aup_lo = aup_lo;
@@ -601,6 +841,21 @@ inline void tf32_prepare(Tf32Plan& pl, int sm_count, int C, int R, int Kup, int 
   make_map_f32_2d(&pl.m_vl, w.Vl, (uint64_t)n_layers_total * R * 2 * C, Kup, T3G_BN, gbk);
   make_map_f32_2d(&pl.m_w2h, w.W2h, (uint64_t)n_layers_total * C, C, T3R_BN);
   make_map_f32_2d(&pl.m_w2l, w.W2l, (uint64_t)n_layers_total * C, C, T3R_BN);
+  make_map_f32_2d(&pl.p_w1h, w.W1h, (uint64_t)n_layers_total * 2 * C, 3 * C, T3G_BN / 2, gbk);
+  make_map_f32_2d(&pl.p_w1l, w.W1l, (uint64_t)n_layers_total * 2 * C, 3 * C, T3G_BN / 2, gbk);
+  make_map_f32_2d(&pl.p_vh, w.Vh, (uint64_t)n_layers_total * R * 2 * C, Kup, T3G_BN / 2, gbk);
+  make_map_f32_2d(&pl.p_vl, w.Vl, (uint64_t)n_layers_total * R * 2 * C, Kup, T3G_BN / 2, gbk);
+  make_map_f32_2d(&pl.p_w2h, w.W2h, (uint64_t)n_layers_total * C, C, T3R_BN / 2);
+  make_map_f32_2d(&pl.p_w2l, w.W2l, (uint64_t)n_layers_total * C, C, T3R_BN / 2);
+  // CTA pairs halve the B bytes each SM pulls in and reads per MMA (the single-CTA kernel is bound by its operand feed);
+  // a pair needs two tiles of one phase, so an odd tile count per phase block costs a ghost tile. pair_policy: 1 / 0
+  // force, -1 = by wave count: (pair items / resident pairs) waves at ~0.7 of a single-CTA wave (measured).
+  pl.max_pairs = max_pairs;
+  const int n_chunks = 2 * C / T3G_BN;
+  const long items1 = (long)p.n_tiles * n_chunks, items2 = (long)((p.tiles_per_row + 1) / 2) * R * n_chunks;
+  const long waves1 = (items1 + sm_count - 1) / sm_count;
+  const long waves2 = max_pairs > 0 ? (items2 + max_pairs - 1) / max_pairs : 0;
+  pl.pair = max_pairs > 0 && (pair_policy == 1 || (pair_policy < 0 && 0.7 * (double)waves2 < (double)waves1));
 }
 
 inline int tf32_upsample(const Tf32Plan& pl, const float* mel, cudaStream_t st) {
@@ -612,17 +867,42 @@ inline int tf32_upsample(const Tf32Plan& pl, const float* mel, cudaStream_t st) 
 
 // One WN layer: gate kernel (+ residual kernel unless it is the flow's last layer). Returns the launch count.
 inline int tf32_wn_layer(const Tf32Plan& pl, int layer, int dilation, bool last, int hcur, const float* b1, const float* b2,
-                         const float* wse, cudaStream_t st) {
+                         const float* wse, cudaStream_t st, unsigned long long* timing = nullptr) {
   Tf32Params g = pl.base;
+  g.timing = timing;
   g.layer = layer; g.dilation = dilation;
   g.n_chunks = 2 * g.C / T3G_BN; g.kb_conv = 3 * g.C / pl.gate_bk; g.kb_cond = pl.Kup / pl.gate_bk;
   g.wc_row0 = layer * g.R * 2 * g.C; g.wc_rstride = 2 * g.C;
   g.bias = b1; g.wse = wse;
-  const int items_g = g.n_tiles * g.n_chunks;
-  const int grid_g = items_g < pl.sm_count ? items_g : pl.sm_count;
-#define WG_T3G_LAUNCH(LASTV, BKV)                                                                                          \
-  tf32_gate_kernel<LASTV, BKV><<<grid_g, T3_THREADS, T3G<BKV>::SMEM, st>>>(pl.m_h_hi[hcur], pl.m_h_lo[hcur], pl.m_c_hi, pl.m_c_lo, \
-                                                                           pl.m_w1h, pl.m_w1l, pl.m_vh, pl.m_vl, g)
+  const bool pair = pl.pair;
+  auto grid_for = [&](const Tf32Params& q) {
+    if (pair) {
+      const int items = ((q.tiles_per_row + 1) / 2) * q.R * q.n_chunks;
+      return 2 * (items < pl.max_pairs ? items : pl.max_pairs);
+    }
+    const int items = q.n_tiles * q.n_chunks;
+    return items < pl.sm_count ? items : pl.sm_count;
+  };
+  // 16 epilogue warps when every CTA runs ONE item (nothing to hide the epilogue behind), else 8
+  auto one_item = [&](const Tf32Params& q) {
+    return pair ? ((q.tiles_per_row + 1) / 2) * q.R * q.n_chunks <= pl.max_pairs : q.n_tiles * q.n_chunks <= pl.sm_count;
+  };
+  const int grid_g = grid_for(g);
+  const bool wide_g = pl.epi_warps == 16 || (pl.epi_warps == 0 && one_item(g));
+#define WG_T3G_LAUNCH2(LASTV, BKV, EWV)                                                                               \
+  do {                                                                                                                \
+    if (pair)                                                                                                         \
+      t3_launch(tf32_gate_kernel<LASTV, BKV, true, EWV>, grid_g, EWV, T3G<BKV, true>::SMEM, st, true, pl.m_h_hi[hcur], \
+                pl.m_h_lo[hcur], pl.m_c_hi, pl.m_c_lo, pl.p_w1h, pl.p_w1l, pl.p_vh, pl.p_vl, g);                      \
+    else                                                                                                              \
+      t3_launch(tf32_gate_kernel<LASTV, BKV, false, EWV>, grid_g, EWV, T3G<BKV, false>::SMEM, st, false,              \
+                pl.m_h_hi[hcur], pl.m_h_lo[hcur], pl.m_c_hi, pl.m_c_lo, pl.m_w1h, pl.m_w1l, pl.m_vh, pl.m_vl, g);     \
+  } while (0)
+#define WG_T3G_LAUNCH(LASTV, BKV)              \
+  do {                                         \
+    if (wide_g) WG_T3G_LAUNCH2(LASTV, BKV, 16); \
+    else WG_T3G_LAUNCH2(LASTV, BKV, 8);         \
+  } while (0)
   if (pl.gate_bk == 32) {
     if (last) WG_T3G_LAUNCH(true, 32);
     else WG_T3G_LAUNCH(false, 32);
@@ -631,16 +911,25 @@ inline int tf32_wn_layer(const Tf32Plan& pl, int layer, int dilation, bool last,
     else WG_T3G_LAUNCH(false, 16);
   }
 #undef WG_T3G_LAUNCH
+#undef WG_T3G_LAUNCH2
   WG_CK(cudaGetLastError());
   if (last) return 1;
   Tf32Params r = pl.base;
+  r.timing = timing;
   r.layer = layer; r.dilation = dilation;
   r.n_chunks = r.C / T3R_BN; r.kb_conv = r.C / T3_BK; r.kb_cond = 0;
   r.bias = b2;
   r.h_hi = pl.h_hi[hcur]; r.h_lo = pl.h_lo[hcur]; r.ho_hi = pl.h_hi[hcur ^ 1]; r.ho_lo = pl.h_lo[hcur ^ 1];
-  const int items_r = r.n_tiles * r.n_chunks;
-  const int grid_r = items_r < pl.sm_count ? items_r : pl.sm_count;
-  tf32_res_kernel<<<grid_r, T3_THREADS, T3R_SMEM, st>>>(pl.m_a_hi, pl.m_a_lo, pl.m_w2h, pl.m_w2l, r);
+  const int grid_r = grid_for(r);
+  const bool wide_r = pl.epi_warps == 16 || (pl.epi_warps == 0 && one_item(r));
+#define WG_T3R_LAUNCH(EWV)                                                                                                      \
+  do {                                                                                                                          \
+    if (pair) t3_launch(tf32_res_kernel<true, EWV>, grid_r, EWV, T3RG<true>::SMEM, st, true, pl.m_a_hi, pl.m_a_lo, pl.p_w2h, pl.p_w2l, r);   \
+    else t3_launch(tf32_res_kernel<false, EWV>, grid_r, EWV, T3RG<false>::SMEM, st, false, pl.m_a_hi, pl.m_a_lo, pl.m_w2h, pl.m_w2l, r);     \
+  } while (0)
+  if (wide_r) WG_T3R_LAUNCH(16);
+  else WG_T3R_LAUNCH(8);
+#undef WG_T3R_LAUNCH
   WG_CK(cudaGetLastError());
   return 2;
 }
