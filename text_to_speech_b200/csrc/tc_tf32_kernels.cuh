@@ -47,6 +47,9 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
+__device__ __forceinline__ void st_shared_f4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
@@ -194,6 +197,7 @@ tf32_gate_kernel(const __grid_constant__ CUtensorMap map_hh, const __grid_consta
                  const __grid_constant__ CUtensorMap map_ch, const __grid_constant__ CUtensorMap map_cl,
                  const __grid_constant__ CUtensorMap map_w1h, const __grid_constant__ CUtensorMap map_w1l,
                  const __grid_constant__ CUtensorMap map_vh, const __grid_constant__ CUtensorMap map_vl,
+                 const __grid_constant__ CUtensorMap smap_hi, const __grid_constant__ CUtensorMap smap_lo,
                  const Tf32Params p) {
   using G = T3G<BK, PAIR>;
   static_assert(EW == 8 || EW == 16, "8 or 16 epilogue warps");
@@ -341,6 +345,11 @@ tf32_gate_kernel(const __grid_constant__ CUtensorMap map_hh, const __grid_consta
     const int quarter = warp & 3;       // TMEM lane quarter this warp may access
     const int cg = we >> 2;             // column group: CH of the chunk's 128 gate channels
     constexpr int CH = 128 / T3_NCG, NP = CH / 32;   // channels per thread; 32-channel fold partials per thread
+    // One item per CTA (the 16-warp case): once the accumulator is complete the operand ring is idle, so each warp
+    // stages its 32 x 32 (hi, lo) output tiles there (128-byte swizzled rows) and writes them with two TMA stores
+    // instead of 16 row-strided 16-byte stores per thread (32 half-filled sectors per instruction).
+    const bool stage_out = !LAST && EW == 16 && n_items <= item_step;
+    const uint32_t stg_hi = smem_base + static_cast<uint32_t>(we) * 8192u, stg_lo = stg_hi + 4096u;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     uint32_t n = 0;
@@ -389,21 +398,39 @@ tf32_gate_kernel(const __grid_constant__ CUtensorMap map_hh, const __grid_consta
             o8[pi][4] = fmaf(a[j], w1.x, o8[pi][4]); o8[pi][5] = fmaf(a[j], w1.y, o8[pi][5]);
             o8[pi][6] = fmaf(a[j], w1.z, o8[pi][6]); o8[pi][7] = fmaf(a[j], w1.w, o8[pi][7]);
           }
-          if (!LAST && (t0 + row) < p.T) {
+          if (!LAST && (stage_out || (t0 + row) < p.T)) {
             float hi[16], lo[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               hi[j] = valid ? tf32_rna(a[j]) : 0.f;
               lo[j] = valid ? a[j] - hi[j] : 0.f;
             }
-            float4* dh = reinterpret_cast<float4*>(p.acts_hi + m * p.C + q * 128 + ch0);
-            float4* dl = reinterpret_cast<float4*>(p.acts_lo + m * p.C + q * 128 + ch0);
+            if (stage_out) {
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              dh[v] = make_float4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
-              dl[v] = make_float4(lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
+              for (int v = 0; v < 4; ++v) {
+                const uint32_t o = static_cast<uint32_t>(lane) * 128u + (static_cast<uint32_t>((g2 * 4 + v) ^ (lane & 7)) << 4);
+                st_shared_f4(stg_hi + o, hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
+                st_shared_f4(stg_lo + o, lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
+              }
+            } else {
+              float4* dh = reinterpret_cast<float4*>(p.acts_hi + m * p.C + q * 128 + ch0);
+              float4* dl = reinterpret_cast<float4*>(p.acts_lo + m * p.C + q * 128 + ch0);
+#pragma unroll
+              for (int v = 0; v < 4; ++v) {
+                dh[v] = make_float4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
+                dl[v] = make_float4(lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
+              }
             }
           }
+        }
+      }
+      if (stage_out) {       // rows beyond the phase block are clipped by the TMA store
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(&smap_hi, stg_hi, q * 128 + cg * CH, t0 + quarter * 32, r, 0);
+          tma_store_4d(&smap_lo, stg_lo, q * 128 + cg * CH, t0 + quarter * 32, r, 0);
+          bulk_commit();
         }
       }
       tc_fence_before();
@@ -437,6 +464,7 @@ tf32_gate_kernel(const __grid_constant__ CUtensorMap map_hh, const __grid_consta
         o[0] = a0; o[1] = a1;
       }
     }
+    if (stage_out && lane == 0) bulk_wait0();
   }
   tc_fence_before();
   __syncthreads();
@@ -452,6 +480,7 @@ template <bool PAIR = false, int EW = 8>
 __global__ void __launch_bounds__(t3_threads(EW), 1)
 tf32_res_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                 const __grid_constant__ CUtensorMap map_w2h, const __grid_constant__ CUtensorMap map_w2l,
+                const __grid_constant__ CUtensorMap smap_hi, const __grid_constant__ CUtensorMap smap_lo,
                 const Tf32Params p) {
   using G = T3RG<PAIR>;
   static_assert(EW == 8 || EW == 16, "8 or 16 epilogue warps");
@@ -583,6 +612,8 @@ tf32_res_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
     // With 32 columns per thread the residual stream's old value is fetched BEFORE the accumulator is waited for
     // (it does not depend on this layer's MMAs): the loads' latency hides behind the MMAs instead of following them.
     constexpr bool PREFETCH = CH <= 32;
+    const bool stage_out = EW == 16 && n_items <= item_step;   // see tf32_gate_kernel
+    const uint32_t stg_hi = smem_base + static_cast<uint32_t>(we) * 8192u, stg_lo = stg_hi + 4096u;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     uint32_t n = 0;
@@ -617,7 +648,7 @@ tf32_res_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
       tc_fence_after();
       const uint32_t taddr = tmem_base + lane_addr + 128u * as + cg * CH;
       auto finish = [&](int g, const uint32_t* rr, const float* old) {
-        if (!in_range) return;
+        if (!in_range && !stage_out) return;
         const size_t off = off0 + g * 16;
         float hi[16], lo[16];
         if (valid) {
@@ -631,6 +662,15 @@ tf32_res_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) hi[j] = lo[j] = 0.f;     // gap row: the next layer's zero padding
+        }
+        if (stage_out) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const uint32_t o = static_cast<uint32_t>(lane) * 128u + (static_cast<uint32_t>((g * 4 + v) ^ (lane & 7)) << 4);
+            st_shared_f4(stg_hi + o, hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
+            st_shared_f4(stg_lo + o, lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
+          }
+          return;
         }
         float4* dh = reinterpret_cast<float4*>(p.ho_hi + off);
         float4* dl = reinterpret_cast<float4*>(p.ho_lo + off);
@@ -659,6 +699,15 @@ tf32_res_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
           finish(g, rr, old);
         }
       }
+      if (stage_out) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(&smap_hi, stg_hi, q * T3R_BN + cg * CH, t0 + quarter * 32, r, 0);
+          tma_store_4d(&smap_lo, stg_lo, q * T3R_BN + cg * CH, t0 + quarter * 32, r, 0);
+          bulk_commit();
+        }
+      }
       tc_fence_before();
       if (timing && threadIdx.x == 64) {
         atomicAdd(p.timing + 35, static_cast<unsigned long long>(tw - tq));
@@ -667,6 +716,7 @@ tf32_res_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
       if (PAIR) mbar_arrive_cluster(mapa_u32(accempty_bar(as), 0));
       else mbar_arrive(accempty_bar(as));
     }
+    if (stage_out && lane == 0) bulk_wait0();
   }
   tc_fence_before();
   __syncthreads();
@@ -796,6 +846,7 @@ inline int tf32_init() {
 struct Tf32Plan {
   CUtensorMap m_h_hi[2], m_h_lo[2], m_c_hi, m_c_lo, m_w1h, m_w1l, m_vh, m_vl, m_a_hi, m_a_lo, m_w2h, m_w2l;
   CUtensorMap p_w1h, p_w1l, p_vh, p_vl, p_w2h, p_w2l;   // CTA-pair variants: boxes of HALF a chunk's B rows
+  CUtensorMap s_a_hi, s_a_lo, s_h_hi[2], s_h_lo[2];     // 32 x 32 boxes for the staged TMA stores of the epilogues
   int max_pairs = 0;     // resident CTA pairs (tf32_init); 0 = single-CTA kernels only
   bool pair = false;     // this plan runs the CTA-pair kernels
   int epi_warps = 0;     // 0 = by shape (16 when every CTA runs one item, else 8); 8 / 16 force (WG_TF32_EPI, A/B)
@@ -841,6 +892,16 @@ inline void tf32_prepare(Tf32Plan& pl, int sm_count, int C, int R, int Kup, int 
   make_map_f32_2d(&pl.m_vl, w.Vl, (uint64_t)n_layers_total * R * 2 * C, Kup, T3G_BN, gbk);
   make_map_f32_2d(&pl.m_w2h, w.W2h, (uint64_t)n_layers_total * C, C, T3R_BN);
   make_map_f32_2d(&pl.m_w2l, w.W2l, (uint64_t)n_layers_total * C, C, T3R_BN);
+  {
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)rows1, (uint64_t)R, 1};
+    const uint32_t box[4] = {32, 32, 1, 1};
+    make_map_f32(&pl.s_a_hi, acts_hi, 4, dims, box);
+    make_map_f32(&pl.s_a_lo, acts_lo, 4, dims, box);
+    for (int i = 0; i < 2; ++i) {
+      make_map_f32(&pl.s_h_hi[i], pl.h_hi[i], 4, dims, box);
+      make_map_f32(&pl.s_h_lo[i], pl.h_lo[i], 4, dims, box);
+    }
+  }
   make_map_f32_2d(&pl.p_w1h, w.W1h, (uint64_t)n_layers_total * 2 * C, 3 * C, T3G_BN / 2, gbk);
   make_map_f32_2d(&pl.p_w1l, w.W1l, (uint64_t)n_layers_total * 2 * C, 3 * C, T3G_BN / 2, gbk);
   make_map_f32_2d(&pl.p_vh, w.Vh, (uint64_t)n_layers_total * R * 2 * C, Kup, T3G_BN / 2, gbk);
@@ -893,10 +954,11 @@ inline int tf32_wn_layer(const Tf32Plan& pl, int layer, int dilation, bool last,
   do {                                                                                                                \
     if (pair)                                                                                                         \
       t3_launch(tf32_gate_kernel<LASTV, BKV, true, EWV>, grid_g, EWV, T3G<BKV, true>::SMEM, st, true, pl.m_h_hi[hcur], \
-                pl.m_h_lo[hcur], pl.m_c_hi, pl.m_c_lo, pl.p_w1h, pl.p_w1l, pl.p_vh, pl.p_vl, g);                      \
+                pl.m_h_lo[hcur], pl.m_c_hi, pl.m_c_lo, pl.p_w1h, pl.p_w1l, pl.p_vh, pl.p_vl, pl.s_a_hi, pl.s_a_lo, g);                      \
     else                                                                                                              \
       t3_launch(tf32_gate_kernel<LASTV, BKV, false, EWV>, grid_g, EWV, T3G<BKV, false>::SMEM, st, false,              \
-                pl.m_h_hi[hcur], pl.m_h_lo[hcur], pl.m_c_hi, pl.m_c_lo, pl.m_w1h, pl.m_w1l, pl.m_vh, pl.m_vl, g);     \
+                pl.m_h_hi[hcur], pl.m_h_lo[hcur], pl.m_c_hi, pl.m_c_lo, pl.m_w1h, pl.m_w1l, pl.m_vh, pl.m_vl, pl.s_a_hi,  \
+                pl.s_a_lo, g);     \
   } while (0)
 #define WG_T3G_LAUNCH(LASTV, BKV)              \
   do {                                         \
@@ -924,8 +986,8 @@ inline int tf32_wn_layer(const Tf32Plan& pl, int layer, int dilation, bool last,
   const bool wide_r = pl.epi_warps == 16 || (pl.epi_warps == 0 && one_item(r));
 #define WG_T3R_LAUNCH(EWV)                                                                                                      \
   do {                                                                                                                          \
-    if (pair) t3_launch(tf32_res_kernel<true, EWV>, grid_r, EWV, T3RG<true>::SMEM, st, true, pl.m_a_hi, pl.m_a_lo, pl.p_w2h, pl.p_w2l, r);   \
-    else t3_launch(tf32_res_kernel<false, EWV>, grid_r, EWV, T3RG<false>::SMEM, st, false, pl.m_a_hi, pl.m_a_lo, pl.m_w2h, pl.m_w2l, r);     \
+    if (pair) t3_launch(tf32_res_kernel<true, EWV>, grid_r, EWV, T3RG<true>::SMEM, st, true, pl.m_a_hi, pl.m_a_lo, pl.p_w2h, pl.p_w2l, pl.s_h_hi[hcur ^ 1], pl.s_h_lo[hcur ^ 1], r);   \
+    else t3_launch(tf32_res_kernel<false, EWV>, grid_r, EWV, T3RG<false>::SMEM, st, false, pl.m_a_hi, pl.m_a_lo, pl.m_w2h, pl.m_w2l, pl.s_h_hi[hcur ^ 1], pl.s_h_lo[hcur ^ 1], r);     \
   } while (0)
   if (wide_r) WG_T3R_LAUNCH(16);
   else WG_T3R_LAUNCH(8);
