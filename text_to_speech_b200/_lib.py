@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("WG_LIB_PATH") or os.path.join(_HERE, "libwg_b200.so")
 SOURCES = [os.path.join(_HERE, "csrc", "engine.cu"), os.path.join(_HERE, "csrc", "mel.cu"),
            os.path.join(_HERE, "csrc", "taco.cu")]
-HEADERS = [os.path.join(_HERE, "csrc", f) for f in ("common.cuh", "simt_kernels.cuh", "tc_kernels.cuh", "tc_pair_kernels.cuh", "tc_c512_kernels.cuh", "tc_tf32_kernels.cuh")] + \
+HEADERS = [os.path.join(_HERE, "csrc", f) for f in ("common.cuh", "simt_kernels.cuh", "tc_kernels.cuh", "tc_pair_kernels.cuh", "tc_c512_kernels.cuh", "tc_tf32_kernels.cuh", "tc_tf32_flow_kernel.cuh")] + \
           [os.path.join(os.path.dirname(_HERE), "include", f) for f in ("wg_b200.h", "wg_mel_b200.h", "wg_taco_b200.h")]
 
 WG_OK = 0

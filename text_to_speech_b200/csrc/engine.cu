@@ -23,6 +23,7 @@
 #include "tc_pair_kernels.cuh"
 #include "tc_c512_kernels.cuh"
 #include "tc_tf32_kernels.cuh"
+#include "tc_tf32_flow_kernel.cuh"
 
 namespace {
 
@@ -103,10 +104,13 @@ struct wg_engine {
   int dbg_flags = 0;                      // WG_DEBUG_FLAGS, honoured only by a -DWG_PROBES build (WnLayerParams::flags)
   int pair_policy = -1;                   // WG_PAIR: 1 = CTA-pair (cta_group::2) layer kernel, 0 = single-CTA kernel, -1 = default
   int pair_max = 0;                       // CTA pairs that can be resident at once on this device (tc_pair_init)
+  int last_flow_kernel = 0;               // the last wg_infer ran its flows on tf32_flow_kernel
   int last_pair = 0;                      // the last wg_infer ran its layers on the CTA-pair kernel
   int pair_epi_warps = 8;                 // WG_PAIR_EPI=16: 16 epilogue warps in the pair kernel
   bool pdl = true;                        // WG_PDL=0: no programmatic dependent launch of the BF16 layer kernels (A/B)
   int t3_gate_bk = 32;                    // WG_TF32_BK=16: SWIZZLE_64B ring of 16-float K-blocks in the tf32x3 gate kernel (A/B)
+  Tf32FlowState t3_flow;                  // one-launch-per-flow kernel for single-wave tf32x3 calls (tc_tf32_flow_kernel.cuh)
+  int t3_flow_policy = -1;                // WG_TF32_FLOW: 0 = per-layer kernels only, 1 / -1 = flow kernel where it fits
   int t3_epi_warps = 0;                   // WG_TF32_EPI=8 / 16: force the epilogue warp count of the tf32x3 kernels (A/B)
   int t3_max_pairs = 0;                   // resident CTA pairs of the tf32x3 kernels (tf32_init)
   bool profiling = false;
@@ -394,6 +398,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
                  reinterpret_cast<float*>(base + w.t3_ahi), reinterpret_cast<float*>(base + w.t3_alo), acc8, t3_acc_stride,
                  e->t3_gate_bk, e->t3_max_pairs, e->pair_policy, e->t3_epi_warps);
     e->last_pair = plan3.pair ? 1 : 0;
+    e->last_flow_kernel = 0;
     e->launches += tf32_upsample(plan3, mel, st);
   } else if (ffma) {
     GemmArgs g{};
@@ -479,6 +484,22 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
       const LayerW& lw = e->layers[k * c.n_layers + i];
       const int d = 1 << i;
       const bool last = i == c.n_layers - 1;
+      if (tf32 && i == 0 && e->t3_flow_policy != 0 && !(k == stop_flow && stop_layer >= 0) &&
+          tf32_flow_fits(plan3, e->t3_flow.max_pairs, c.n_layers)) {
+        // single-wave call: the whole flow as ONE persistent launch (grid barriers instead of kernel boundaries)
+        const float *b1s[T3F_MAX_LAYERS], *b2s[T3F_MAX_LAYERS], *wses[T3F_MAX_LAYERS];
+        for (int j = 0; j < c.n_layers; ++j) {
+          const LayerW& lj = e->layers[k * c.n_layers + j];
+          b1s[j] = lj.b1_pm; b2s[j] = lj.b2; wses[j] = lj.wse_d;
+        }
+        prof_mark();
+        if (e->profiling) e->ev_count.push_back(c.n_layers);
+        e->launches += tf32_wn_flow(plan3, e->t3_flow, k * c.n_layers, c.n_layers, hcur, b1s, b2s, wses, st);
+        prof_mark();
+        if ((c.n_layers - 1) & 1) hcur ^= 1;
+        e->last_flow_kernel = 1;
+        break;
+      }
       if (tf32) {
         // one event pair per flow around its back-to-back layer launches (gate + residual kernel per layer)
         if (i == 0) {
@@ -893,6 +914,11 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
     e->t3_max_pairs = std::min(tf32_init(), e->sm_count / 2);
     if (const char* pr = std::getenv("WG_PAIR")) e->pair_policy = std::atoi(pr);
     if (const char* bk = std::getenv("WG_TF32_BK")) e->t3_gate_bk = std::atoi(bk) == 16 ? 16 : 32;
+    e->t3_flow.max_pairs = std::min(tf32_flow_init(), e->sm_count / 2);
+    CK(cudaMalloc(&e->t3_flow.sync, 2 * sizeof(unsigned int)));
+    e->allocs.push_back(e->t3_flow.sync);
+    CK(cudaMemset(e->t3_flow.sync, 0, 2 * sizeof(unsigned int)));
+    if (const char* fl = std::getenv("WG_TF32_FLOW")) e->t3_flow_policy = std::atoi(fl);
     if (const char* ew = std::getenv("WG_TF32_EPI")) e->t3_epi_warps = std::atoi(ew) == 16 ? 16 : (std::atoi(ew) == 8 ? 8 : 0);
     // folded conditioning weights as an fp32 (hi, lo) pair: V[(layer*R + r)*2C + n][k] = sum_s Wup_r[k][s] * Wcond[s][n]
     const int Kw = e->Kup;

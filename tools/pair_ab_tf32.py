@@ -17,6 +17,7 @@ reps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 hp = WaveGlowHParams()
 w = generate_weights(hp, 1234)
 engines = {}
+os.environ["WG_TF32_FLOW"] = "0"       # the per-layer kernels; `default` below may run a flow as one persistent launch
 for bk in ("16", "32"):
     os.environ["WG_TF32_BK"] = bk
     for pr in ("0", "1"):
@@ -26,7 +27,7 @@ os.environ["WG_TF32_BK"], os.environ["WG_PAIR"] = "32", "1"
 for ew in ("8", "16"):
     os.environ["WG_TF32_EPI"] = ew                 # default: by shape (16 epilogue warps when every CTA runs one item)
     engines["pair32_ew" + ew] = WaveGlowEngine(hp, w, mode="tf32x3")
-del os.environ["WG_PAIR"], os.environ["WG_TF32_BK"], os.environ["WG_TF32_EPI"]
+del os.environ["WG_PAIR"], os.environ["WG_TF32_BK"], os.environ["WG_TF32_EPI"], os.environ["WG_TF32_FLOW"]
 engines["default"] = WaveGlowEngine(hp, w, mode="tf32x3")
 
 
