@@ -251,13 +251,17 @@ def test_pipelined_sweep_equals_the_plain_one(lib_built, tmp_path):
     assert r.data_ptr() == d.data_ptr() and np.array_equal(d.cpu().numpy(), rt(mel, z=z, sigma=0.6))
 
 
-@pytest.mark.parametrize("C,mode,pair", [(256, "bf16", "0"), (256, "bf16", "1"), (256, "tf32x3", "0"), (512, "bf16", "0"), (256, "fp32", "0")])
-def test_no_write_outside_the_workspace_or_the_output(lib_built, monkeypatch, C, mode, pair):
+@pytest.mark.parametrize("C,mode,pair,flow", [(256, "bf16", "0", "1"), (256, "bf16", "1", "1"), (256, "tf32x3", "0", "1"),
+                                              (256, "tf32x3", "1", "0"), (256, "tf32x3", "1", "1"), (512, "bf16", "0", "1"),
+                                              (256, "fp32", "0", "1")])
+def test_no_write_outside_the_workspace_or_the_output(lib_built, monkeypatch, C, mode, pair, flow):
     """Canary check through the raw C ABI (compute-sanitizer is not available on this pool): the scratch the engine asks
     for and the caller's waveform buffer sit between guard bands; after uniform and ragged infers on every kernel path
-    (single-CTA, CTA pair incl. a ghost tile, tf32x3, WaveGlow-512, FFMA) the bands must be untouched."""
+    (single-CTA, CTA pair incl. a ghost tile, tf32x3 per-layer kernels and the one-launch-per-flow kernel, WaveGlow-512,
+    FFMA) the bands must be untouched."""
     monkeypatch.setenv("WG_PM", "1")
     monkeypatch.setenv("WG_PAIR", pair)
+    monkeypatch.setenv("WG_TF32_FLOW", flow)
     hp = WaveGlowHParams(n_channels=C, n_flows=4 if C == 512 else 12)
     eng = _engine(hp, generate_weights(hp, 7), mode)
     lib, h = eng._lib, eng._h

@@ -107,12 +107,14 @@ def test_tf32x3_refuses_what_it_cannot_run(lib_built):
 @pytest.mark.parametrize("B,T,lengths", [(1, 12, None), (3, 300, None), (1, 200, None), (4, 97, [97, 5, 33, 64])])
 def test_tf32x3_kernel_variants_give_the_same_bits(lib_built, monkeypatch, B, T, lengths):
     """The CTA-pair kernels (cta_group::2 kind::tf32, an odd tile count per phase block = a ghost tile included) against
-    the single-CTA kernels, and 8 against 16 epilogue warps: the engine picks among them by shape, so a ragged batch is
-    bit-identical to its stand-alone utterances only if all of them produce the same bits."""
+    the single-CTA kernels, 8 against 16 epilogue warps, and the one-launch-per-flow kernel (grid barriers) against the
+    per-layer kernels: the engine picks among them by shape, so a ragged batch is bit-identical to its stand-alone
+    utterances only if all of them produce the same bits."""
     hp = WaveGlowHParams()
     w = generate_weights(hp, 1234)
     mel, z = synthetic_inputs(B * 1000 + T, B, T, hp)
     outs = {}
+    monkeypatch.setenv("WG_TF32_FLOW", "0")          # the per-layer kernels
     for pair in ("0", "1"):
         for ew in ("8", "16"):
             monkeypatch.setenv("WG_PAIR", pair)
@@ -123,9 +125,54 @@ def test_tf32x3_kernel_variants_give_the_same_bits(lib_built, monkeypatch, B, T,
             eng.close()
     monkeypatch.delenv("WG_PAIR")
     monkeypatch.delenv("WG_TF32_EPI")
+    monkeypatch.delenv("WG_TF32_FLOW")               # default: a flow as ONE persistent launch where the call is one wave
     eng = _engine(hp, w)
     ref = _run(eng, mel, z, 0.6, lengths=lengths)
+    # one wave (<= 2 row tiles per phase: 64 CTA pairs): 12 flow launches + 12 boundaries + geometry / im2col instead of
+    # 180 layer launches; 3 x 300 frames is 8 tiles per phase and stays on the per-layer kernels
+    one_wave = (B, T) != (3, 300)
+    assert (eng.last_launch_count < 40) == one_wave, eng.last_launch_count
+    again = _run(eng, mel, z, 0.6, lengths=lengths)  # the grid barrier re-arms itself
+    assert np.array_equal(ref, again)
     eng.close()
     assert np.isfinite(ref).all()
     for k, o in outs.items():
         assert np.array_equal(ref, o), k
+
+
+def test_tf32x3_flow_kernel_under_a_cuda_graph_and_on_two_streams(lib_built):
+    """tf32_flow_kernel is a cooperative launch: it must survive CUDA-graph capture / replay (the runtime's call path for
+    short utterances) and two engines running on two streams at once (co-residency is the launch's, not the caller's,
+    problem)."""
+    hp = WaveGlowHParams()
+    w = generate_weights(hp, 1234)
+    mel, z = synthetic_inputs(9, 1, 64, hp)
+    md, zd = torch.from_numpy(mel).cuda(), torch.from_numpy(z).cuda()
+    e1, e2 = _engine(hp, w), _engine(hp, w)
+    ref = _run(e1, mel, z, 0.6)
+    assert e1.last_launch_count < 40
+    out = torch.empty(1, 64 * 256, device="cuda")
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        e1.infer_device(md, zd, 0.6, out=out)          # warm-up on a side stream (workspace allocation)
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        e1.infer_device(md, zd, 0.6, out=out)
+    for _ in range(3):
+        out.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), ref)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    o1, o2 = torch.empty_like(out), torch.empty_like(out)
+    for _ in range(5):
+        with torch.cuda.stream(s1):
+            e1.infer_device(md, zd, 0.6, out=o1)
+        with torch.cuda.stream(s2):
+            e2.infer_device(md, zd, 0.6, out=o2)
+    torch.cuda.synchronize()
+    assert np.array_equal(o1.cpu().numpy(), ref) and np.array_equal(o2.cpu().numpy(), ref)
+    e1.close()
+    e2.close()

@@ -494,7 +494,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
         }
         prof_mark();
         if (e->profiling) e->ev_count.push_back(c.n_layers);
-        e->launches += tf32_wn_flow(plan3, e->t3_flow, k * c.n_layers, c.n_layers, hcur, b1s, b2s, wses, st);
+        e->launches += tf32_wn_flow(plan3, e->t3_flow, k * c.n_layers, c.n_layers, hcur, b1s, b2s, wses, st, e->timing);
         prof_mark();
         if ((c.n_layers - 1) & 1) hcur ^= 1;
         e->last_flow_kernel = 1;

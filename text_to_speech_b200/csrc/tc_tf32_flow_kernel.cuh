@@ -105,6 +105,9 @@ tf32_flow_kernel(const __grid_constant__ Tf32FlowMaps maps, const __grid_constan
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   if ((smem_base & 1023u) != 0u) __trap();
+  // WG_LAYER_TIMING=1 (debug): cycle counters, slots 48.. of Tf32Params::timing (see tools/layer_timing_tf32.py)
+  unsigned long long* const tm = fp.base.timing;
+  const long long t_entry = tm ? clock64() : 0;
 
   if (warp == 0 && lane == 0) {
     const CUtensorMap* m = reinterpret_cast<const CUtensorMap*>(&maps);
@@ -146,13 +149,16 @@ tf32_flow_kernel(const __grid_constant__ Tf32FlowMaps maps, const __grid_constan
   if (warp == 0) {
     // ===================================== TMA producer ======================================
     uint32_t itg = 0, itr = 0;
+    long long t_gw = 0, t_gw1 = 0;
     for (int l = 0; l < fp.n_layers; ++l) {
       const bool last = l == fp.n_layers - 1;
       const int hcur = fp.hcur0 ^ (l & 1);
       const int layer = fp.layer0 + l, dil = fp.dilation[l];
       if (l > 0) {
+        const long long tq = tm ? clock64() : 0;
         if (lane == 0) t3f_grid_wait(fp.sync, gen0 + 2u * l);   // every CTA's h of layer l-1 is in memory
         __syncwarp();
+        if (tm) t_gw += clock64() - tq;
       }
       const int bq = q * T3G_BN + static_cast<int>(rank) * (T3G_BN / 2);
       for (int kb = 0; kb < kb1; ++kb, ++itg) {
@@ -182,8 +188,10 @@ tf32_flow_kernel(const __grid_constant__ Tf32FlowMaps maps, const __grid_constan
         __syncwarp();
       }
       if (last) break;
+      const long long tq1 = tm ? clock64() : 0;
       if (lane == 0) t3f_grid_wait(fp.sync, gen0 + 2u * l + 1u);   // every CTA's acts of layer l are in memory
       __syncwarp();
+      if (tm) t_gw1 += clock64() - tq1;
       const int b2q = q * T3R_BN + static_cast<int>(rank) * (T3R_BN / 2);
       for (int kb = 0; kb < kb2; ++kb, ++itr) {
         const int s = itr % RS;
@@ -200,17 +208,24 @@ tf32_flow_kernel(const __grid_constant__ Tf32FlowMaps maps, const __grid_constan
         __syncwarp();
       }
     }
+    if (tm && lane == 0) {
+      atomicAdd(tm + 48, static_cast<unsigned long long>(t_gw));
+      atomicAdd(tm + 57, static_cast<unsigned long long>(t_gw1));
+    }
   } else if (warp == 1) {
     // =========================== MMA issuer (the leader CTA of the pair) =======================
     if (leader) {
       constexpr uint32_t idesc_g = umma_idesc_tf32(2 * T3_BM, T3G_BN), idesc_r = umma_idesc_tf32(2 * T3_BM, T3R_BN);
       const uint32_t d_g = tmem_base, d_r = tmem_base + 256u;
       uint32_t itg = 0, itr = 0;
+      long long t_gf = 0, t_rf = 0;
       for (int l = 0; l < fp.n_layers; ++l) {
         const bool last = l == fp.n_layers - 1;
         for (int kb = 0; kb < kb1; ++kb, ++itg) {
           const int s = itg % GS;
+          const long long tq = tm ? clock64() : 0;
           mbar_wait(gfull(s), (itg / GS) & 1);
+          if (tm) t_gf += clock64() - tq;
           tc_fence_after();
           const uint32_t base = smem_base + s * GSB;
           const uint64_t ahi = umma_desc_sw128(base), alo = umma_desc_sw128(base + GA);
@@ -230,7 +245,9 @@ tf32_flow_kernel(const __grid_constant__ Tf32FlowMaps maps, const __grid_constan
         if (last) break;
         for (int kb = 0; kb < kb2; ++kb, ++itr) {
           const int s = itr % RS;
+          const long long tq = tm ? clock64() : 0;
           mbar_wait(rfull(s), (itr / RS) & 1);
+          if (tm) t_rf += clock64() - tq;
           tc_fence_after();
           const uint32_t base = smem_base + s * RSB;
           const uint64_t ahi = umma_desc_sw128(base), alo = umma_desc_sw128(base + T3_A_BYTES);
@@ -247,6 +264,10 @@ tf32_flow_kernel(const __grid_constant__ Tf32FlowMaps maps, const __grid_constan
           }
           __syncwarp();
         }
+      }
+      if (tm && lane == 0) {
+        atomicAdd(tm + 49, static_cast<unsigned long long>(t_gf));
+        atomicAdd(tm + 50, static_cast<unsigned long long>(t_rf));
       }
     }
   } else {
@@ -269,7 +290,9 @@ tf32_flow_kernel(const __grid_constant__ Tf32FlowMaps maps, const __grid_constan
         for (int i = tid; i < T3R_BN; i += T3F_EPI_THREADS) s_b2[i] = fp.b2[l][q * T3R_BN + i];
       asm volatile("bar.sync 1, %0;" ::"n"(T3F_EPI_THREADS) : "memory");
       // ---- gate epilogue (tf32_gate_kernel, 16 warps, staged stores)
+      const long long te0 = tm ? clock64() : 0;
       mbar_wait(gacc_bar, l & 1);
+      const long long te1 = tm ? clock64() : 0;
       tc_fence_after();
       float o8[8];
 #pragma unroll
@@ -341,11 +364,17 @@ tf32_flow_kernel(const __grid_constant__ Tf32FlowMaps maps, const __grid_constan
         a1.x += tot[4]; a1.y += tot[5]; a1.z += tot[6]; a1.w += tot[7];
         o[0] = a0; o[1] = a1;
       }
+      if (tm && tid == 0) {
+        atomicAdd(tm + 51, static_cast<unsigned long long>(te1 - te0));
+        atomicAdd(tm + 52, static_cast<unsigned long long>(clock64() - te1));
+      }
       if (last) break;
       // ---- acts complete -> grid barrier (the residual GEMM of every CTA reads all C channels of its rows)
+      const long long te2 = tm ? clock64() : 0;
       if (lane == 0) bulk_wait0();
       asm volatile("bar.sync 3, %0;" ::"n"(T3F_EPI_THREADS) : "memory");
       if (tid == 0) t3f_grid_arrive(fp.sync, n_ctas);
+      const long long te3 = tm ? clock64() : 0;
       // ---- residual epilogue (tf32_res_kernel): the old value of h is fetched while the residual GEMM runs
       const size_t off0 = m * p.C + q * T3R_BN + cg * CH;
       // (L2 loads: this buffer was read two layers ago and rewritten since by TMA stores, which do not update L1)
@@ -363,6 +392,7 @@ tf32_flow_kernel(const __grid_constant__ Tf32FlowMaps maps, const __grid_constan
         }
       }
       mbar_wait(racc_bar, l & 1);
+      const long long te4 = tm ? clock64() : 0;
       tc_fence_after();
       {
         const uint32_t taddr = tmem_base + lane_addr + 256u + cg * CH;
@@ -398,6 +428,15 @@ tf32_flow_kernel(const __grid_constant__ Tf32FlowMaps maps, const __grid_constan
       tc_fence_before();
       asm volatile("bar.sync 3, %0;" ::"n"(T3F_EPI_THREADS) : "memory");
       if (tid == 0) t3f_grid_arrive(fp.sync, n_ctas);
+      if (tm && tid == 0) {
+        atomicAdd(tm + 53, static_cast<unsigned long long>(te3 - te2));       // store completion + arrive (acts)
+        atomicAdd(tm + 54, static_cast<unsigned long long>(te4 - te3));       // arrive -> residual accumulator complete
+        atomicAdd(tm + 55, static_cast<unsigned long long>(clock64() - te4)); // residual epilogue incl. store completion + arrive
+      }
+    }
+    if (tm && tid == 0) {
+      atomicAdd(tm + 56, static_cast<unsigned long long>(clock64() - t_entry));
+      atomicAdd(tm + 58, 1ull);
     }
   }
   tc_fence_before();
@@ -441,7 +480,7 @@ inline bool tf32_flow_fits(const Tf32Plan& pl, int max_pairs, int n_layers) {
 
 // All `n_layers` layers of one flow (dilation 2^i). Returns the launch count (1).
 inline int tf32_wn_flow(const Tf32Plan& pl, const Tf32FlowState& fs, int layer0, int n_layers, int hcur0, const float* const* b1,
-                        const float* const* b2, const float* const* wse, cudaStream_t st) {
+                        const float* const* b2, const float* const* wse, cudaStream_t st, unsigned long long* timing = nullptr) {
   Tf32FlowMaps m;
   for (int i = 0; i < 2; ++i) {
     m.hh[i] = pl.m_h_hi[i]; m.hl[i] = pl.m_h_lo[i];
@@ -454,7 +493,7 @@ inline int tf32_wn_flow(const Tf32Plan& pl, const Tf32FlowState& fs, int layer0,
   Tf32FlowParams fp{};
   fp.base = pl.base;
   fp.base.kb_cond = pl.Kup / 32;
-  fp.base.timing = nullptr;
+  fp.base.timing = timing;
   fp.n_layers = n_layers; fp.layer0 = layer0; fp.hcur0 = hcur0;
   for (int i = 0; i < n_layers; ++i) {
     fp.dilation[i] = 1 << i;

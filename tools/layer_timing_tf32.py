@@ -15,6 +15,7 @@ from text_to_speech_b200.weights import WaveGlowHParams, generate_weights, synth
 hp = WaveGlowHParams()
 w = generate_weights(hp, 1234)
 os.environ["WG_LAYER_TIMING"] = "1"
+os.environ["WG_TF32_FLOW"] = "0"
 for (B, T) in [(1, 200), (8, 860)]:
     mel, z = synthetic_inputs(2024, B, T, hp)
     md, zd = torch.from_numpy(mel).cuda(), torch.from_numpy(z).cuda()
@@ -36,3 +37,25 @@ for (B, T) in [(1, 200), (8, 860)]:
                                                  "epi_wait_acc": t[o + 3] / ctas, "epi_work": t[o + 4] / ctas,
                                                  "producer_wait_free_stage": t[o + 6] / ctas}}), flush=True)
         eng.close()
+
+# the one-launch-per-flow kernel (single-wave calls): slots 48.. summed over CTAs x 12 flows
+os.environ["WG_TF32_FLOW"] = "1"
+os.environ.pop("WG_PAIR", None)
+mel, z = synthetic_inputs(2024, 1, 200, hp)
+md, zd = torch.from_numpy(mel).cuda(), torch.from_numpy(z).cuda()
+eng = WaveGlowEngine(hp, w, mode="tf32x3")
+for _ in range(2):
+    eng.infer_device(md, zd, 0.6)
+torch.cuda.synchronize()
+eng.read_layer_timing()
+eng.infer_device(md, zd, 0.6)
+torch.cuda.synchronize()
+t = eng.read_layer_timing()
+n = max(t[58], 1)          # CTAs x flows
+L = 8                      # layers per flow
+print(json.dumps({"kernel": "tf32_flow_kernel", "ctas_x_flows": t[58], "cycles_per_cta_per_layer": {
+    "kernel_total": t[56] / n / L, "producer_wait_h_barrier": t[48] / n / L, "producer_wait_acts_barrier": t[57] / n / L,
+    "mma_wait_gate_operands": t[49] / (n / 2) / L, "mma_wait_residual_operands": t[50] / (n / 2) / L,
+    "epi_wait_gate_acc": t[51] / n / L, "epi_gate_work": t[52] / n / L, "epi_acts_store_and_arrive": t[53] / n / L,
+    "epi_arrive_to_residual_acc": t[54] / n / L, "epi_residual_work_store_arrive": t[55] / n / L},
+    "note": "sums over CTAs (MMA slots: leader CTAs) x 12 flows, divided by CTAs x 8 layers"}), flush=True)
