@@ -108,7 +108,6 @@ struct wg_engine {
   int last_pair = 0;                      // the last wg_infer ran its layers on the CTA-pair kernel
   int pair_epi_warps = 8;                 // WG_PAIR_EPI=16: 16 epilogue warps in the pair kernel
   bool pdl = true;                        // WG_PDL=0: no programmatic dependent launch of the BF16 layer kernels (A/B)
-  int t3_gate_bk = 32;                    // WG_TF32_BK=16: SWIZZLE_64B ring of 16-float K-blocks in the tf32x3 gate kernel (A/B)
   Tf32FlowState t3_flow;                  // one-launch-per-flow kernel for single-wave tf32x3 calls (tc_tf32_flow_kernel.cuh)
   int t3_flow_policy = -1;                // WG_TF32_FLOW: 0 = per-layer kernels only, 1 / -1 = flow kernel where it fits
   int t3_epi_warps = 0;                   // WG_TF32_EPI=8 / 16: force the epilogue warp count of the tf32x3 kernels (A/B)
@@ -184,7 +183,7 @@ struct Ws {  // workspace carving for one (B, T)
   size_t spect = 0, h32 = 0, acts = 0, skip = 0, acc8 = 0, audio0 = 0, audio1 = 0;
   size_t spect16 = 0, h16a = 0, h16b = 0, hlo = 0, aup16 = 0, acts16 = 0, a0 = 0;
   size_t g_off = 0, g_len = 0, g_rowb = 0;   // ragged geometry tables (RowGeom)
-  size_t t3_hhi0 = 0, t3_hhi1 = 0, t3_hlo0 = 0, t3_hlo1 = 0, t3_ahi = 0, t3_alo = 0, t3_chi = 0, t3_clo = 0;
+  size_t t3_hhi0 = 0, t3_hhi1 = 0, t3_hlo0 = 0, t3_hlo1 = 0, t3_hb0 = 0, t3_hb1 = 0, t3_ahi = 0, t3_ab = 0, t3_chi = 0, t3_cb = 0;
   size_t total = 0;
 };
 
@@ -249,11 +248,13 @@ Ws carve(const wg_engine* e, int B, int T, const Ragged* rg = nullptr) {
     w.acts = take(M * e->C * 4);
     w.skip = take(M * e->C * 4);
   } else if (e->cfg.mode == WG_MODE_TF32X3) {
-    // fp32 (hi, lo) pairs: residual stream x2 (ping-pong), acts, mel window; one partial fold accumulator per gate chunk
+    // every MMA operand as tf32(x) in fp32 words + a bf16 companion [.., 2K] (bf16(hi) | bf16(lo)): residual stream x2
+    // (ping-pong; + its exact fp32 remainder for the residual add), acts, mel window; one partial fold accumulator per chunk
     w.t3_hhi0 = take(M * e->C * 4); w.t3_hhi1 = take(M * e->C * 4);
     w.t3_hlo0 = take(M * e->C * 4); w.t3_hlo1 = take(M * e->C * 4);
-    w.t3_ahi = take(M * e->C * 4); w.t3_alo = take(M * e->C * 4);
-    w.t3_chi = take(rows1 * e->Kup * 4); w.t3_clo = take(rows1 * e->Kup * 4);
+    w.t3_hb0 = take(M * e->C * 4); w.t3_hb1 = take(M * e->C * 4);
+    w.t3_ahi = take(M * e->C * 4); w.t3_ab = take(M * e->C * 4);
+    w.t3_chi = take(rows1 * e->Kup * 4); w.t3_cb = take(rows1 * e->Kup * 4);
     if (rg) {
       w.g_off = take((size_t)B * 4);
       w.g_len = take((size_t)B * 4);
@@ -365,6 +366,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
   float* h32 = ffma ? reinterpret_cast<float*>(base + w.h32) : nullptr;
   float* t3_hhi[2] = {reinterpret_cast<float*>(base + w.t3_hhi0), reinterpret_cast<float*>(base + w.t3_hhi1)};
   float* t3_hlo[2] = {reinterpret_cast<float*>(base + w.t3_hlo0), reinterpret_cast<float*>(base + w.t3_hlo1)};
+  __nv_bfloat16* t3_hb[2] = {reinterpret_cast<__nv_bfloat16*>(base + w.t3_hb0), reinterpret_cast<__nv_bfloat16*>(base + w.t3_hb1)};
   const int t3_parts = tf32 ? 2 * C / 256 : 1;                       // partial fold accumulators (one per gate chunk)
   const size_t t3_acc_stride = (size_t)geo.rows() * 8;                // floats between two partials
   float* acc8 = reinterpret_cast<float*>(base + w.acc8);
@@ -392,11 +394,13 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
   if (tf32) {
     RowGeom geo1 = geo;
     geo1.R = 1;
+    Tf32Buffers tb{};
+    for (int i = 0; i < 2; ++i) { tb.h_hi[i] = t3_hhi[i]; tb.h_lo[i] = t3_hlo[i]; tb.h_b[i] = t3_hb[i]; }
+    tb.aup_hi = reinterpret_cast<float*>(base + w.t3_chi); tb.aup_b = reinterpret_cast<__nv_bfloat16*>(base + w.t3_cb);
+    tb.acts_hi = reinterpret_cast<float*>(base + w.t3_ahi); tb.acts_b = reinterpret_cast<__nv_bfloat16*>(base + w.t3_ab);
+    tb.acc8 = acc8; tb.acc8_stride = t3_acc_stride;
     tf32_prepare(plan3, e->sm_count, C, R, e->Kup, c.n_mel_channels, c.n_flows * c.n_layers, geo.rows_per_phase(), geo1,
-                 rg ? 0 : geo.Tp, geo.T, e->t3, t3_hhi[0], t3_hhi[1], t3_hlo[0], t3_hlo[1],
-                 reinterpret_cast<float*>(base + w.t3_chi), reinterpret_cast<float*>(base + w.t3_clo),
-                 reinterpret_cast<float*>(base + w.t3_ahi), reinterpret_cast<float*>(base + w.t3_alo), acc8, t3_acc_stride,
-                 e->t3_gate_bk, e->t3_max_pairs, e->pair_policy, e->t3_epi_warps);
+                 rg ? 0 : geo.Tp, geo.T, e->t3, tb, e->t3_max_pairs, e->pair_policy, e->t3_epi_warps);
     e->last_pair = plan3.pair ? 1 : 0;
     e->last_flow_kernel = 0;
     e->launches += tf32_upsample(plan3, mel, st);
@@ -435,7 +439,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
     a.sigma = sigma; a.audio_out = audio[cur]; a.M = Mi; a.C = C;
     a.Wstart = fold0 ? nullptr : e->flows[F - 1].Wstart; a.bstart = e->flows[F - 1].bstart;
     a.n_half_next = e->flows[F - 1].n_half; a.h32 = h32; a.h16 = bf16 ? h16[hcur] : nullptr; a.hlo = bf16 ? hlo : nullptr;
-    if (tf32) { a.hf_hi = t3_hhi[hcur]; a.hf_lo = t3_hlo[hcur]; }
+    if (tf32) { a.hf_hi = t3_hhi[hcur]; a.hf_lo = t3_hlo[hcur]; a.hf_b = t3_hb[hcur]; }
     a.acc_parts = t3_parts; a.acc_part_stride = t3_acc_stride;
     if (!ffma) { a.acc8_rearm = acc8; std::memcpy(a.acc8_init, e->flows[F - 1].bse8, sizeof a.acc8_init); }
     launch_boundary(e, a, st);
@@ -584,7 +588,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
       a.n_half_next = e->flows[k - 1].n_half; a.h32 = h32;
       hcur = 0;
       a.h16 = bf16 ? h16[hcur] : nullptr; a.hlo = bf16 ? hlo : nullptr;
-      if (tf32) { a.hf_hi = t3_hhi[hcur]; a.hf_lo = t3_hlo[hcur]; }
+      if (tf32) { a.hf_hi = t3_hhi[hcur]; a.hf_lo = t3_hlo[hcur]; a.hf_b = t3_hb[hcur]; }
       if (!ffma) { a.acc8_rearm = acc8; std::memcpy(a.acc8_init, e->flows[k - 1].bse8, sizeof a.acc8_init); }
     } else {
       a.audio_out = out;  // [B*L, 8] == [B, 8L]  (waveglow_arch.py:306)
@@ -715,10 +719,11 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
   e->layers.resize((size_t)F * NL);
   const int K1 = 3 * C + S;
   std::vector<__nv_bfloat16> w1all, w2all, w0all, h0all;
-  std::vector<float> t3w1h, t3w1l, t3w2h, t3w2l;      // tf32x3: (hi, lo) pairs, stacked over the layers
+  std::vector<float> t3w1h, t3w2h;                    // tf32x3: tf32(w) in fp32 words, stacked over the layers
+  std::vector<__nv_bfloat16> t3w1b, t3w2b;            // ... and the bf16 companions [.., 2K] = bf16(hi) | bf16(lo)
   if (tf32) {
-    t3w1h.assign((size_t)F * NL * 2 * C * 3 * C, 0.f); t3w1l.assign(t3w1h.size(), 0.f);
-    t3w2h.assign((size_t)F * NL * C * C, 0.f); t3w2l.assign(t3w2h.size(), 0.f);
+    t3w1h.assign((size_t)F * NL * 2 * C * 3 * C, 0.f); t3w1b.assign(2 * t3w1h.size(), f2bf(0.f));
+    t3w2h.assign((size_t)F * NL * C * C, 0.f); t3w2b.assign(2 * t3w2h.size(), f2bf(0.f));
   }
   const bool build_fold0 = c.mode == WG_MODE_BF16 && NL > 1;
   if (c.mode == WG_MODE_BF16) {
@@ -804,7 +809,8 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
             for (int kk = 0; kk < 3 * C; ++kk) {
               const float v = wsrc(kk, col), hi = tf32_rna_host(v);
               t3w1h[row + kk] = hi;
-              t3w1l[row + kk] = v - hi;
+              t3w1b[2 * row + kk] = f2bf(hi);
+              t3w1b[2 * row + 3 * C + kk] = f2bf(v - hi);
             }
           } else {
             for (int kk = 0; kk < K1; ++kk) w1[(size_t)pcol * K1 + kk] = f2bf(wsrc(kk, col));
@@ -874,8 +880,10 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
               const float v = rw.data[(size_t)kk * rs + n];
               if (tf32) {
                 const size_t at = (((size_t)k * NL + i) * C + n) * C + kk;
+                const size_t rowb = (((size_t)k * NL + i) * C + n) * 2 * C;
                 t3w2h[at] = tf32_rna_host(v);
-                t3w2l[at] = v - t3w2h[at];
+                t3w2b[rowb + kk] = f2bf(t3w2h[at]);
+                t3w2b[rowb + C + kk] = f2bf(v - t3w2h[at]);
               } else {
                 w2[(size_t)n * C + kk] = f2bf(v);
               }
@@ -908,12 +916,11 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
     }
   }
   if (tf32) {
-    e->t3.W1h = upload(e, t3w1h); e->t3.W1l = upload(e, t3w1l);
-    e->t3.W2h = upload(e, t3w2h); e->t3.W2l = upload(e, t3w2l);
+    e->t3.W1h = upload(e, t3w1h); e->t3.W1b = upload(e, t3w1b);
+    e->t3.W2h = upload(e, t3w2h); e->t3.W2b = upload(e, t3w2b);
     tc_init();
     e->t3_max_pairs = std::min(tf32_init(), e->sm_count / 2);
     if (const char* pr = std::getenv("WG_PAIR")) e->pair_policy = std::atoi(pr);
-    if (const char* bk = std::getenv("WG_TF32_BK")) e->t3_gate_bk = std::atoi(bk) == 16 ? 16 : 32;
     e->t3_flow.max_pairs = std::min(tf32_flow_init(), e->sm_count / 2);
     CK(cudaMalloc(&e->t3_flow.sync, 2 * sizeof(unsigned int)));
     e->allocs.push_back(e->t3_flow.sync);
@@ -922,7 +929,8 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
     if (const char* ew = std::getenv("WG_TF32_EPI")) e->t3_epi_warps = std::atoi(ew) == 16 ? 16 : (std::atoi(ew) == 8 ? 8 : 0);
     // folded conditioning weights as an fp32 (hi, lo) pair: V[(layer*R + r)*2C + n][k] = sum_s Wup_r[k][s] * Wcond[s][n]
     const int Kw = e->Kup;
-    float *d_wup = nullptr, *d_wc = nullptr, *d_tmp = nullptr, *vh = nullptr, *vl = nullptr;
+    float *d_wup = nullptr, *d_wc = nullptr, *d_tmp = nullptr, *vh = nullptr;
+    __nv_bfloat16* vb = nullptr;
     const size_t vcount = (size_t)F * NL * R * 2 * C * Kw;
     std::vector<float> wup_rk((size_t)R * Kw * S);
     for (int r = 0; r < R; ++r)
@@ -933,8 +941,8 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
     CK(cudaMalloc(&d_tmp, (size_t)R * Kw * 2 * C * 4));
     CK(cudaMalloc(&vh, vcount * 4));
     e->allocs.push_back(vh);
-    CK(cudaMalloc(&vl, vcount * 4));
-    e->allocs.push_back(vl);
+    CK(cudaMalloc(&vb, vcount * 4));
+    e->allocs.push_back(vb);
     CK(cudaMemcpy(d_wup, wup_rk.data(), wup_rk.size() * 4, cudaMemcpyHostToDevice));
     for (int li = 0; li < F * NL; ++li) {
       CK(cudaMemcpy(d_wc, wcond_packed[li].data(), (size_t)S * 2 * C * 4, cudaMemcpyHostToDevice));
@@ -947,12 +955,12 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
       gemm_f32_kernel<EPI_STORE><<<grid, SG_THREADS>>>(g);
       const size_t n = (size_t)R * Kw * 2 * C;
       const size_t at = (size_t)li * R * 2 * C * Kw;
-      fold_store_tf32_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_tmp, vh + at, vl + at, R, Kw, 2 * C);
+      fold_store_tf32_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_tmp, vh + at, vb + 2 * at, R, Kw, 2 * C);
     }
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     cudaFree(d_wup); cudaFree(d_wc); cudaFree(d_tmp);
-    e->t3.Vh = vh; e->t3.Vl = vl;
+    e->t3.Vh = vh; e->t3.Vb = vb;
   }
   if (c.mode == WG_MODE_BF16) {
     e->W1 = upload(e, w1all);

@@ -284,6 +284,7 @@ struct BoundaryArgs {
   __nv_bfloat16* hlo;     // [M, C] or null: bf16(h - bf16(h))
   float* hf_hi;           // [M, C] or null: tf32(h)            (tf32x3 mode: residual stream = hi + lo, both fp32)
   float* hf_lo;           // [M, C] or null: h - tf32(h)
+  __nv_bfloat16* hf_b;    // [M, 2C] or null: bf16(hi) | bf16(lo), the operands of the cross-term MMAs (tc_tf32_kernels.cuh)
   int acc_parts;          // acc8 is the sum of this many partial accumulators (tf32x3: one per gate chunk), >= 1
   size_t acc_part_stride; // floats between two partials
   int M;
@@ -425,6 +426,16 @@ flow_boundary_kernel(const __grid_constant__ BoundaryArgs a) {
       *reinterpret_cast<float4*>(a.hf_hi + (size_t)m * a.C + c8 + 4) = make_float4(hi[4], hi[5], hi[6], hi[7]);
       *reinterpret_cast<float4*>(a.hf_lo + (size_t)m * a.C + c8) = make_float4(lo[0], lo[1], lo[2], lo[3]);
       *reinterpret_cast<float4*>(a.hf_lo + (size_t)m * a.C + c8 + 4) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+      uint32_t hb[4], lb[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const __nv_bfloat162 ph = __floats2bfloat162_rn(hi[2 * q], hi[2 * q + 1]);
+        const __nv_bfloat162 pl = __floats2bfloat162_rn(lo[2 * q], lo[2 * q + 1]);
+        hb[q] = *reinterpret_cast<const uint32_t*>(&ph);
+        lb[q] = *reinterpret_cast<const uint32_t*>(&pl);
+      }
+      *reinterpret_cast<uint4*>(a.hf_b + (size_t)m * 2 * a.C + c8) = make_uint4(hb[0], hb[1], hb[2], hb[3]);
+      *reinterpret_cast<uint4*>(a.hf_b + (size_t)m * 2 * a.C + a.C + c8) = make_uint4(lb[0], lb[1], lb[2], lb[3]);
     }
   }
 }

@@ -32,13 +32,14 @@ constexpr int T3F_SMEM = T3F_OFF_BARS + T3F_NBARS * 8 + 16;
 static_assert(T3F_SMEM <= 232448, "shared memory budget");
 
 struct Tf32FlowMaps {
-  CUtensorMap hh[2], hl[2];        // residual stream (hi, lo), ping-pong: 128-row boxes (gate A operand, taps)
-  CUtensorMap ch, cl;              // mel window
-  CUtensorMap w1h, w1l, vh, vl;    // gate weights, 128-row boxes (one CTA's half of a chunk)
-  CUtensorMap ah, al;              // acts (residual A operand)
-  CUtensorMap w2h, w2l;            // residual weights, 64-row boxes
-  CUtensorMap sah, sal;            // 32 x 32 store boxes: acts
-  CUtensorMap shh[2], shl[2];      // 32 x 32 store boxes: residual stream
+  // "?h": fp32 words holding tf32(x); "?b": the bf16 companion [.., 2K] = bf16(hi) | bf16(lo)  (tc_tf32_kernels.cuh)
+  CUtensorMap hh[2], hb[2];        // residual stream, ping-pong: 128-row boxes (gate A operand, taps)
+  CUtensorMap ch, cb;              // mel window
+  CUtensorMap w1h, w1b, vh, vb;    // gate weights, 128-row boxes (one CTA's half of a chunk)
+  CUtensorMap ah, ab;              // acts (residual A operand)
+  CUtensorMap w2h, w2b;            // residual weights, 64-row boxes
+  CUtensorMap sah, sab;            // 32 x 32 store boxes: acts
+  CUtensorMap shh[2], shl[2], shb[2];   // 32 x 32 store boxes: residual stream (hi, exact lo, bf16 companion)
 };
 
 struct Tf32FlowParams {
@@ -167,22 +168,22 @@ tf32_flow_kernel(const __grid_constant__ Tf32FlowMaps maps, const __grid_constan
         if (elect_one()) {
           if (leader) mbar_expect_tx(gfull(s), 2 * GSB);
           const uint32_t fb = gfull(s) & kPeerBitMask;
-          const uint32_t a_hi = smem_base + s * GSB, a_lo = a_hi + GA, b_hi = a_lo + GA, b_lo = b_hi + GB;
+          const uint32_t a_hi = smem_base + s * GSB, a_b = a_hi + GA, b_hi = a_b + GA, b_b = b_hi + GB;
           if (kb < kb_conv) {
             const int tap = kb / cblks, cblk = kb - tap * cblks;
             const int rs = r + (tap - 1) * dil;
             const int carry = (rs >= 0) ? rs / p.R : -((-rs + p.R - 1) / p.R);
             tma2_load_4d(a_hi, &maps.hh[hcur], fb, cblk * BK, t0 + carry, rs - carry * p.R, 0);
-            tma2_load_4d(a_lo, &maps.hl[hcur], fb, cblk * BK, t0 + carry, rs - carry * p.R, 0);
+            t3_load_b_4d<true>(a_b, GA / 2, &maps.hb[hcur], gfull(s), p.C, cblk * BK, t0 + carry, rs - carry * p.R, 0);
             tma2_load_2d(b_hi, &maps.w1h, fb, kb * BK, layer * 2 * p.C + bq);
-            tma2_load_2d(b_lo, &maps.w1l, fb, kb * BK, layer * 2 * p.C + bq);
+            t3_load_b_2d<true>(b_b, GB / 2, &maps.w1b, gfull(s), 3 * p.C, kb * BK, layer * 2 * p.C + bq);
           } else {
             const int kc = kb - kb_conv;
             const int vrow = layer * p.R * 2 * p.C + r * 2 * p.C + bq;
             tma2_load_4d(a_hi, &maps.ch, fb, kc * BK, t0, 0, 0);
-            tma2_load_4d(a_lo, &maps.cl, fb, kc * BK, t0, 0, 0);
+            t3_load_b_4d<true>(a_b, GA / 2, &maps.cb, gfull(s), kb_cond * BK, kc * BK, t0, 0, 0);
             tma2_load_2d(b_hi, &maps.vh, fb, kc * BK, vrow);
-            tma2_load_2d(b_lo, &maps.vl, fb, kc * BK, vrow);
+            t3_load_b_2d<true>(b_b, GB / 2, &maps.vb, gfull(s), kb_cond * BK, kc * BK, vrow);
           }
         }
         __syncwarp();
@@ -199,11 +200,11 @@ tf32_flow_kernel(const __grid_constant__ Tf32FlowMaps maps, const __grid_constan
         if (elect_one()) {
           if (leader) mbar_expect_tx(rfull(s), 2 * RSB);
           const uint32_t fb = rfull(s) & kPeerBitMask;
-          const uint32_t a_hi = smem_base + s * RSB, a_lo = a_hi + T3_A_BYTES, b_hi = a_lo + T3_A_BYTES, b_lo = b_hi + RB;
+          const uint32_t a_hi = smem_base + s * RSB, a_b = a_hi + T3_A_BYTES, b_hi = a_b + T3_A_BYTES, b_b = b_hi + RB;
           tma2_load_4d(a_hi, &maps.ah, fb, kb * BK, t0, r, 0);
-          tma2_load_4d(a_lo, &maps.al, fb, kb * BK, t0, r, 0);
+          t3_load_b_4d<true>(a_b, T3_A_BYTES / 2, &maps.ab, rfull(s), p.C, kb * BK, t0, r, 0);
           tma2_load_2d(b_hi, &maps.w2h, fb, kb * BK, layer * p.C + b2q);
-          tma2_load_2d(b_lo, &maps.w2l, fb, kb * BK, layer * p.C + b2q);
+          t3_load_b_2d<true>(b_b, RB / 2, &maps.w2b, rfull(s), p.C, kb * BK, layer * p.C + b2q);
         }
         __syncwarp();
       }
@@ -216,6 +217,7 @@ tf32_flow_kernel(const __grid_constant__ Tf32FlowMaps maps, const __grid_constan
     // =========================== MMA issuer (the leader CTA of the pair) =======================
     if (leader) {
       constexpr uint32_t idesc_g = umma_idesc_tf32(2 * T3_BM, T3G_BN), idesc_r = umma_idesc_tf32(2 * T3_BM, T3R_BN);
+      constexpr uint32_t idesc16_g = umma_idesc_bf16(2 * T3_BM, T3G_BN), idesc16_r = umma_idesc_bf16(2 * T3_BM, T3R_BN);
       const uint32_t d_g = tmem_base, d_r = tmem_base + 256u;
       uint32_t itg = 0, itr = 0;
       long long t_gf = 0, t_rf = 0;
@@ -228,15 +230,8 @@ tf32_flow_kernel(const __grid_constant__ Tf32FlowMaps maps, const __grid_constan
           if (tm) t_gf += clock64() - tq;
           tc_fence_after();
           const uint32_t base = smem_base + s * GSB;
-          const uint64_t ahi = umma_desc_sw128(base), alo = umma_desc_sw128(base + GA);
-          const uint64_t bhi = umma_desc_sw128(base + 2 * GA), blo = umma_desc_sw128(base + 2 * GA + GB);
           if (elect_one()) {
-#pragma unroll
-            for (int k = 0; k < BK / 8; ++k) umma2_tf32(d_g, alo + 2 * k, bhi + 2 * k, idesc_g, (kb | k) ? 1u : 0u);
-#pragma unroll
-            for (int k = 0; k < BK / 8; ++k) umma2_tf32(d_g, ahi + 2 * k, blo + 2 * k, idesc_g, 1u);
-#pragma unroll
-            for (int k = 0; k < BK / 8; ++k) umma2_tf32(d_g, ahi + 2 * k, bhi + 2 * k, idesc_g, 1u);
+            t3_mma_stage<true>(d_g, base, GA, base + 2 * GA, GB, idesc_g, idesc16_g, kb == 0);
             tc2_commit(gempty(s));
             if (kb == kb1 - 1) tc2_commit(gacc_bar);
           }
@@ -250,15 +245,8 @@ tf32_flow_kernel(const __grid_constant__ Tf32FlowMaps maps, const __grid_constan
           if (tm) t_rf += clock64() - tq;
           tc_fence_after();
           const uint32_t base = smem_base + s * RSB;
-          const uint64_t ahi = umma_desc_sw128(base), alo = umma_desc_sw128(base + T3_A_BYTES);
-          const uint64_t bhi = umma_desc_sw128(base + 2 * T3_A_BYTES), blo = umma_desc_sw128(base + 2 * T3_A_BYTES + RB);
           if (elect_one()) {
-#pragma unroll
-            for (int k = 0; k < BK / 8; ++k) umma2_tf32(d_r, alo + 2 * k, bhi + 2 * k, idesc_r, (kb | k) ? 1u : 0u);
-#pragma unroll
-            for (int k = 0; k < BK / 8; ++k) umma2_tf32(d_r, ahi + 2 * k, blo + 2 * k, idesc_r, 1u);
-#pragma unroll
-            for (int k = 0; k < BK / 8; ++k) umma2_tf32(d_r, ahi + 2 * k, bhi + 2 * k, idesc_r, 1u);
+            t3_mma_stage<true>(d_r, base, T3_A_BYTES, base + 2 * T3_A_BYTES, RB, idesc_r, idesc16_r, kb == 0);
             tc2_commit(rempty(s));
             if (kb == kb2 - 1) tc2_commit(racc_bar);
           }
@@ -277,7 +265,8 @@ tf32_flow_kernel(const __grid_constant__ Tf32FlowMaps maps, const __grid_constan
     const int cg = we >> 2;             // column group: 32 of the chunk's 128 gate channels / residual columns
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t stg_hi = smem_base + static_cast<uint32_t>(we) * 8192u, stg_lo = stg_hi + 4096u;
+    // staging tiles of this warp: gate (acts) hi 4 KB | hb 2 KB | lb 2 KB;  residual (h) hi | lo 4 KB each | hb | lb 2 KB each
+    const uint32_t stg = smem_base + static_cast<uint32_t>(we) * 12288u;
     const bool valid = t3_row_valid(p, t0 + row);
     const size_t m = static_cast<size_t>(r) * p.T + t0 + row;
     const int tid = threadIdx.x - 64;
@@ -321,18 +310,11 @@ tf32_flow_kernel(const __grid_constant__ Tf32FlowMaps maps, const __grid_constan
             o8[6] = fmaf(a[j], w1.z, o8[6]); o8[7] = fmaf(a[j], w1.w, o8[7]);
           }
           if (!last) {
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              float hi[4], lo[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                hi[j] = valid ? tf32_rna(a[4 * v + j]) : 0.f;
-                lo[j] = valid ? a[4 * v + j] - hi[j] : 0.f;
-              }
-              const uint32_t o = static_cast<uint32_t>(lane) * 128u + (static_cast<uint32_t>((g2 * 4 + v) ^ (lane & 7)) << 4);
-              st_shared_f4(stg_hi + o, hi[0], hi[1], hi[2], hi[3]);
-              st_shared_f4(stg_lo + o, lo[0], lo[1], lo[2], lo[3]);
-            }
+            T3Split16 sp;
+            t3_split16(a, valid, sp);
+            t3_stage_f32(stg, lane, g2, sp.hi);
+            t3_stage_b16(stg + 4096u, lane, g2, sp.hb);
+            t3_stage_b16(stg + 6144u, lane, g2, sp.lb);
           }
         }
       }
@@ -340,8 +322,9 @@ tf32_flow_kernel(const __grid_constant__ Tf32FlowMaps maps, const __grid_constan
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_4d(&maps.sah, stg_hi, q * 128 + cg * CH, t0 + quarter * 32, r, 0);
-          tma_store_4d(&maps.sal, stg_lo, q * 128 + cg * CH, t0 + quarter * 32, r, 0);
+          tma_store_4d(&maps.sah, stg, q * 128 + cg * CH, t0 + quarter * 32, r, 0);
+          tma_store_4d(&maps.sab, stg + 4096u, q * 128 + cg * CH, t0 + quarter * 32, r, 0);
+          tma_store_4d(&maps.sab, stg + 6144u, p.C + q * 128 + cg * CH, t0 + quarter * 32, r, 0);
           bulk_commit();
         }
       }
@@ -401,27 +384,25 @@ tf32_flow_kernel(const __grid_constant__ Tf32FlowMaps maps, const __grid_constan
           uint32_t rr[16];
           tmem_ld16(taddr + g * 16, rr);
           tmem_ld_wait();
+          // h_new = (acts @ Wres + b) + h   (waveglow_arch.py:131-133); gap rows: the next layer's zero padding
+          float x[16];
 #pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            float hi[4], lo[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              // h_new = (acts @ Wres + b) + h   (waveglow_arch.py:131-133); gap rows: the next layer's zero padding
-              const float x = (__uint_as_float(rr[4 * v + j]) + s_b2[cg * CH + g * 16 + 4 * v + j]) + old[g * 16 + 4 * v + j];
-              hi[j] = valid ? tf32_rna(x) : 0.f;
-              lo[j] = valid ? x - hi[j] : 0.f;
-            }
-            const uint32_t o = static_cast<uint32_t>(lane) * 128u + (static_cast<uint32_t>((g * 4 + v) ^ (lane & 7)) << 4);
-            st_shared_f4(stg_hi + o, hi[0], hi[1], hi[2], hi[3]);
-            st_shared_f4(stg_lo + o, lo[0], lo[1], lo[2], lo[3]);
-          }
+          for (int j = 0; j < 16; ++j) x[j] = (__uint_as_float(rr[j]) + s_b2[cg * CH + g * 16 + j]) + old[g * 16 + j];
+          T3Split16 sp;
+          t3_split16(x, valid, sp);
+          t3_stage_f32(stg, lane, g, sp.hi);
+          t3_stage_f32(stg + 4096u, lane, g, sp.lo);
+          t3_stage_b16(stg + 8192u, lane, g, sp.hb);
+          t3_stage_b16(stg + 10240u, lane, g, sp.lb);
         }
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        tma_store_4d(&maps.shh[hcur ^ 1], stg_hi, q * T3R_BN + cg * CH, t0 + quarter * 32, r, 0);
-        tma_store_4d(&maps.shl[hcur ^ 1], stg_lo, q * T3R_BN + cg * CH, t0 + quarter * 32, r, 0);
+        tma_store_4d(&maps.shh[hcur ^ 1], stg, q * T3R_BN + cg * CH, t0 + quarter * 32, r, 0);
+        tma_store_4d(&maps.shl[hcur ^ 1], stg + 4096u, q * T3R_BN + cg * CH, t0 + quarter * 32, r, 0);
+        tma_store_4d(&maps.shb[hcur ^ 1], stg + 8192u, q * T3R_BN + cg * CH, t0 + quarter * 32, r, 0);
+        tma_store_4d(&maps.shb[hcur ^ 1], stg + 10240u, p.C + q * T3R_BN + cg * CH, t0 + quarter * 32, r, 0);
         bulk_commit();
         bulk_wait0();
       }
@@ -472,7 +453,7 @@ inline int tf32_flow_init() {
 
 // Can this plan run a flow as one launch?  Every pair item needs its own CTA pair, all co-resident.
 inline bool tf32_flow_fits(const Tf32Plan& pl, int max_pairs, int n_layers) {
-  if (!pl.pair || pl.gate_bk != 32 || max_pairs < 1 || n_layers > T3F_MAX_LAYERS) return false;
+  if (!pl.pair || max_pairs < 1 || n_layers > T3F_MAX_LAYERS) return false;
   const int n_chunks = 2 * pl.base.C / T3G_BN;
   const int items = ((pl.base.tiles_per_row + 1) / 2) * pl.base.R * n_chunks;
   return items <= max_pairs;
@@ -483,13 +464,13 @@ inline int tf32_wn_flow(const Tf32Plan& pl, const Tf32FlowState& fs, int layer0,
                         const float* const* b2, const float* const* wse, cudaStream_t st, unsigned long long* timing = nullptr) {
   Tf32FlowMaps m;
   for (int i = 0; i < 2; ++i) {
-    m.hh[i] = pl.m_h_hi[i]; m.hl[i] = pl.m_h_lo[i];
-    m.shh[i] = pl.s_h_hi[i]; m.shl[i] = pl.s_h_lo[i];
+    m.hh[i] = pl.m_h_hi[i]; m.hb[i] = pl.m_h_b[i];
+    m.shh[i] = pl.s_h_hi[i]; m.shl[i] = pl.s_h_lo[i]; m.shb[i] = pl.s_h_b[i];
   }
-  m.ch = pl.m_c_hi; m.cl = pl.m_c_lo;
-  m.w1h = pl.p_w1h; m.w1l = pl.p_w1l; m.vh = pl.p_vh; m.vl = pl.p_vl;
-  m.ah = pl.m_a_hi; m.al = pl.m_a_lo; m.w2h = pl.p_w2h; m.w2l = pl.p_w2l;
-  m.sah = pl.s_a_hi; m.sal = pl.s_a_lo;
+  m.ch = pl.m_c_hi; m.cb = pl.m_c_b;
+  m.w1h = pl.p_w1h; m.w1b = pl.p_w1b; m.vh = pl.p_vh; m.vb = pl.p_vb;
+  m.ah = pl.m_a_hi; m.ab = pl.m_a_b; m.w2h = pl.p_w2h; m.w2b = pl.p_w2b;
+  m.sah = pl.s_a_hi; m.sab = pl.s_a_b;
   Tf32FlowParams fp{};
   fp.base = pl.base;
   fp.base.kb_cond = pl.Kup / 32;

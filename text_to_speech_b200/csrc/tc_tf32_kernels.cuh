@@ -154,13 +154,14 @@ struct Tf32Params {
   const float* bias;   // gate: [2C] chunk-packed (cond bias folded in);  residual: [C]
   const float* wse;    // gate: [C, 8] = Wskip @ Wend (fp32)
   float* acts_hi;      // gate out / residual A operand: [rows, C] internal row order
-  float* acts_lo;
+  __nv_bfloat16* acts_b;   // [rows, 2C]: bf16(acts_hi) | bf16(acts - acts_hi), the operands of the cross-term MMAs
   float* acc8;         // gate: partial fold accumulators [n_chunks][rows][8]
   size_t acc8_stride;  // floats between two partials
   const float* h_hi;   // residual epilogue: the residual stream of this layer (read), [rows, C]
   const float* h_lo;
   float* ho_hi;        // residual epilogue: the next layer's stream (written; gap rows as zeros)
   float* ho_lo;
+  __nv_bfloat16* ho_b;     // [rows, 2C]: bf16(hi) | bf16(lo) of the next layer's stream
   // WG_LAYER_TIMING=1 (debug): cycle counters, summed over CTAs. Gate kernel slots 16..: [16] MMA warp first wait -> last
   // accumulator complete, [17] MMA waiting for TMA data, [18] MMA waiting for the epilogue, [19] epilogue waiting for an
   // accumulator, [20] epilogue work, [21] kernel entry -> MMA loop entry, [22] producer waiting for a free stage,
@@ -205,6 +206,76 @@ __device__ __forceinline__ void t3_mma(uint32_t d, uint64_t a, uint64_t b, uint3
   else umma_tf32(d, a, b, idesc, acc);
 }
 template <bool PAIR>
+__device__ __forceinline__ void t3_mma16(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if (PAIR) umma2_bf16(d, a, b, idesc, acc);
+  else umma_bf16(d, a, b, idesc, acc);
+}
+// The (bf16(hi) | bf16(lo)) companion of a 32-float K-block: two boxes of 32 bf16 (64-byte rows) from the array
+// [.., 2K], at columns c0 and K + c0, landing in two consecutive half-size tiles.
+template <bool PAIR>
+__device__ __forceinline__ void t3_load_b_2d(uint32_t dst, uint32_t tile_bytes, const CUtensorMap* m, uint32_t bar, int K, int c0, int c1) {
+  t3_load_2d<PAIR>(dst, m, bar, c0, c1);
+  t3_load_2d<PAIR>(dst + tile_bytes, m, bar, K + c0, c1);
+}
+template <bool PAIR>
+__device__ __forceinline__ void t3_load_b_4d(uint32_t dst, uint32_t tile_bytes, const CUtensorMap* m, uint32_t bar, int K, int c0, int c1,
+                                             int c2, int c3) {
+  t3_load_4d<PAIR>(dst, m, bar, c0, c1, c2, c3);
+  t3_load_4d<PAIR>(dst + tile_bytes, m, bar, K + c0, c1, c2, c3);
+}
+// One pipeline stage = one K-block of 32: [A_hi fp32 | A_hb | A_lb bf16][B_hi | B_hb | B_lb].  Small cross terms first
+// (BF16 MMAs, K = 16 each), then the main product (TF32 MMAs, K = 8 each), all into the same fp32 accumulator.
+// Call from ONE elected thread.
+template <bool PAIR>
+__device__ __forceinline__ void t3_mma_stage(uint32_t d_tmem, uint32_t a_base, uint32_t a_bytes, uint32_t b_base, uint32_t b_bytes,
+                                             uint32_t idesc32, uint32_t idesc16, bool first) {
+  const uint64_t ahi = umma_desc_sw128(a_base), ahb = umma_desc_sw64(a_base + a_bytes), alb = umma_desc_sw64(a_base + a_bytes + a_bytes / 2);
+  const uint64_t bhi = umma_desc_sw128(b_base), bhb = umma_desc_sw64(b_base + b_bytes), blb = umma_desc_sw64(b_base + b_bytes + b_bytes / 2);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) t3_mma16<PAIR>(d_tmem, alb + 2 * k, bhb + 2 * k, idesc16, (first && k == 0) ? 0u : 1u);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) t3_mma16<PAIR>(d_tmem, ahb + 2 * k, blb + 2 * k, idesc16, 1u);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) t3_mma<PAIR>(d_tmem, ahi + 2 * k, bhi + 2 * k, idesc32, 1u);
+}
+__device__ __forceinline__ void st_shared_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// Operand split of 16 consecutive values: hi = tf32(x) (fp32 words), and the BF16 companions of hi and of lo = x - hi
+struct T3Split16 {
+  float hi[16];
+  float lo[16];
+  uint32_t hb[8], lb[8];
+};
+__device__ __forceinline__ void t3_split16(const float* x, bool valid, T3Split16& o) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    o.hi[j] = valid ? tf32_rna(x[j]) : 0.f;
+    o.lo[j] = valid ? x[j] - o.hi[j] : 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    o.hb[j] = pack_bf16x2(o.hi[2 * j], o.hi[2 * j + 1]);
+    o.lb[j] = pack_bf16x2(o.lo[2 * j], o.lo[2 * j + 1]);
+  }
+}
+// staged tiles of one warp (32 rows): fp32 tile = 128-byte rows, SWIZZLE_128B; bf16 tile = 64-byte rows, SWIZZLE_64B.
+// `j4` = which group of 16 values of the thread's 32 (0 / 1).
+__device__ __forceinline__ void t3_stage_f32(uint32_t tile, int lane, int j4, const float* v) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t o = static_cast<uint32_t>(lane) * 128u + (static_cast<uint32_t>((j4 * 4 + c) ^ (lane & 7)) << 4);
+    st_shared_f4(tile + o, v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+  }
+}
+__device__ __forceinline__ void t3_stage_b16(uint32_t tile, int lane, int j4, const uint32_t* w) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const uint32_t o = static_cast<uint32_t>(lane) * 64u + (static_cast<uint32_t>((j4 * 2 + c) ^ ((lane >> 1) & 3)) << 4);
+    st_shared_u4(tile + o, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+  }
+}
+template <bool PAIR>
 __device__ __forceinline__ void t3_commit(uint32_t bar) {   // PAIR: arrives at this offset in BOTH CTAs
   if (PAIR) tc2_commit(bar);
   else tc_commit(bar);
@@ -212,12 +283,13 @@ __device__ __forceinline__ void t3_commit(uint32_t bar) {   // PAIR: arrives at 
 
 template <bool LAST, int BK = 32, bool PAIR = false, int EW = 8>
 __global__ void __launch_bounds__(t3_threads(EW), 1)
-tf32_gate_kernel(const __grid_constant__ CUtensorMap map_hh, const __grid_constant__ CUtensorMap map_hl,
-                 const __grid_constant__ CUtensorMap map_ch, const __grid_constant__ CUtensorMap map_cl,
-                 const __grid_constant__ CUtensorMap map_w1h, const __grid_constant__ CUtensorMap map_w1l,
-                 const __grid_constant__ CUtensorMap map_vh, const __grid_constant__ CUtensorMap map_vl,
-                 const __grid_constant__ CUtensorMap smap_hi, const __grid_constant__ CUtensorMap smap_lo,
+tf32_gate_kernel(const __grid_constant__ CUtensorMap map_hh, const __grid_constant__ CUtensorMap map_hb,
+                 const __grid_constant__ CUtensorMap map_ch, const __grid_constant__ CUtensorMap map_cb,
+                 const __grid_constant__ CUtensorMap map_w1h, const __grid_constant__ CUtensorMap map_w1b,
+                 const __grid_constant__ CUtensorMap map_vh, const __grid_constant__ CUtensorMap map_vb,
+                 const __grid_constant__ CUtensorMap smap_hi, const __grid_constant__ CUtensorMap smap_b,
                  const Tf32Params p) {
+  static_assert(BK == 32, "one 128-byte fp32 row / one 64-byte bf16 row per K-block");
   using G = T3G<BK, PAIR>;
   static_assert(EW == 8 || EW == 16, "8 or 16 epilogue warps");
   constexpr int T3_EPI_THREADS = EW * 32, T3_NCG = EW / 4;
@@ -243,8 +315,8 @@ tf32_gate_kernel(const __grid_constant__ CUtensorMap map_hh, const __grid_consta
   const long long t_entry = timing ? clock64() : 0;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&map_hh); prefetch_tmap(&map_hl); prefetch_tmap(&map_ch); prefetch_tmap(&map_cl);
-    prefetch_tmap(&map_w1h); prefetch_tmap(&map_w1l); prefetch_tmap(&map_vh); prefetch_tmap(&map_vl);
+    prefetch_tmap(&map_hh); prefetch_tmap(&map_hb); prefetch_tmap(&map_ch); prefetch_tmap(&map_cb);
+    prefetch_tmap(&map_w1h); prefetch_tmap(&map_w1b); prefetch_tmap(&map_vh); prefetch_tmap(&map_vb);
     for (int s = 0; s < T3G_STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -288,23 +360,24 @@ tf32_gate_kernel(const __grid_constant__ CUtensorMap map_hh, const __grid_consta
         if (elect_one()) {
           if (leader) mbar_expect_tx(full_bar(s), (PAIR ? 2 : 1) * T3G_STAGE_BYTES);   // PAIR: the bytes of both CTAs
           const int bq = q * T3G_BN + (PAIR ? static_cast<int>(rank) * (T3G_BN / 2) : 0);   // first B row this CTA loads
-          const uint32_t a_hi = smem_base + s * T3G_STAGE_BYTES, a_lo = a_hi + T3G_A_BYTES;
-          const uint32_t b_hi = a_lo + T3G_A_BYTES, b_lo = b_hi + T3G_B_BYTES;
+          // stage = [A_hi | A_hb | A_lb][B_hi | B_hb | B_lb]  (t3_mma_stage)
+          const uint32_t a_hi = smem_base + s * T3G_STAGE_BYTES, a_b = a_hi + T3G_A_BYTES;
+          const uint32_t b_hi = a_b + T3G_A_BYTES, b_b = b_hi + T3G_B_BYTES;
           if (kb < p.kb_conv) {
             // tap shifted by (tap-1)*dilation positions: phase (r+sh) mod R, frames moved by floor((r+sh)/R)
             const int tap = kb / cblks, cblk = kb - tap * cblks;
             const int rs = r + (tap - 1) * p.dilation;
             const int carry = (rs >= 0) ? rs / p.R : -((-rs + p.R - 1) / p.R);
             t3_load_4d<PAIR>(a_hi, &map_hh, full_bar(s), cblk * BK, t0 + carry, rs - carry * p.R, 0);
-            t3_load_4d<PAIR>(a_lo, &map_hl, full_bar(s), cblk * BK, t0 + carry, rs - carry * p.R, 0);
+            t3_load_b_4d<PAIR>(a_b, T3G_A_BYTES / 2, &map_hb, full_bar(s), p.C, cblk * BK, t0 + carry, rs - carry * p.R, 0);
             t3_load_2d<PAIR>(b_hi, &map_w1h, full_bar(s), kb * BK, p.layer * 2 * p.C + bq);
-            t3_load_2d<PAIR>(b_lo, &map_w1l, full_bar(s), kb * BK, p.layer * 2 * p.C + bq);
+            t3_load_b_2d<PAIR>(b_b, T3G_B_BYTES / 2, &map_w1b, full_bar(s), 3 * p.C, kb * BK, p.layer * 2 * p.C + bq);
           } else {
             const int kc = kb - p.kb_conv;
             t3_load_4d<PAIR>(a_hi, &map_ch, full_bar(s), kc * BK, t0, 0, 0);
-            t3_load_4d<PAIR>(a_lo, &map_cl, full_bar(s), kc * BK, t0, 0, 0);
+            t3_load_b_4d<PAIR>(a_b, T3G_A_BYTES / 2, &map_cb, full_bar(s), p.kb_cond * BK, kc * BK, t0, 0, 0);
             t3_load_2d<PAIR>(b_hi, &map_vh, full_bar(s), kc * BK, p.wc_row0 + r * p.wc_rstride + bq);
-            t3_load_2d<PAIR>(b_lo, &map_vl, full_bar(s), kc * BK, p.wc_row0 + r * p.wc_rstride + bq);
+            t3_load_b_2d<PAIR>(b_b, T3G_B_BYTES / 2, &map_vb, full_bar(s), p.kb_cond * BK, kc * BK, p.wc_row0 + r * p.wc_rstride + bq);
           }
         }
         __syncwarp();
@@ -314,6 +387,7 @@ tf32_gate_kernel(const __grid_constant__ CUtensorMap map_hh, const __grid_consta
   } else if (warp == 1) {
     // =========================== MMA issuer (PAIR: the leader CTA only) ========================
     constexpr uint32_t idesc = umma_idesc_tf32(PAIR ? 2 * T3_BM : T3_BM, T3G_BN);
+    constexpr uint32_t idesc16 = umma_idesc_bf16(PAIR ? 2 * T3_BM : T3_BM, T3G_BN);
     uint32_t it = 0, n = 0;
     long long t_full = 0, t_epi = 0;
     const long long t_begin = timing ? clock64() : 0;
@@ -331,16 +405,8 @@ tf32_gate_kernel(const __grid_constant__ CUtensorMap map_hh, const __grid_consta
         if (timing) t_full += clock64() - tq;
         tc_fence_after();
         const uint32_t base = smem_base + s * T3G_STAGE_BYTES;
-        const uint64_t ahi = t3_desc<BK>(base), alo = t3_desc<BK>(base + T3G_A_BYTES);
-        const uint64_t bhi = t3_desc<BK>(base + 2 * T3G_A_BYTES), blo = t3_desc<BK>(base + 2 * T3G_A_BYTES + T3G_B_BYTES);
         if (elect_one()) {
-          // small cross terms first, then the main product (K = 8 floats = 32 bytes per instruction: +2 in the descriptor)
-#pragma unroll
-          for (int k = 0; k < BK / 8; ++k) t3_mma<PAIR>(d_tmem, alo + 2 * k, bhi + 2 * k, idesc, (kb | k) ? 1u : 0u);
-#pragma unroll
-          for (int k = 0; k < BK / 8; ++k) t3_mma<PAIR>(d_tmem, ahi + 2 * k, blo + 2 * k, idesc, 1u);
-#pragma unroll
-          for (int k = 0; k < BK / 8; ++k) t3_mma<PAIR>(d_tmem, ahi + 2 * k, bhi + 2 * k, idesc, 1u);
+          t3_mma_stage<PAIR>(d_tmem, base, T3G_A_BYTES, base + 2 * T3G_A_BYTES, T3G_B_BYTES, idesc, idesc16, kb == 0);
           t3_commit<PAIR>(empty_bar(s));
           if (kb == kb1 - 1) t3_commit<PAIR>(accfull_bar(as));
         }
@@ -368,7 +434,7 @@ tf32_gate_kernel(const __grid_constant__ CUtensorMap map_hh, const __grid_consta
     // stages its 32 x 32 (hi, lo) output tiles there (128-byte swizzled rows) and writes them with two TMA stores
     // instead of 16 row-strided 16-byte stores per thread (32 half-filled sectors per instruction).
     const bool stage_out = !LAST && EW == 16 && n_items <= item_step;
-    const uint32_t stg_hi = smem_base + static_cast<uint32_t>(we) * 8192u, stg_lo = stg_hi + 4096u;
+    const uint32_t stg_hi = smem_base + static_cast<uint32_t>(we) * 8192u, stg_hb = stg_hi + 4096u, stg_lb = stg_hi + 6144u;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     uint32_t n = 0;
@@ -418,26 +484,22 @@ tf32_gate_kernel(const __grid_constant__ CUtensorMap map_hh, const __grid_consta
             o8[pi][6] = fmaf(a[j], w1.z, o8[pi][6]); o8[pi][7] = fmaf(a[j], w1.w, o8[pi][7]);
           }
           if (!LAST && (stage_out || (t0 + row) < p.T)) {
-            float hi[16], lo[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              hi[j] = valid ? tf32_rna(a[j]) : 0.f;
-              lo[j] = valid ? a[j] - hi[j] : 0.f;
-            }
+            T3Split16 sp;
+            t3_split16(a, valid, sp);
             if (stage_out) {
-#pragma unroll
-              for (int v = 0; v < 4; ++v) {
-                const uint32_t o = static_cast<uint32_t>(lane) * 128u + (static_cast<uint32_t>((g2 * 4 + v) ^ (lane & 7)) << 4);
-                st_shared_f4(stg_hi + o, hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
-                st_shared_f4(stg_lo + o, lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
-              }
+              t3_stage_f32(stg_hi, lane, g2, sp.hi);
+              t3_stage_b16(stg_hb, lane, g2, sp.hb);
+              t3_stage_b16(stg_lb, lane, g2, sp.lb);
             } else {
               float4* dh = reinterpret_cast<float4*>(p.acts_hi + m * p.C + q * 128 + ch0);
-              float4* dl = reinterpret_cast<float4*>(p.acts_lo + m * p.C + q * 128 + ch0);
+              uint4* db = reinterpret_cast<uint4*>(p.acts_b + m * 2 * p.C + q * 128 + ch0);
+              uint4* dl = reinterpret_cast<uint4*>(p.acts_b + m * 2 * p.C + p.C + q * 128 + ch0);
 #pragma unroll
-              for (int v = 0; v < 4; ++v) {
-                dh[v] = make_float4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
-                dl[v] = make_float4(lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
+              for (int v = 0; v < 4; ++v) dh[v] = make_float4(sp.hi[4 * v], sp.hi[4 * v + 1], sp.hi[4 * v + 2], sp.hi[4 * v + 3]);
+#pragma unroll
+              for (int v = 0; v < 2; ++v) {
+                db[v] = make_uint4(sp.hb[4 * v], sp.hb[4 * v + 1], sp.hb[4 * v + 2], sp.hb[4 * v + 3]);
+                dl[v] = make_uint4(sp.lb[4 * v], sp.lb[4 * v + 1], sp.lb[4 * v + 2], sp.lb[4 * v + 3]);
               }
             }
           }
@@ -448,7 +510,8 @@ tf32_gate_kernel(const __grid_constant__ CUtensorMap map_hh, const __grid_consta
         __syncwarp();
         if (lane == 0) {
           tma_store_4d(&smap_hi, stg_hi, q * 128 + cg * CH, t0 + quarter * 32, r, 0);
-          tma_store_4d(&smap_lo, stg_lo, q * 128 + cg * CH, t0 + quarter * 32, r, 0);
+          tma_store_4d(&smap_b, stg_hb, q * 128 + cg * CH, t0 + quarter * 32, r, 0);
+          tma_store_4d(&smap_b, stg_lb, p.C + q * 128 + cg * CH, t0 + quarter * 32, r, 0);
           bulk_commit();
         }
       }
@@ -497,10 +560,10 @@ tf32_gate_kernel(const __grid_constant__ CUtensorMap map_hh, const __grid_consta
 
 template <bool PAIR = false, int EW = 8>
 __global__ void __launch_bounds__(t3_threads(EW), 1)
-tf32_res_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
-                const __grid_constant__ CUtensorMap map_w2h, const __grid_constant__ CUtensorMap map_w2l,
+tf32_res_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_ab,
+                const __grid_constant__ CUtensorMap map_w2h, const __grid_constant__ CUtensorMap map_w2b,
                 const __grid_constant__ CUtensorMap smap_hi, const __grid_constant__ CUtensorMap smap_lo,
-                const Tf32Params p) {
+                const __grid_constant__ CUtensorMap smap_b, const Tf32Params p) {
   using G = T3RG<PAIR>;
   static_assert(EW == 8 || EW == 16, "8 or 16 epilogue warps");
   constexpr int T3_EPI_THREADS = EW * 32, T3_NCG = EW / 4;
@@ -525,7 +588,7 @@ tf32_res_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
   const long long t_entry = timing ? clock64() : 0;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&map_ah); prefetch_tmap(&map_al); prefetch_tmap(&map_w2h); prefetch_tmap(&map_w2l);
+    prefetch_tmap(&map_ah); prefetch_tmap(&map_ab); prefetch_tmap(&map_w2h); prefetch_tmap(&map_w2b);
     for (int s = 0; s < T3R_STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -567,12 +630,12 @@ tf32_res_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
         if (elect_one()) {
           if (leader) mbar_expect_tx(full_bar(s), (PAIR ? 2 : 1) * T3R_STAGE_BYTES);
           const int bq = q * T3R_BN + (PAIR ? static_cast<int>(rank) * (T3R_BN / 2) : 0);
-          const uint32_t a_hi = smem_base + s * T3R_STAGE_BYTES, a_lo = a_hi + T3_A_BYTES;
-          const uint32_t b_hi = a_lo + T3_A_BYTES, b_lo = b_hi + T3R_B_BYTES;
+          const uint32_t a_hi = smem_base + s * T3R_STAGE_BYTES, a_b = a_hi + T3_A_BYTES;
+          const uint32_t b_hi = a_b + T3_A_BYTES, b_b = b_hi + T3R_B_BYTES;
           t3_load_4d<PAIR>(a_hi, &map_ah, full_bar(s), kb * T3_BK, t0, r, 0);
-          t3_load_4d<PAIR>(a_lo, &map_al, full_bar(s), kb * T3_BK, t0, r, 0);
+          t3_load_b_4d<PAIR>(a_b, T3_A_BYTES / 2, &map_ab, full_bar(s), p.C, kb * T3_BK, t0, r, 0);
           t3_load_2d<PAIR>(b_hi, &map_w2h, full_bar(s), kb * T3_BK, p.layer * p.C + bq);
-          t3_load_2d<PAIR>(b_lo, &map_w2l, full_bar(s), kb * T3_BK, p.layer * p.C + bq);
+          t3_load_b_2d<PAIR>(b_b, T3R_B_BYTES / 2, &map_w2b, full_bar(s), p.C, kb * T3_BK, p.layer * p.C + bq);
         }
         __syncwarp();
       }
@@ -580,6 +643,7 @@ tf32_res_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
     if (timing && lane == 0) atomicAdd(p.timing + 38, static_cast<unsigned long long>(t_wait));
   } else if (warp == 1) {
     constexpr uint32_t idesc = umma_idesc_tf32(PAIR ? 2 * T3_BM : T3_BM, T3R_BN);
+    constexpr uint32_t idesc16 = umma_idesc_bf16(PAIR ? 2 * T3_BM : T3_BM, T3R_BN);
     uint32_t it = 0, n = 0;
     long long t_full = 0, t_epi = 0;
     const long long t_begin = timing ? clock64() : 0;
@@ -597,15 +661,8 @@ tf32_res_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
         if (timing) t_full += clock64() - tq;
         tc_fence_after();
         const uint32_t base = smem_base + s * T3R_STAGE_BYTES;
-        const uint64_t ahi = umma_desc_sw128(base), alo = umma_desc_sw128(base + T3_A_BYTES);
-        const uint64_t bhi = umma_desc_sw128(base + 2 * T3_A_BYTES), blo = umma_desc_sw128(base + 2 * T3_A_BYTES + T3R_B_BYTES);
         if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < T3_BK / 8; ++k) t3_mma<PAIR>(d_tmem, alo + 2 * k, bhi + 2 * k, idesc, (kb | k) ? 1u : 0u);
-#pragma unroll
-          for (int k = 0; k < T3_BK / 8; ++k) t3_mma<PAIR>(d_tmem, ahi + 2 * k, blo + 2 * k, idesc, 1u);
-#pragma unroll
-          for (int k = 0; k < T3_BK / 8; ++k) t3_mma<PAIR>(d_tmem, ahi + 2 * k, bhi + 2 * k, idesc, 1u);
+          t3_mma_stage<PAIR>(d_tmem, base, T3_A_BYTES, base + 2 * T3_A_BYTES, T3R_B_BYTES, idesc, idesc16, kb == 0);
           t3_commit<PAIR>(empty_bar(s));
           if (kb == kb2 - 1) t3_commit<PAIR>(accfull_bar(as));
         }
@@ -632,7 +689,9 @@ tf32_res_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
     // (it does not depend on this layer's MMAs): the loads' latency hides behind the MMAs instead of following them.
     constexpr bool PREFETCH = CH <= 32;
     const bool stage_out = EW == 16 && n_items <= item_step;   // see tf32_gate_kernel
-    const uint32_t stg_hi = smem_base + static_cast<uint32_t>(we) * 8192u, stg_lo = stg_hi + 4096u;
+    // per warp: h_hi and the exact h_lo (fp32: the next residual add reads h = hi + lo) and the BF16 MMA companions
+    const uint32_t stg_hi = smem_base + static_cast<uint32_t>(we) * 12288u, stg_lo = stg_hi + 4096u, stg_hb = stg_hi + 8192u,
+                   stg_lb = stg_hi + 10240u;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     uint32_t n = 0;
@@ -669,34 +728,33 @@ tf32_res_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
       auto finish = [&](int g, const uint32_t* rr, const float* old) {
         if (!in_range && !stage_out) return;
         const size_t off = off0 + g * 16;
-        float hi[16], lo[16];
-        if (valid) {
-          // h_new = (acts @ Wres + b) + h   (waveglow_arch.py:131-133)
+        float x[16];
+        // h_new = (acts @ Wres + b) + h   (waveglow_arch.py:131-133); a gap row is the next layer's zero padding
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float x = (__uint_as_float(rr[j]) + s_b2[cg * CH + g * 16 + j]) + old[j];
-            hi[j] = tf32_rna(x);
-            lo[j] = x - hi[j];
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) hi[j] = lo[j] = 0.f;     // gap row: the next layer's zero padding
-        }
+        for (int j = 0; j < 16; ++j) x[j] = (__uint_as_float(rr[j]) + s_b2[cg * CH + g * 16 + j]) + old[j];
+        T3Split16 sp;
+        t3_split16(x, valid, sp);
         if (stage_out) {
-#pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            const uint32_t o = static_cast<uint32_t>(lane) * 128u + (static_cast<uint32_t>((g * 4 + v) ^ (lane & 7)) << 4);
-            st_shared_f4(stg_hi + o, hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
-            st_shared_f4(stg_lo + o, lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
-          }
+          t3_stage_f32(stg_hi, lane, g, sp.hi);
+          t3_stage_f32(stg_lo, lane, g, sp.lo);
+          t3_stage_b16(stg_hb, lane, g, sp.hb);
+          t3_stage_b16(stg_lb, lane, g, sp.lb);
           return;
         }
         float4* dh = reinterpret_cast<float4*>(p.ho_hi + off);
         float4* dl = reinterpret_cast<float4*>(p.ho_lo + off);
+        const size_t offb = (m * 2 * p.C) + (off - m * p.C);
+        uint4* db = reinterpret_cast<uint4*>(p.ho_b + offb);
+        uint4* dlb = reinterpret_cast<uint4*>(p.ho_b + offb + p.C);
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
-          dh[v] = make_float4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
-          dl[v] = make_float4(lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
+          dh[v] = make_float4(sp.hi[4 * v], sp.hi[4 * v + 1], sp.hi[4 * v + 2], sp.hi[4 * v + 3]);
+          dl[v] = make_float4(sp.lo[4 * v], sp.lo[4 * v + 1], sp.lo[4 * v + 2], sp.lo[4 * v + 3]);
+        }
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          db[v] = make_uint4(sp.hb[4 * v], sp.hb[4 * v + 1], sp.hb[4 * v + 2], sp.hb[4 * v + 3]);
+          dlb[v] = make_uint4(sp.lb[4 * v], sp.lb[4 * v + 1], sp.lb[4 * v + 2], sp.lb[4 * v + 3]);
         }
       };
       if (PREFETCH) {
@@ -724,6 +782,8 @@ tf32_res_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
         if (lane == 0) {
           tma_store_4d(&smap_hi, stg_hi, q * T3R_BN + cg * CH, t0 + quarter * 32, r, 0);
           tma_store_4d(&smap_lo, stg_lo, q * T3R_BN + cg * CH, t0 + quarter * 32, r, 0);
+          tma_store_4d(&smap_b, stg_hb, q * T3R_BN + cg * CH, t0 + quarter * 32, r, 0);
+          tma_store_4d(&smap_b, stg_lb, p.C + q * T3R_BN + cg * CH, t0 + quarter * 32, r, 0);
           bulk_commit();
         }
       }
@@ -749,7 +809,7 @@ tf32_res_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
 
 // ---- helper kernels ---------------------------------------------------------------------------------------------
 // mel window (A operand of the conditioning) as an fp32 (hi, lo) pair; rows follow one phase block (RowGeom, R = 1)
-__global__ void tf32_im2col_kernel(const float* __restrict__ mel, float* __restrict__ a_hi, float* __restrict__ a_lo,
+__global__ void tf32_im2col_kernel(const float* __restrict__ mel, float* __restrict__ a_hi, __nv_bfloat16* __restrict__ a_b,
                                    const RowGeom geo, int n_mel, int Kup) {
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<size_t>(geo.rows_per_phase()) * Kup) return;
@@ -762,11 +822,12 @@ __global__ void tf32_im2col_kernel(const float* __restrict__ mel, float* __restr
   if (valid && j < 4 && t - j >= 0) v = mel[(static_cast<size_t>(b) * geo.T + t - j) * n_mel + i];
   const float hi = tf32_rna(v);
   a_hi[idx] = hi;
-  a_lo[idx] = v - hi;
+  a_b[static_cast<size_t>(row) * 2 * Kup + kk] = __float2bfloat16_rn(hi);
+  a_b[static_cast<size_t>(row) * 2 * Kup + Kup + kk] = __float2bfloat16_rn(v - hi);
 }
 
-// folded conditioning weights: in [(r, k), n] fp32 -> (hi, lo)[(r*N + n)*K + k]
-__global__ void fold_store_tf32_kernel(const float* __restrict__ in, float* __restrict__ o_hi, float* __restrict__ o_lo,
+// folded conditioning weights: in [(r, k), n] fp32 -> hi[(r*N + n)*K + k] (fp32) and b[(r*N + n)*2K + {k, K + k}] (bf16 hi | lo)
+__global__ void fold_store_tf32_kernel(const float* __restrict__ in, float* __restrict__ o_hi, __nv_bfloat16* __restrict__ o_b,
                                        int R, int K, int N) {
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<size_t>(R) * K * N) return;
@@ -776,7 +837,8 @@ __global__ void fold_store_tf32_kernel(const float* __restrict__ in, float* __re
   const float v = in[(static_cast<size_t>(r) * K + k) * N + n];
   const float hi = tf32_rna(v);
   o_hi[idx] = hi;
-  o_lo[idx] = v - hi;
+  o_b[rn * 2 * K + k] = __float2bfloat16_rn(hi);
+  o_b[rn * 2 * K + K + k] = __float2bfloat16_rn(v - hi);
 }
 
 // ---- host side --------------------------------------------------------------------------------------------------
@@ -796,12 +858,40 @@ inline void make_map_f32(CUtensorMap* m, const void* ptr, int rank, const uint64
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) fail(WG_ERR_CUDA, "cuTensorMapEncodeTiled (fp32) failed with CUresult %d", (int)r);
 }
-inline void make_map_f32_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, int bk = T3_BK) {
+// bf16 companion arrays [.., rows, 2K]: boxes of 32 elements (64-byte rows, SWIZZLE_64B)
+inline void make_map_b16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint32_t* box) {
+  cuuint64_t gdim[4], gstr[3];
+  cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
+  uint64_t stride = 2;
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    stride *= dims[i];
+    if (i < rank - 1) gstr[i] = stride;
+  }
+  CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) fail(WG_ERR_CUDA, "cuTensorMapEncodeTiled (bf16 companion) failed with CUresult %d", (int)r);
+}
+inline void make_map_b16_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t K, uint32_t box_rows) {
+  const uint64_t dims[2] = {2 * K, rows};
+  const uint32_t box[2] = {32, box_rows};
+  make_map_b16(m, ptr, 2, dims, box);
+}
+inline void make_map_b16_4d(CUtensorMap* m, const void* ptr, uint64_t phases, uint64_t rows, uint64_t K, uint32_t box_rows = T3_BM) {
+  const uint64_t dims[4] = {2 * K, rows, phases, 1};
+  const uint32_t box[4] = {32, box_rows, 1, 1};
+  make_map_b16(m, ptr, 4, dims, box);
+}
+inline void make_map_f32_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  const int bk = T3_BK;
   const uint64_t dims[2] = {cols, rows};
   const uint32_t box[2] = {(uint32_t)bk, box_rows};
   make_map_f32(m, ptr, 2, dims, box);
 }
-inline void make_map_f32_4d(CUtensorMap* m, const void* ptr, uint64_t phases, uint64_t rows, uint64_t cols, int bk = T3_BK) {
+inline void make_map_f32_4d(CUtensorMap* m, const void* ptr, uint64_t phases, uint64_t rows, uint64_t cols) {
+  const int bk = T3_BK;
   const uint64_t dims[4] = {cols, rows, phases, 1};
   const uint32_t box[4] = {(uint32_t)bk, T3_BM, 1, 1};
   make_map_f32(m, ptr, 4, dims, box);
@@ -845,12 +935,8 @@ inline int tf32_init() {
 #define WG_T3_ATTRS(EWV)                                                                   \
   WG_T3_ATTR((tf32_gate_kernel<false, 32, false, EWV>), (T3G<32, false>::SMEM));           \
   WG_T3_ATTR((tf32_gate_kernel<true, 32, false, EWV>), (T3G<32, false>::SMEM));            \
-  WG_T3_ATTR((tf32_gate_kernel<false, 16, false, EWV>), (T3G<16, false>::SMEM));           \
-  WG_T3_ATTR((tf32_gate_kernel<true, 16, false, EWV>), (T3G<16, false>::SMEM));            \
   WG_T3_ATTR((tf32_gate_kernel<false, 32, true, EWV>), (T3G<32, true>::SMEM));             \
   WG_T3_ATTR((tf32_gate_kernel<true, 32, true, EWV>), (T3G<32, true>::SMEM));              \
-  WG_T3_ATTR((tf32_gate_kernel<false, 16, true, EWV>), (T3G<16, true>::SMEM));             \
-  WG_T3_ATTR((tf32_gate_kernel<true, 16, true, EWV>), (T3G<16, true>::SMEM));              \
   WG_T3_ATTR((tf32_res_kernel<false, EWV>), T3RG<false>::SMEM);                            \
   WG_T3_ATTR((tf32_res_kernel<true, EWV>), T3RG<true>::SMEM)
   WG_T3_ATTRS(8);
@@ -863,71 +949,80 @@ inline int tf32_init() {
 }
 
 struct Tf32Plan {
-  CUtensorMap m_h_hi[2], m_h_lo[2], m_c_hi, m_c_lo, m_w1h, m_w1l, m_vh, m_vl, m_a_hi, m_a_lo, m_w2h, m_w2l;
-  CUtensorMap p_w1h, p_w1l, p_vh, p_vl, p_w2h, p_w2l;   // CTA-pair variants: boxes of HALF a chunk's B rows
-  CUtensorMap s_a_hi, s_a_lo, s_h_hi[2], s_h_lo[2];     // 32 x 32 boxes for the staged TMA stores of the epilogues
+  // "*_hi": fp32 words holding tf32(x) (TF32 MMAs); "*_b": the bf16 companion [.., 2K] = bf16(hi) | bf16(lo) (cross terms)
+  CUtensorMap m_h_hi[2], m_h_b[2], m_c_hi, m_c_b, m_w1h, m_w1b, m_vh, m_vb, m_a_hi, m_a_b, m_w2h, m_w2b;
+  CUtensorMap p_w1h, p_w1b, p_vh, p_vb, p_w2h, p_w2b;   // CTA-pair variants: boxes of HALF a chunk's B rows
+  CUtensorMap s_a_hi, s_a_b, s_h_hi[2], s_h_lo[2], s_h_b[2];   // 32 x 32 boxes for the staged TMA stores of the epilogues
   int max_pairs = 0;     // resident CTA pairs (tf32_init); 0 = single-CTA kernels only
   bool pair = false;     // this plan runs the CTA-pair kernels
   int epi_warps = 0;     // 0 = by shape (16 when every CTA runs one item, else 8); 8 / 16 force (WG_TF32_EPI, A/B)
   Tf32Params base{};
   RowGeom geo1{};
   int sm_count = 0, n_mel = 0, Kup = 0;
-  int gate_bk = 32;      // K-block width of the gate kernel (WG_TF32_BK=16: SWIZZLE_64B ring of twice as many, half-size stages)
-  float *h_hi[2] = {nullptr, nullptr}, *h_lo[2] = {nullptr, nullptr}, *aup_hi = nullptr, *aup_lo = nullptr;
+  float *h_hi[2] = {nullptr, nullptr}, *h_lo[2] = {nullptr, nullptr}, *aup_hi = nullptr;
+  __nv_bfloat16 *h_b[2] = {nullptr, nullptr}, *aup_b = nullptr;
 };
 
 struct Tf32Weights {   // device pointers, stacked over all layers
-  const float *W1h, *W1l;   // [n_layers_total * 2C, 3C]  chunk-packed rows, K-major
-  const float *Vh, *Vl;     // [n_layers_total * R * 2C, Kup]
-  const float *W2h, *W2l;   // [n_layers_total * C, C]
+  const float* W1h;  const __nv_bfloat16* W1b;   // [n_layers_total * 2C, 3C] (+ [.., 6C])  chunk-packed rows, K-major
+  const float* Vh;   const __nv_bfloat16* Vb;    // [n_layers_total * R * 2C, Kup]
+  const float* W2h;  const __nv_bfloat16* W2b;   // [n_layers_total * C, C]
+};
+
+struct Tf32Buffers {   // per-call scratch (engine workspace)
+  float *h_hi[2], *h_lo[2];        // residual stream: tf32(h) and the exact remainder (the residual add reads h = hi + lo)
+  __nv_bfloat16* h_b[2];           // its bf16 companion
+  float* aup_hi; __nv_bfloat16* aup_b;       // mel window (conditioning A operand)
+  float* acts_hi; __nv_bfloat16* acts_b;     // gate output / residual A operand
+  float* acc8; size_t acc8_stride;           // skip/end fold partials
 };
 
 // rows1 = rows of one phase block (B*(T+gap), or the ragged total); geo1 = that block's utterance geometry (R = 1)
 inline void tf32_prepare(Tf32Plan& pl, int sm_count, int C, int R, int Kup, int n_mel, int n_layers_total, int rows1,
-                         const RowGeom& geo1, int Tp, int Tv, const Tf32Weights& w, float* h_hi0, float* h_hi1,
-                         float* h_lo0, float* h_lo1, float* aup_hi, float* aup_lo, float* acts_hi, float* acts_lo,
-                         float* acc8, size_t acc8_stride, int gate_bk = 32, int max_pairs = 0, int pair_policy = -1, int epi_warps = 0) {
+                         const RowGeom& geo1, int Tp, int Tv, const Tf32Weights& w, const Tf32Buffers& b,
+                         int max_pairs = 0, int pair_policy = -1, int epi_warps = 0) {
   if (C % 128 || Kup % T3_BK) fail(WG_ERR_UNSUPPORTED, "tf32x3 path needs n_channels %% 128 == 0 (got %d)", C);
-  pl.gate_bk = gate_bk == 16 ? 16 : 32;
   pl.epi_warps = epi_warps;
-  const int gbk = pl.gate_bk;
   pl.sm_count = sm_count; pl.n_mel = n_mel; pl.Kup = Kup; pl.geo1 = geo1;
-  pl.h_hi[0] = h_hi0; pl.h_hi[1] = h_hi1; pl.h_lo[0] = h_lo0; pl.h_lo[1] = h_lo1; pl.aup_hi = aup_hi; pl.aup_lo = aup_lo;
+  for (int i = 0; i < 2; ++i) { pl.h_hi[i] = b.h_hi[i]; pl.h_lo[i] = b.h_lo[i]; pl.h_b[i] = b.h_b[i]; }
+  pl.aup_hi = b.aup_hi; pl.aup_b = b.aup_b;
   Tf32Params& p = pl.base;
   p.T = rows1; p.R = R; p.tiles_per_row = (rows1 + T3_BM - 1) / T3_BM; p.n_tiles = p.tiles_per_row * R;
   p.C = C; p.Tp = Tp; p.Tv = Tv; p.row_b = geo1.row_b;
-  p.acts_hi = acts_hi; p.acts_lo = acts_lo; p.acc8 = acc8; p.acc8_stride = acc8_stride;
+  p.acts_hi = b.acts_hi; p.acts_b = b.acts_b; p.acc8 = b.acc8; p.acc8_stride = b.acc8_stride;
+  const uint64_t LT = (uint64_t)n_layers_total;
   for (int i = 0; i < 2; ++i) {
-    make_map_f32_4d(&pl.m_h_hi[i], pl.h_hi[i], R, rows1, C, gbk);
-    make_map_f32_4d(&pl.m_h_lo[i], pl.h_lo[i], R, rows1, C, gbk);
+    make_map_f32_4d(&pl.m_h_hi[i], pl.h_hi[i], R, rows1, C);
+    make_map_b16_4d(&pl.m_h_b[i], pl.h_b[i], R, rows1, C);
   }
-  make_map_f32_4d(&pl.m_c_hi, aup_hi, 1, rows1, Kup, gbk);
-  make_map_f32_4d(&pl.m_c_lo, aup_lo, 1, rows1, Kup, gbk);
-  make_map_f32_4d(&pl.m_a_hi, acts_hi, R, rows1, C);
-  make_map_f32_4d(&pl.m_a_lo, acts_lo, R, rows1, C);
-  make_map_f32_2d(&pl.m_w1h, w.W1h, (uint64_t)n_layers_total * 2 * C, 3 * C, T3G_BN, gbk);
-  make_map_f32_2d(&pl.m_w1l, w.W1l, (uint64_t)n_layers_total * 2 * C, 3 * C, T3G_BN, gbk);
-  make_map_f32_2d(&pl.m_vh, w.Vh, (uint64_t)n_layers_total * R * 2 * C, Kup, T3G_BN, gbk);
-  make_map_f32_2d(&pl.m_vl, w.Vl, (uint64_t)n_layers_total * R * 2 * C, Kup, T3G_BN, gbk);
-  make_map_f32_2d(&pl.m_w2h, w.W2h, (uint64_t)n_layers_total * C, C, T3R_BN);
-  make_map_f32_2d(&pl.m_w2l, w.W2l, (uint64_t)n_layers_total * C, C, T3R_BN);
+  make_map_f32_4d(&pl.m_c_hi, b.aup_hi, 1, rows1, Kup);
+  make_map_b16_4d(&pl.m_c_b, b.aup_b, 1, rows1, Kup);
+  make_map_f32_4d(&pl.m_a_hi, b.acts_hi, R, rows1, C);
+  make_map_b16_4d(&pl.m_a_b, b.acts_b, R, rows1, C);
+  make_map_f32_2d(&pl.m_w1h, w.W1h, LT * 2 * C, 3 * C, T3G_BN);
+  make_map_b16_2d(&pl.m_w1b, w.W1b, LT * 2 * C, 3 * C, T3G_BN);
+  make_map_f32_2d(&pl.m_vh, w.Vh, LT * R * 2 * C, Kup, T3G_BN);
+  make_map_b16_2d(&pl.m_vb, w.Vb, LT * R * 2 * C, Kup, T3G_BN);
+  make_map_f32_2d(&pl.m_w2h, w.W2h, LT * C, C, T3R_BN);
+  make_map_b16_2d(&pl.m_w2b, w.W2b, LT * C, C, T3R_BN);
   {
     const uint64_t dims[4] = {(uint64_t)C, (uint64_t)rows1, (uint64_t)R, 1};
     const uint32_t box[4] = {32, 32, 1, 1};
-    make_map_f32(&pl.s_a_hi, acts_hi, 4, dims, box);
-    make_map_f32(&pl.s_a_lo, acts_lo, 4, dims, box);
+    make_map_f32(&pl.s_a_hi, b.acts_hi, 4, dims, box);
+    make_map_b16_4d(&pl.s_a_b, b.acts_b, R, rows1, C, 32);
     for (int i = 0; i < 2; ++i) {
       make_map_f32(&pl.s_h_hi[i], pl.h_hi[i], 4, dims, box);
       make_map_f32(&pl.s_h_lo[i], pl.h_lo[i], 4, dims, box);
+      make_map_b16_4d(&pl.s_h_b[i], pl.h_b[i], R, rows1, C, 32);
     }
   }
-  make_map_f32_2d(&pl.p_w1h, w.W1h, (uint64_t)n_layers_total * 2 * C, 3 * C, T3G_BN / 2, gbk);
-  make_map_f32_2d(&pl.p_w1l, w.W1l, (uint64_t)n_layers_total * 2 * C, 3 * C, T3G_BN / 2, gbk);
-  make_map_f32_2d(&pl.p_vh, w.Vh, (uint64_t)n_layers_total * R * 2 * C, Kup, T3G_BN / 2, gbk);
-  make_map_f32_2d(&pl.p_vl, w.Vl, (uint64_t)n_layers_total * R * 2 * C, Kup, T3G_BN / 2, gbk);
-  make_map_f32_2d(&pl.p_w2h, w.W2h, (uint64_t)n_layers_total * C, C, T3R_BN / 2);
-  make_map_f32_2d(&pl.p_w2l, w.W2l, (uint64_t)n_layers_total * C, C, T3R_BN / 2);
-  // CTA pairs halve the B bytes each SM pulls in and reads per MMA (the single-CTA kernel is bound by its operand feed);
+  make_map_f32_2d(&pl.p_w1h, w.W1h, LT * 2 * C, 3 * C, T3G_BN / 2);
+  make_map_b16_2d(&pl.p_w1b, w.W1b, LT * 2 * C, 3 * C, T3G_BN / 2);
+  make_map_f32_2d(&pl.p_vh, w.Vh, LT * R * 2 * C, Kup, T3G_BN / 2);
+  make_map_b16_2d(&pl.p_vb, w.Vb, LT * R * 2 * C, Kup, T3G_BN / 2);
+  make_map_f32_2d(&pl.p_w2h, w.W2h, LT * C, C, T3R_BN / 2);
+  make_map_b16_2d(&pl.p_w2b, w.W2b, LT * C, C, T3R_BN / 2);
+  // CTA pairs halve the B bytes each SM pulls in and reads per MMA and issue faster MMAs (tools/probes/mma_rate.cu);
   // a pair needs two tiles of one phase, so an odd tile count per phase block costs a ghost tile. pair_policy: 1 / 0
   // force, -1 = by wave count: (pair items / resident pairs) waves at ~0.7 of a single-CTA wave (measured).
   pl.max_pairs = max_pairs;
@@ -940,7 +1035,7 @@ inline void tf32_prepare(Tf32Plan& pl, int sm_count, int C, int R, int Kup, int 
 
 inline int tf32_upsample(const Tf32Plan& pl, const float* mel, cudaStream_t st) {
   const size_t total = (size_t)pl.geo1.rows_per_phase() * pl.Kup;
-  tf32_im2col_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(mel, pl.aup_hi, pl.aup_lo, pl.geo1, pl.n_mel, pl.Kup);
+  tf32_im2col_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(mel, pl.aup_hi, pl.aup_b, pl.geo1, pl.n_mel, pl.Kup);
   WG_CK(cudaGetLastError());
   return 1;
 }
@@ -951,7 +1046,7 @@ inline int tf32_wn_layer(const Tf32Plan& pl, int layer, int dilation, bool last,
   Tf32Params g = pl.base;
   g.timing = timing;
   g.layer = layer; g.dilation = dilation;
-  g.n_chunks = 2 * g.C / T3G_BN; g.kb_conv = 3 * g.C / pl.gate_bk; g.kb_cond = pl.Kup / pl.gate_bk;
+  g.n_chunks = 2 * g.C / T3G_BN; g.kb_conv = 3 * g.C / T3_BK; g.kb_cond = pl.Kup / T3_BK;
   g.wc_row0 = layer * g.R * 2 * g.C; g.wc_rstride = 2 * g.C;
   g.bias = b1; g.wse = wse;
   const bool pair = pl.pair;
@@ -969,28 +1064,23 @@ inline int tf32_wn_layer(const Tf32Plan& pl, int layer, int dilation, bool last,
   };
   const int grid_g = grid_for(g);
   const bool wide_g = pl.epi_warps == 16 || (pl.epi_warps == 0 && one_item(g));
-#define WG_T3G_LAUNCH2(LASTV, BKV, EWV)                                                                               \
+#define WG_T3G_LAUNCH2(LASTV, EWV)                                                                                    \
   do {                                                                                                                \
     if (pair)                                                                                                         \
-      t3_launch(tf32_gate_kernel<LASTV, BKV, true, EWV>, grid_g, EWV, T3G<BKV, true>::SMEM, st, true, pl.m_h_hi[hcur], \
-                pl.m_h_lo[hcur], pl.m_c_hi, pl.m_c_lo, pl.p_w1h, pl.p_w1l, pl.p_vh, pl.p_vl, pl.s_a_hi, pl.s_a_lo, g);                      \
+      t3_launch(tf32_gate_kernel<LASTV, 32, true, EWV>, grid_g, EWV, T3G<32, true>::SMEM, st, true, pl.m_h_hi[hcur],  \
+                pl.m_h_b[hcur], pl.m_c_hi, pl.m_c_b, pl.p_w1h, pl.p_w1b, pl.p_vh, pl.p_vb, pl.s_a_hi, pl.s_a_b, g);   \
     else                                                                                                              \
-      t3_launch(tf32_gate_kernel<LASTV, BKV, false, EWV>, grid_g, EWV, T3G<BKV, false>::SMEM, st, false,              \
-                pl.m_h_hi[hcur], pl.m_h_lo[hcur], pl.m_c_hi, pl.m_c_lo, pl.m_w1h, pl.m_w1l, pl.m_vh, pl.m_vl, pl.s_a_hi,  \
-                pl.s_a_lo, g);     \
+      t3_launch(tf32_gate_kernel<LASTV, 32, false, EWV>, grid_g, EWV, T3G<32, false>::SMEM, st, false,                \
+                pl.m_h_hi[hcur], pl.m_h_b[hcur], pl.m_c_hi, pl.m_c_b, pl.m_w1h, pl.m_w1b, pl.m_vh, pl.m_vb,           \
+                pl.s_a_hi, pl.s_a_b, g);                                                                              \
   } while (0)
-#define WG_T3G_LAUNCH(LASTV, BKV)              \
-  do {                                         \
-    if (wide_g) WG_T3G_LAUNCH2(LASTV, BKV, 16); \
-    else WG_T3G_LAUNCH2(LASTV, BKV, 8);         \
+#define WG_T3G_LAUNCH(LASTV)              \
+  do {                                    \
+    if (wide_g) WG_T3G_LAUNCH2(LASTV, 16); \
+    else WG_T3G_LAUNCH2(LASTV, 8);         \
   } while (0)
-  if (pl.gate_bk == 32) {
-    if (last) WG_T3G_LAUNCH(true, 32);
-    else WG_T3G_LAUNCH(false, 32);
-  } else {
-    if (last) WG_T3G_LAUNCH(true, 16);
-    else WG_T3G_LAUNCH(false, 16);
-  }
+  if (last) WG_T3G_LAUNCH(true);
+  else WG_T3G_LAUNCH(false);
 #undef WG_T3G_LAUNCH
 #undef WG_T3G_LAUNCH2
   WG_CK(cudaGetLastError());
@@ -1001,12 +1091,13 @@ inline int tf32_wn_layer(const Tf32Plan& pl, int layer, int dilation, bool last,
   r.n_chunks = r.C / T3R_BN; r.kb_conv = r.C / T3_BK; r.kb_cond = 0;
   r.bias = b2;
   r.h_hi = pl.h_hi[hcur]; r.h_lo = pl.h_lo[hcur]; r.ho_hi = pl.h_hi[hcur ^ 1]; r.ho_lo = pl.h_lo[hcur ^ 1];
+  r.ho_b = pl.h_b[hcur ^ 1];
   const int grid_r = grid_for(r);
   const bool wide_r = pl.epi_warps == 16 || (pl.epi_warps == 0 && one_item(r));
 #define WG_T3R_LAUNCH(EWV)                                                                                                      \
   do {                                                                                                                          \
-    if (pair) t3_launch(tf32_res_kernel<true, EWV>, grid_r, EWV, T3RG<true>::SMEM, st, true, pl.m_a_hi, pl.m_a_lo, pl.p_w2h, pl.p_w2l, pl.s_h_hi[hcur ^ 1], pl.s_h_lo[hcur ^ 1], r);   \
-    else t3_launch(tf32_res_kernel<false, EWV>, grid_r, EWV, T3RG<false>::SMEM, st, false, pl.m_a_hi, pl.m_a_lo, pl.m_w2h, pl.m_w2l, pl.s_h_hi[hcur ^ 1], pl.s_h_lo[hcur ^ 1], r);     \
+    if (pair) t3_launch(tf32_res_kernel<true, EWV>, grid_r, EWV, T3RG<true>::SMEM, st, true, pl.m_a_hi, pl.m_a_b, pl.p_w2h, pl.p_w2b, pl.s_h_hi[hcur ^ 1], pl.s_h_lo[hcur ^ 1], pl.s_h_b[hcur ^ 1], r);   \
+    else t3_launch(tf32_res_kernel<false, EWV>, grid_r, EWV, T3RG<false>::SMEM, st, false, pl.m_a_hi, pl.m_a_b, pl.m_w2h, pl.m_w2b, pl.s_h_hi[hcur ^ 1], pl.s_h_lo[hcur ^ 1], pl.s_h_b[hcur ^ 1], r);     \
   } while (0)
   if (wide_r) WG_T3R_LAUNCH(16);
   else WG_T3R_LAUNCH(8);
