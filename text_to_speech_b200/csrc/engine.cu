@@ -926,6 +926,10 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
     e->allocs.push_back(e->t3_flow.sync);
     CK(cudaMemset(e->t3_flow.sync, 0, 2 * sizeof(unsigned int)));
     if (const char* fl = std::getenv("WG_TF32_FLOW")) e->t3_flow_policy = std::atoi(fl);
+    // Nsight Compute refuses a cooperative launch of a cluster kernel ("LaunchFailed", which ends the profiled process):
+    // under its injection the flow kernel is launched plainly -- ncu serialises kernels, so co-residency holds anyway.
+    if (std::getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || std::getenv("NV_NSIGHT_INJECTION_PORT_BASE")) e->t3_flow.cooperative = false;
+    if (const char* co = std::getenv("WG_TF32_COOP")) e->t3_flow.cooperative = co[0] != '0';
     if (const char* ew = std::getenv("WG_TF32_EPI")) e->t3_epi_warps = std::atoi(ew) == 16 ? 16 : (std::atoi(ew) == 8 ? 8 : 0);
     // folded conditioning weights as an fp32 (hi, lo) pair: V[(layer*R + r)*2C + n][k] = sum_s Wup_r[k][s] * Wcond[s][n]
     const int Kw = e->Kup;

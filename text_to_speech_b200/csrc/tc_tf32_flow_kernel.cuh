@@ -433,6 +433,7 @@ tf32_flow_kernel(const __grid_constant__ Tf32FlowMaps maps, const __grid_constan
 struct Tf32FlowState {
   unsigned int* sync = nullptr;   // device: [arrivals, generation]
   int max_pairs = 0;              // co-resident CTA pairs of tf32_flow_kernel (0: unavailable)
+  bool cooperative = true;        // launch attribute: all CTAs co-resident or the launch fails (WG_TF32_COOP=0: plain launch)
 };
 
 inline int tf32_flow_init() {
@@ -495,7 +496,7 @@ inline int tf32_wn_flow(const Tf32Plan& pl, const Tf32FlowState& fs, int layer0,
   attr[1].id = cudaLaunchAttributeCooperative;
   attr[1].val.cooperative = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 2;
+  cfg.numAttrs = fs.cooperative ? 2 : 1;
   WG_CK(cudaLaunchKernelEx(&cfg, tf32_flow_kernel, m, fp));
   return 1;
 }

@@ -9,6 +9,7 @@ using namespace wg;
 // mode 0: f16 N256 one accumulator; 1: tf32 N256 one accumulator; 2: tf32 N256 two accumulators alternating;
 // 3: tf32 N128; 4: f16 N128; 5: tf32 SWIZZLE_64B descriptors N256; 6 / 7 / 8: CTA pair (cta_group::2, M = 256): f16 N256,
 // tf32 N256, tf32 N128 (launched as clusters of 2; the leader issues)
+template <bool pair>
 __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int mode, int n_mma, unsigned long long* cycles) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
@@ -16,7 +17,6 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int mode, int n_mma, u
   const uint32_t base = smem_u32(smem);
   for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
   const int warp = threadIdx.x >> 5;
-  const bool pair = mode >= 6;
   const bool leader = !pair || cluster_ctarank() == 0;
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&bar), 1);
@@ -42,8 +42,8 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int mode, int n_mma, u
       t0 = clock64();
       for (int i = 0; i < n_mma; ++i) {
         const uint32_t d = tm + ((mode == 2 && (i & 1)) ? 256u : 0u);
-        if (mode == 6) umma2_bf16(d, a + 2 * (i & 3), b + 2 * (i & 3), id16, i > 1);
-        else if (mode >= 7) umma2_tf32(d, a + 2 * (i & 3), b + 2 * (i & 3), id32, i > 1);
+        if (pair && mode == 6) umma2_bf16(d, a + 2 * (i & 3), b + 2 * (i & 3), id16, i > 1);
+        else if (pair) umma2_tf32(d, a + 2 * (i & 3), b + 2 * (i & 3), id32, i > 1);
         else if (mode == 0 || mode == 4) umma_bf16(d, a + 2 * (i & 3), b + 2 * (i & 3), id16, i > 1);
         else umma_tf32(d, a + 2 * (i & 3), b + 2 * (i & 3), id32, i > 1);
       }
@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int mode, int n_mma, u
 int main() {
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-  cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  cudaFuncSetAttribute(mma_rate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  cudaFuncSetAttribute(mma_rate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   unsigned long long* d;
   cudaMalloc(&d, sms * 8);
   const char* names[] = {"f16  M128 N256 K16", "tf32 M128 N256 K8", "tf32 M128 N256 K8, two accumulators", "tf32 M128 N128 K8",
@@ -90,7 +91,9 @@ int main() {
         attr.id = cudaLaunchAttributeClusterDimension;
         attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
         cfg.attrs = &attr; cfg.numAttrs = mode >= 6 ? 1 : 0;
-        cudaLaunchKernelEx(&cfg, mma_rate_kernel, mode, n, d);
+        cudaError_t le = mode >= 6 ? cudaLaunchKernelEx(&cfg, mma_rate_kernel<true>, mode, n, d)
+                                  : cudaLaunchKernelEx(&cfg, mma_rate_kernel<false>, mode, n, d);
+        if (le != cudaSuccess) { printf("launch error (mode %d): %s\n", mode, cudaGetErrorString(le)); return 1; }
         if (cudaDeviceSynchronize() != cudaSuccess) { printf("launch failed: %s\n", cudaGetErrorString(cudaGetLastError())); return 1; }
       }
       std::vector<unsigned long long> h(grid);
