@@ -45,11 +45,15 @@ def test_sass_is_blackwell_native(lib_built):
     bodies = {}
     for chunk in sass.split("Function : ")[1:]:
         bodies[chunk.split("\n", 1)[0].strip()] = chunk
-    for frag in ("tc_wn_layer_kernel", "tc_wn_pair_kernel", "tc512_gate_kernel", "tc512_res_kernel", "tf32_gate_kernel", "tf32_res_kernel"):
+    for frag in ("tc_wn_layer_kernel", "tc_wn_pair_kernel", "tc512_gate_kernel", "tc512_res_kernel", "tf32_gate_kernel", "tf32_res_kernel",
+                 "tf32_flow_kernel"):
         hits = [b for name, b in bodies.items() if frag in name]
         assert hits, f"no kernel named *{frag}* in the library"
         for b in hits:
             assert "UTCHMMA" in b and "UTMALDG" in b and "LDTM" in b, f"{frag}: not a tcgen05/TMA kernel"
+    # the one-launch-per-flow kernel writes its outputs with TMA stores (UTMASTG) and runs on CTA pairs (.2CTA MMAs)
+    flow = next(b for name, b in bodies.items() if "tf32_flow_kernel" in name)
+    assert "UTMASTG" in flow and "2CTA" in flow
 
 
 def test_null_arguments_are_rejected(lib_built):

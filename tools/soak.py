@@ -18,10 +18,12 @@ hp = WaveGlowHParams()
 weights = generate_weights(hp, 1234)
 bad = 0
 # (engine mode, WG_PAIR, shapes): the BF16 layer kernel as the engine picks it (CTA pairs for the big batch), the single-CTA
-# kernel forced, a ragged batch on either, and the tf32x3 kernels
+# kernel forced, a ragged batch on either, and the tf32x3 kernels: one persistent launch per flow with grid barriers (1 x 200,
+# the ragged 5 x 90), the per-layer CTA-pair kernels (2 x 150, 4 x 860) and the single-CTA ones
 for mode, pair, cases in (("bf16", "-1", ((16, 860, None), (3, 333, None), (1, 37, None), (12, 300, "ragged"))),
                           ("bf16", "0", ((16, 860, None), (12, 300, "ragged"))),
-                          ("tf32x3", "-1", ((2, 150, None), (5, 90, "ragged")))):
+                          ("tf32x3", "-1", ((1, 200, None), (5, 90, "ragged"), (2, 150, None), (4, 860, None))),
+                          ("tf32x3", "0", ((1, 200, None), (2, 150, None)))):
     os.environ["WG_PAIR"] = pair
     eng = WaveGlowEngine(hp, weights, mode=mode, device=0)
     for B, T, ragged in cases:
@@ -29,7 +31,7 @@ for mode, pair, cases in (("bf16", "-1", ((16, 860, None), (3, 333, None), (1, 3
         lengths = [max(1, T - 23 * b) for b in range(B)] if ragged else None
         mel_d, z_d = torch.from_numpy(mel).cuda(), torch.from_numpy(z).cuda()
         ref = eng.infer_device(mel_d, z_d, 0.6, lengths=lengths).clone()
-        n = (n_wg if B * T > 5000 else 3 * n_wg) // (1 if mode == "bf16" else 6)
+        n = (n_wg if B * T > 5000 else 3 * n_wg) // (1 if mode == "bf16" or B * T <= 500 else 6)
         for i in range(n):
             out = eng.infer_device(mel_d, z_d, 0.6, lengths=lengths)
             if not torch.equal(out, ref):
@@ -37,7 +39,7 @@ for mode, pair, cases in (("bf16", "-1", ((16, 860, None), (3, 333, None), (1, 3
                 print(f"WaveGlow {mode} {B}x{T}: run {i} differs, max {float((out - ref).abs().max()):.3e}")
         torch.cuda.synchronize()
         print(f"WaveGlow {mode} WG_PAIR={pair} {B}x{T}{' ragged' if ragged else ''}: {n} runs, pair kernel {eng.pair_info()[1]}, "
-              f"finite {bool(torch.isfinite(ref).all())}", flush=True)
+              f"launches per infer {eng.last_launch_count}, finite {bool(torch.isfinite(ref).all())}", flush=True)
     eng.close()
 thp = Tacotron2HParams()
 tw = generate_tacotron2_weights(thp, 77)
