@@ -1,25 +1,29 @@
-// WG_MODE_TF32X3 -- the fp32-grade WN layer on the 5th-gen tensor cores (tcgen05.mma kind::tf32), sm_100a only.
+// WG_MODE_TF32X3 -- the fp32-grade WN layer on the 5th-gen tensor cores (tcgen05.mma), sm_100a only.
 //
 // Reference arithmetic: architectures/waveglow_arch.py:19-24 (gate), :105-141 (WN layer) in fp32. The tensor cores
-// read TF32 (10 explicit mantissa bits), so every fp32 operand x travels as the pair
-//     x_hi = tf32(x)  (cvt.rna)          x_lo = x - x_hi   (exact in fp32; the MMA reads its top 11 bits)
-// and every product is issued three times:  a_hi*b_hi + a_lo*b_hi + a_hi*b_lo  (the dropped a_lo*b_lo term is
-// <= 2^-22 relative), accumulated in fp32 in TMEM: "3xTF32" (BASELINE.json north_star). The gate is evaluated in fp32
-// to ~2e-7 absolute (t3_gate_act). Everything else -- phase-major gapped row layout (RowGeom), the conditioning folded to the 4-frame mel
-// window (V = Wup_r @ Wcond, rank 320, exact in fp32), the skip->end fold into [C, 8] -- is the algebra of the BF16
-// path (tc_kernels.cuh), so ragged batches (wg_infer_ragged) work the same way.
+// read at most TF32 (10 explicit mantissa bits), so every fp32 operand x is split as
+//     x_hi = tf32(x)  (cvt.rna, kept in fp32 words)          x_lo = x - x_hi   (exact in fp32)
+// and every multiply is issued as three products, small terms first, into one fp32 TMEM accumulator:
+//     a_lo*b_hi + a_hi*b_lo   kind::f16 MMAs on a BF16 companion [.., 2K] = bf16(x_hi) | bf16(x_lo) of every operand
+//                             (the cross terms are 2^-11 of the product: 8 mantissa bits carry them to ~2e-7)
+//     a_hi*b_hi               kind::tf32 MMAs
+// (the dropped a_lo*b_lo term is <= 2^-22 relative): the "fp32/3xTF32 mode" of BASELINE.json's north_star. The gate is
+// evaluated in fp32 to ~2e-7 absolute (t3_gate_act). Everything else -- phase-major gapped row layout (RowGeom), the
+// conditioning folded to the 4-frame mel window (V = Wup_r @ Wcond, rank 320, exact in fp32), the skip->end fold into
+// [C, 8] -- is the algebra of the BF16 path (tc_kernels.cuh), so ragged batches (wg_infer_ragged) work the same way.
 //
-// Two kernels per layer (the fp32 acts tile, 128 x C x 2 x 4 B, does not fit beside the operand ring):
+// Two kernels per layer (the fp32 acts tile does not fit beside the operand ring):
 //   tf32_gate_kernel   item = (128-row tile, 256-column chunk q of the gate pre-activation = 128 tanh + 128 sigmoid
-//                      channels).  GEMM1 [128 x (3C + 320)] @ [(3C + 320) x 256], K-blocks of 16 floats (64-byte
-//                      swizzled rows), 4-stage TMA ring of {A_hi, A_lo, B_hi, B_lo} = 48 KB, 6 MMAs per stage
-//                      (WG_TF32_BK=32: K-blocks of 32 floats, 2 stages of 96 KB -- measured 7.5 % slower at K1);
-//                      epilogue: gate, acts -> (hi, lo) in HBM, skip/end fold into this chunk's OWN partial
-//                      accumulator acc8[q] (no cross-CTA race: the flow boundary sums the partials in a fixed order).
-//   tf32_res_kernel    item = (128-row tile, 128-column chunk of the residual half).  GEMM2 acts[128 x C] @ Wres,
-//                      3-stage ring of 64 KB; epilogue: h = acc + b + (h_hi + h_lo) -> (hi, lo) for the next layer.
+//                      channels).  GEMM1 [128 x (3C + 320)] @ [(3C + 320) x 256] in K-blocks of 32; one pipeline stage =
+//                      [A_hi fp32 | A_hb | A_lb bf16][B_hi | B_hb | B_lb] (t3_mma_stage);
+//                      epilogue: gate, acts -> split -> HBM, skip/end fold into this chunk's OWN partial accumulator
+//                      acc8[q] (no cross-CTA race: the flow boundary sums the partials in a fixed order).
+//   tf32_res_kernel    item = (128-row tile, 128-column chunk of the residual half).  GEMM2 acts[128 x C] @ Wres;
+//                      epilogue: h = acc + b + (h_hi + h_lo) -> split for the next layer (h keeps its exact fp32 x_lo).
 // Both are persistent (static schedule) with a double-buffered TMEM accumulator so the epilogue of one item overlaps
-// the MMAs of the next. K1 (1 x 200 frames) is 32 phases x 2 tiles = 64 tiles -> 128 gate items: one item per CTA, one wave.
+// the MMAs of the next, and exist for single CTAs and for CTA pairs (PAIR: cta_group::2, tc_pair_kernels.cuh's
+// protocol), with 8 or 16 epilogue warps (EW). All variants, and tf32_flow_kernel (tc_tf32_flow_kernel.cuh: one
+// persistent launch per flow for a single utterance), produce the same bits.
 #pragma once
 #include "tc_pair_kernels.cuh"
 
@@ -91,21 +95,20 @@ constexpr int T3_BM = 128, T3_BK = 32;                 // 32 floats = one 128-by
 constexpr int T3_A_BYTES = T3_BM * T3_BK * 4;          // 16 KB
 // Epilogue warps EW (template parameter, 8 or 16): NCG = EW / 4 warps share a TMEM lane quarter and split the accumulator
 // columns. A single utterance runs ONE item per CTA, so the epilogue is not hidden behind the next item's MMAs and its
-// latency (accurate tanhf / expf; 2 warps per scheduler with EW = 8) is paid per layer: 16 warps there (K1 7.8 -> 7.1 ms);
-// with several items per CTA the epilogue is hidden and 8 warps are faster (8 x 860: 141 vs 150 ms). Same bits either way:
+// latency (2 warps per scheduler with EW = 8) is paid per layer: 16 warps there (K1 7.8 -> 7.1 ms when it was introduced);
+// with several items per CTA the epilogue is hidden and 8 warps are faster (8 x 860: 130 vs 145 ms). Same bits either way:
 // the skip/end fold has one canonical order.
 constexpr int t3_threads(int ew) { return 64 + ew * 32; }
-// gate kernel: N = 256 per item. K-block width BK floats per stage: 32 (one 128-byte swizzle row, 2 stages of 96 KB) or
-// 16 (64-byte swizzle rows, 4 stages of 48 KB): the same 192 KB ring in finer slices keeps more bytes in flight while the
-// MMA works on a stage -- the kernel is bound by the latency of its operand feed (8 B per operand element for the fp32 pairs).
+// gate kernel: N = 256 per item, K-blocks of BK = 32 (a 128-byte fp32 row / a 64-byte bf16 row): 8 B per operand element
+// (4 of hi + 2 + 2 of the bf16 companion), a 192 KB ring of 2 stages (single CTA) or 3 stages (CTA pair).
 constexpr int T3G_BN = 256;
 template <int BK, bool PAIR = false>
 struct T3G {
-  static_assert(BK == 32 || BK == 16, "K-block of 32 floats (SWIZZLE_128B) or 16 floats (SWIZZLE_64B)");
+  static_assert(BK == 32, "K-block of 32: 128-byte fp32 rows (SWIZZLE_128B), 64-byte bf16 rows (SWIZZLE_64B)");
   // PAIR: this CTA holds its own 128 A rows and 128 of the chunk's 256 B rows (the other half sits in the peer CTA)
   static constexpr int A_BYTES = T3_BM * BK * 4, B_BYTES = (PAIR ? T3G_BN / 2 : T3G_BN) * BK * 4;
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;                // 96 / 48 KB;  pair: 64 / 32 KB
-  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;                    // 2 / 4;  pair: 3 / 6
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;                // 96 KB;  pair: 64 KB  (hi + companion, A and B)
+  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;                    // 2;  pair: 3
   static constexpr int OFF_B1 = STAGES * STAGE_BYTES;
   static constexpr int OFF_O8 = OFF_B1 + 256 * 4;
   static constexpr int OFF_BARS = OFF_O8 + 3 * T3_BM * 8 * 4;   // fold partials of column groups 1 .. NCG-1 (NCG <= 4)
@@ -122,10 +125,6 @@ __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(4) << 61;
   return d;
-}
-template <int BK>
-__device__ __forceinline__ uint64_t t3_desc(uint32_t smem_addr) {
-  return BK == 32 ? umma_desc_sw128(smem_addr) : umma_desc_sw64(smem_addr);
 }
 // residual kernel: N = 128 per item
 constexpr int T3R_BN = 128;
@@ -843,7 +842,7 @@ __global__ void fold_store_tf32_kernel(const float* __restrict__ in, float* __re
 
 // ---- host side --------------------------------------------------------------------------------------------------
 inline void make_map_f32(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint32_t* box) {
-  const CUtensorMapSwizzle swz = box[0] == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;   // 64- or 128-byte rows
+  const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B;   // boxes of 32 floats = 128-byte rows
   cuuint64_t gdim[4], gstr[3];
   cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
   uint64_t stride = 4;
