@@ -176,3 +176,40 @@ def test_tf32x3_flow_kernel_under_a_cuda_graph_and_on_two_streams(lib_built):
     assert np.array_equal(o1.cpu().numpy(), ref) and np.array_equal(o2.cpu().numpy(), ref)
     e1.close()
     e2.close()
+
+
+def test_tf32x3_one_handle_on_two_streams(lib_built):
+    """include/wg_b200.h: a handle is immutable after wg_create -- concurrent wg_infer calls with different workspaces
+    are safe. For the flow kernel that means its grid-barrier words live in the CALLER's workspace, not in the handle:
+    two host threads drive one handle (one call per flow kernel, one on the per-layer kernels), every result
+    bit-identical to the serial run."""
+    import threading
+    hp = WaveGlowHParams()
+    eng = _engine(hp, generate_weights(hp, 1234))
+    lib, h = eng._lib, eng._h
+    jobs = []
+    for seed, (B, T) in enumerate([(1, 200), (1, 120), (2, 333)]):
+        mel, z = synthetic_inputs(700 + seed, B, T, hp)
+        serial = _run(eng, mel, z, 0.6)
+        nbytes = eng.workspace_bytes(B, T)
+        ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device="cuda")
+        jobs.append(dict(B=B, T=T, serial=serial, mel=torch.from_numpy(mel).cuda(), z=torch.from_numpy(z).cuda(),
+                         out=torch.zeros(B, T * 256, device="cuda"), ws=ws, ws_ptr=(ws.data_ptr() + 1023) // 1024 * 1024,
+                         ws_bytes=nbytes, stream=torch.cuda.Stream(), rc=[]))
+    torch.cuda.synchronize()
+
+    def worker(j):
+        for _ in range(8):
+            j["rc"].append(lib.wg_infer(h, j["mel"].data_ptr(), j["z"].data_ptr(), 0.6, 0, j["B"], j["T"],
+                                        j["out"].data_ptr(), j["ws_ptr"], j["ws_bytes"], j["stream"].cuda_stream))
+
+    threads = [threading.Thread(target=worker, args=(j,)) for j in jobs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    torch.cuda.synchronize()
+    for j in jobs:
+        assert j["rc"] == [0] * 8, lib.wg_last_error(h)
+        assert np.array_equal(j["out"].cpu().numpy(), j["serial"])
+    eng.close()

@@ -183,7 +183,7 @@ struct Ws {  // workspace carving for one (B, T)
   size_t spect = 0, h32 = 0, acts = 0, skip = 0, acc8 = 0, audio0 = 0, audio1 = 0;
   size_t spect16 = 0, h16a = 0, h16b = 0, hlo = 0, aup16 = 0, acts16 = 0, a0 = 0;
   size_t g_off = 0, g_len = 0, g_rowb = 0;   // ragged geometry tables (RowGeom)
-  size_t t3_hhi0 = 0, t3_hhi1 = 0, t3_hlo0 = 0, t3_hlo1 = 0, t3_hb0 = 0, t3_hb1 = 0, t3_ahi = 0, t3_ab = 0, t3_chi = 0, t3_cb = 0;
+  size_t t3_hhi0 = 0, t3_hhi1 = 0, t3_hlo0 = 0, t3_hlo1 = 0, t3_hb0 = 0, t3_hb1 = 0, t3_ahi = 0, t3_ab = 0, t3_chi = 0, t3_cb = 0, t3_sync = 0;
   size_t total = 0;
 };
 
@@ -255,6 +255,7 @@ Ws carve(const wg_engine* e, int B, int T, const Ragged* rg = nullptr) {
     w.t3_hb0 = take(M * e->C * 4); w.t3_hb1 = take(M * e->C * 4);
     w.t3_ahi = take(M * e->C * 4); w.t3_ab = take(M * e->C * 4);
     w.t3_chi = take(rows1 * e->Kup * 4); w.t3_cb = take(rows1 * e->Kup * 4);
+    w.t3_sync = take(2 * sizeof(unsigned int));   // grid-barrier words of tf32_flow_kernel: per CALL, a handle may run two at once
     if (rg) {
       w.g_off = take((size_t)B * 4);
       w.g_len = take((size_t)B * 4);
@@ -390,6 +391,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
   TcPairMaps pmaps;
   Tc512PairMaps pmaps512;
   Tf32Plan plan3;
+  Tf32FlowState flow3;
   // ---- (1) upsample + trim + regroup: spect[B*L, S]  (waveglow_arch.py:245-253) ---------------
   if (tf32) {
     RowGeom geo1 = geo;
@@ -403,6 +405,12 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
                  rg ? 0 : geo.Tp, geo.T, e->t3, tb, e->t3_max_pairs, e->pair_policy, e->t3_epi_warps);
     e->last_pair = plan3.pair ? 1 : 0;
     e->last_flow_kernel = 0;
+    flow3 = e->t3_flow;
+    flow3.sync = reinterpret_cast<unsigned int*>(base + w.t3_sync);
+    if (e->t3_flow_policy != 0 && tf32_flow_fits(plan3, flow3.max_pairs, c.n_layers)) {
+      CK(cudaMemsetAsync(flow3.sync, 0, 2 * sizeof(unsigned int), st));   // arrivals = 0; the barrier re-arms itself afterwards
+      e->launches++;
+    }
     e->launches += tf32_upsample(plan3, mel, st);
   } else if (ffma) {
     GemmArgs g{};
@@ -489,7 +497,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
       const int d = 1 << i;
       const bool last = i == c.n_layers - 1;
       if (tf32 && i == 0 && e->t3_flow_policy != 0 && !(k == stop_flow && stop_layer >= 0) &&
-          tf32_flow_fits(plan3, e->t3_flow.max_pairs, c.n_layers)) {
+          tf32_flow_fits(plan3, flow3.max_pairs, c.n_layers)) {
         // single-wave call: the whole flow as ONE persistent launch (grid barriers instead of kernel boundaries)
         const float *b1s[T3F_MAX_LAYERS], *b2s[T3F_MAX_LAYERS], *wses[T3F_MAX_LAYERS];
         for (int j = 0; j < c.n_layers; ++j) {
@@ -498,7 +506,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
         }
         prof_mark();
         if (e->profiling) e->ev_count.push_back(c.n_layers);
-        e->launches += tf32_wn_flow(plan3, e->t3_flow, k * c.n_layers, c.n_layers, hcur, b1s, b2s, wses, st, e->timing);
+        e->launches += tf32_wn_flow(plan3, flow3, k * c.n_layers, c.n_layers, hcur, b1s, b2s, wses, st, e->timing);
         prof_mark();
         if ((c.n_layers - 1) & 1) hcur ^= 1;
         e->last_flow_kernel = 1;
@@ -922,9 +930,6 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
     e->t3_max_pairs = std::min(tf32_init(), e->sm_count / 2);
     if (const char* pr = std::getenv("WG_PAIR")) e->pair_policy = std::atoi(pr);
     e->t3_flow.max_pairs = std::min(tf32_flow_init(), e->sm_count / 2);
-    CK(cudaMalloc(&e->t3_flow.sync, 2 * sizeof(unsigned int)));
-    e->allocs.push_back(e->t3_flow.sync);
-    CK(cudaMemset(e->t3_flow.sync, 0, 2 * sizeof(unsigned int)));
     if (const char* fl = std::getenv("WG_TF32_FLOW")) e->t3_flow_policy = std::atoi(fl);
     // Nsight Compute refuses a cooperative launch of a cluster kernel ("LaunchFailed", which ends the profiled process):
     // under its injection the flow kernel is launched plainly -- ncu serialises kernels, so co-residency holds anyway.
