@@ -13,7 +13,8 @@ LISTINGS = {   # demangled-name fragment -> file suffix
     "wg::tc_wn_layer_kernel<false, false>": "tc_wn_layer_kernel_0",
     "wg::tc_wn_layer_kernel<false, true>": "tc_wn_layer_kernel_first",
     "wg::tc_wn_pair_kernel<false, false, 8>": "tc_wn_pair_kernel_0",
-    "wg::tf32_gate_kernel<false>": "tf32_gate_kernel_0",
+    "wg::tf32_gate_kernel<false, 32, true, 8>": "tf32_gate_kernel_0",
+    "wg::tf32_flow_kernel": "tf32_flow_kernel",
     "wg::flow_boundary_kernel": "flow_boundary_kernel",
     "mel_frames_kernel": "mel_frames_kernel",
     "lstm_mma_kernel": "lstm_mma_kernel",
@@ -21,7 +22,7 @@ LISTINGS = {   # demangled-name fragment -> file suffix
 
 
 def main():
-    prefix = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    prefix = sys.argv[1] if len(sys.argv) > 1 else "r02"
     sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
     kernels, cur = [], None
     for line in sass.splitlines():
