@@ -817,8 +817,9 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
             for (int kk = 0; kk < 3 * C; ++kk) {
               const float v = wsrc(kk, col), hi = tf32_rna_host(v);
               t3w1h[row + kk] = hi;
-              t3w1b[2 * row + kk] = f2bf(hi);
-              t3w1b[2 * row + 3 * C + kk] = f2bf(v - hi);
+              const size_t bp = 2 * row + 64 * (size_t)(kk >> 5) + (kk & 31);   // B operand: [lb | hb] per K-block of 32
+              t3w1b[bp] = f2bf(v - hi);
+              t3w1b[bp + 32] = f2bf(hi);
             }
           } else {
             for (int kk = 0; kk < K1; ++kk) w1[(size_t)pcol * K1 + kk] = f2bf(wsrc(kk, col));
@@ -890,8 +891,9 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
                 const size_t at = (((size_t)k * NL + i) * C + n) * C + kk;
                 const size_t rowb = (((size_t)k * NL + i) * C + n) * 2 * C;
                 t3w2h[at] = tf32_rna_host(v);
-                t3w2b[rowb + kk] = f2bf(t3w2h[at]);
-                t3w2b[rowb + C + kk] = f2bf(v - t3w2h[at]);
+                const size_t bp = rowb + 64 * (size_t)(kk >> 5) + (kk & 31);
+                t3w2b[bp] = f2bf(v - t3w2h[at]);
+                t3w2b[bp + 32] = f2bf(t3w2h[at]);
               } else {
                 w2[(size_t)n * C + kk] = f2bf(v);
               }

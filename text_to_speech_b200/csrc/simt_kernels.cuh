@@ -284,7 +284,7 @@ struct BoundaryArgs {
   __nv_bfloat16* hlo;     // [M, C] or null: bf16(h - bf16(h))
   float* hf_hi;           // [M, C] or null: tf32(h)            (tf32x3 mode: residual stream = hi + lo, both fp32)
   float* hf_lo;           // [M, C] or null: h - tf32(h)
-  __nv_bfloat16* hf_b;    // [M, 2C] or null: bf16(hi) | bf16(lo), the operands of the cross-term MMAs (tc_tf32_kernels.cuh)
+  __nv_bfloat16* hf_b;    // [M, 2C] or null: per 32 channels bf16(hi) x 32 | bf16(lo) x 32, the operands of the cross-term MMAs (tc_tf32_kernels.cuh)
   int acc_parts;          // acc8 is the sum of this many partial accumulators (tf32x3: one per gate chunk), >= 1
   size_t acc_part_stride; // floats between two partials
   int M;
@@ -434,8 +434,10 @@ flow_boundary_kernel(const __grid_constant__ BoundaryArgs a) {
         hb[q] = *reinterpret_cast<const uint32_t*>(&ph);
         lb[q] = *reinterpret_cast<const uint32_t*>(&pl);
       }
-      *reinterpret_cast<uint4*>(a.hf_b + (size_t)m * 2 * a.C + c8) = make_uint4(hb[0], hb[1], hb[2], hb[3]);
-      *reinterpret_cast<uint4*>(a.hf_b + (size_t)m * 2 * a.C + a.C + c8) = make_uint4(lb[0], lb[1], lb[2], lb[3]);
+      // A-operand companion: per K-block of 32 channels [hb x 32 | lb x 32]
+      __nv_bfloat16* bp = a.hf_b + (size_t)m * 2 * a.C + 64 * (c8 >> 5) + (c8 & 31);
+      *reinterpret_cast<uint4*>(bp) = make_uint4(hb[0], hb[1], hb[2], hb[3]);
+      *reinterpret_cast<uint4*>(bp + 32) = make_uint4(lb[0], lb[1], lb[2], lb[3]);
     }
   }
 }

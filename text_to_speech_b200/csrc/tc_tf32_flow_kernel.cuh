@@ -174,16 +174,16 @@ tf32_flow_kernel(const __grid_constant__ Tf32FlowMaps maps, const __grid_constan
             const int rs = r + (tap - 1) * dil;
             const int carry = (rs >= 0) ? rs / p.R : -((-rs + p.R - 1) / p.R);
             tma2_load_4d(a_hi, &maps.hh[hcur], fb, cblk * BK, t0 + carry, rs - carry * p.R, 0);
-            t3_load_b_4d<true>(a_b, GA / 2, &maps.hb[hcur], gfull(s), p.C, cblk * BK, t0 + carry, rs - carry * p.R, 0);
+            t3_load_b_4d<true>(a_b, &maps.hb[hcur], gfull(s), cblk * BK, t0 + carry, rs - carry * p.R, 0);
             tma2_load_2d(b_hi, &maps.w1h, fb, kb * BK, layer * 2 * p.C + bq);
-            t3_load_b_2d<true>(b_b, GB / 2, &maps.w1b, gfull(s), 3 * p.C, kb * BK, layer * 2 * p.C + bq);
+            t3_load_b_2d<true>(b_b, &maps.w1b, gfull(s), kb * BK, layer * 2 * p.C + bq);
           } else {
             const int kc = kb - kb_conv;
             const int vrow = layer * p.R * 2 * p.C + r * 2 * p.C + bq;
             tma2_load_4d(a_hi, &maps.ch, fb, kc * BK, t0, 0, 0);
-            t3_load_b_4d<true>(a_b, GA / 2, &maps.cb, gfull(s), kb_cond * BK, kc * BK, t0, 0, 0);
+            t3_load_b_4d<true>(a_b, &maps.cb, gfull(s), kc * BK, t0, 0, 0);
             tma2_load_2d(b_hi, &maps.vh, fb, kc * BK, vrow);
-            t3_load_b_2d<true>(b_b, GB / 2, &maps.vb, gfull(s), kb_cond * BK, kc * BK, vrow);
+            t3_load_b_2d<true>(b_b, &maps.vb, gfull(s), kc * BK, vrow);
           }
         }
         __syncwarp();
@@ -202,9 +202,9 @@ tf32_flow_kernel(const __grid_constant__ Tf32FlowMaps maps, const __grid_constan
           const uint32_t fb = rfull(s) & kPeerBitMask;
           const uint32_t a_hi = smem_base + s * RSB, a_b = a_hi + T3_A_BYTES, b_hi = a_b + T3_A_BYTES, b_b = b_hi + RB;
           tma2_load_4d(a_hi, &maps.ah, fb, kb * BK, t0, r, 0);
-          t3_load_b_4d<true>(a_b, T3_A_BYTES / 2, &maps.ab, rfull(s), p.C, kb * BK, t0, r, 0);
+          t3_load_b_4d<true>(a_b, &maps.ab, rfull(s), kb * BK, t0, r, 0);
           tma2_load_2d(b_hi, &maps.w2h, fb, kb * BK, layer * p.C + b2q);
-          t3_load_b_2d<true>(b_b, RB / 2, &maps.w2b, rfull(s), p.C, kb * BK, layer * p.C + b2q);
+          t3_load_b_2d<true>(b_b, &maps.w2b, rfull(s), kb * BK, layer * p.C + b2q);
         }
         __syncwarp();
       }
@@ -265,7 +265,7 @@ tf32_flow_kernel(const __grid_constant__ Tf32FlowMaps maps, const __grid_constan
     const int cg = we >> 2;             // column group: 32 of the chunk's 128 gate channels / residual columns
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
-    // staging tiles of this warp: gate (acts) hi 4 KB | hb 2 KB | lb 2 KB;  residual (h) hi | lo 4 KB each | hb | lb 2 KB each
+    // staging tiles of this warp: gate (acts) hi 4 KB | companion 4 KB;  residual (h) hi | lo | companion, 4 KB each
     const uint32_t stg = smem_base + static_cast<uint32_t>(we) * 12288u;
     const bool valid = t3_row_valid(p, t0 + row);
     const size_t m = static_cast<size_t>(r) * p.T + t0 + row;
@@ -313,8 +313,8 @@ tf32_flow_kernel(const __grid_constant__ Tf32FlowMaps maps, const __grid_constan
             T3Split16 sp;
             t3_split16(a, valid, sp);
             t3_stage_f32(stg, lane, g2, sp.hi);
-            t3_stage_b16(stg + 4096u, lane, g2, sp.hb);
-            t3_stage_b16(stg + 6144u, lane, g2, sp.lb);
+            t3_stage_b16(stg + 4096u, lane, g2, sp.hb, false);
+            t3_stage_b16(stg + 4096u, lane, g2, sp.lb, true);
           }
         }
       }
@@ -323,8 +323,7 @@ tf32_flow_kernel(const __grid_constant__ Tf32FlowMaps maps, const __grid_constan
         __syncwarp();
         if (lane == 0) {
           tma_store_4d(&maps.sah, stg, q * 128 + cg * CH, t0 + quarter * 32, r, 0);
-          tma_store_4d(&maps.sab, stg + 4096u, q * 128 + cg * CH, t0 + quarter * 32, r, 0);
-          tma_store_4d(&maps.sab, stg + 6144u, p.C + q * 128 + cg * CH, t0 + quarter * 32, r, 0);
+          tma_store_4d(&maps.sab, stg + 4096u, 2 * (q * 128 + cg * CH), t0 + quarter * 32, r, 0);
           bulk_commit();
         }
       }
@@ -392,8 +391,8 @@ tf32_flow_kernel(const __grid_constant__ Tf32FlowMaps maps, const __grid_constan
           t3_split16(x, valid, sp);
           t3_stage_f32(stg, lane, g, sp.hi);
           t3_stage_f32(stg + 4096u, lane, g, sp.lo);
-          t3_stage_b16(stg + 8192u, lane, g, sp.hb);
-          t3_stage_b16(stg + 10240u, lane, g, sp.lb);
+          t3_stage_b16(stg + 8192u, lane, g, sp.hb, false);
+          t3_stage_b16(stg + 8192u, lane, g, sp.lb, true);
         }
       }
       fence_proxy_async_smem();
@@ -401,8 +400,7 @@ tf32_flow_kernel(const __grid_constant__ Tf32FlowMaps maps, const __grid_constan
       if (lane == 0) {
         tma_store_4d(&maps.shh[hcur ^ 1], stg, q * T3R_BN + cg * CH, t0 + quarter * 32, r, 0);
         tma_store_4d(&maps.shl[hcur ^ 1], stg + 4096u, q * T3R_BN + cg * CH, t0 + quarter * 32, r, 0);
-        tma_store_4d(&maps.shb[hcur ^ 1], stg + 8192u, q * T3R_BN + cg * CH, t0 + quarter * 32, r, 0);
-        tma_store_4d(&maps.shb[hcur ^ 1], stg + 10240u, p.C + q * T3R_BN + cg * CH, t0 + quarter * 32, r, 0);
+        tma_store_4d(&maps.shb[hcur ^ 1], stg + 8192u, 2 * (q * T3R_BN + cg * CH), t0 + quarter * 32, r, 0);
         bulk_commit();
         bulk_wait0();
       }

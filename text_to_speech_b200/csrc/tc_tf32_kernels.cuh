@@ -209,31 +209,29 @@ __device__ __forceinline__ void t3_mma16(uint32_t d, uint64_t a, uint64_t b, uin
   if (PAIR) umma2_bf16(d, a, b, idesc, acc);
   else umma_bf16(d, a, b, idesc, acc);
 }
-// The (bf16(hi) | bf16(lo)) companion of a 32-float K-block: two boxes of 32 bf16 (64-byte rows) from the array
-// [.., 2K], at columns c0 and K + c0, landing in two consecutive half-size tiles.
+// The bf16 companion of an operand: [.., 2K], per K-block of 32 one 128-byte row segment of 64 bf16 --
+//     A operands (h, acts, mel window):  [ bf16(hi) x 32 | bf16(lo) x 32 ]
+//     B operands (W1, V, W2):            [ bf16(lo) x 32 | bf16(hi) x 32 ]
+// so that ONE K = 64 sweep of BF16 MMAs over a companion tile pair gives both cross terms, a_hi*b_lo + a_lo*b_hi, and a
+// K-block is one TMA box of 128-byte rows (two boxes of 64-byte rows cost the SM's TMA port twice the row requests).
 template <bool PAIR>
-__device__ __forceinline__ void t3_load_b_2d(uint32_t dst, uint32_t tile_bytes, const CUtensorMap* m, uint32_t bar, int K, int c0, int c1) {
-  t3_load_2d<PAIR>(dst, m, bar, c0, c1);
-  t3_load_2d<PAIR>(dst + tile_bytes, m, bar, K + c0, c1);
+__device__ __forceinline__ void t3_load_b_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  t3_load_2d<PAIR>(dst, m, bar, 2 * c0, c1);
 }
 template <bool PAIR>
-__device__ __forceinline__ void t3_load_b_4d(uint32_t dst, uint32_t tile_bytes, const CUtensorMap* m, uint32_t bar, int K, int c0, int c1,
-                                             int c2, int c3) {
-  t3_load_4d<PAIR>(dst, m, bar, c0, c1, c2, c3);
-  t3_load_4d<PAIR>(dst + tile_bytes, m, bar, K + c0, c1, c2, c3);
+__device__ __forceinline__ void t3_load_b_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+  t3_load_4d<PAIR>(dst, m, bar, 2 * c0, c1, c2, c3);
 }
-// One pipeline stage = one K-block of 32: [A_hi fp32 | A_hb | A_lb bf16][B_hi | B_hb | B_lb].  Small cross terms first
-// (BF16 MMAs, K = 16 each), then the main product (TF32 MMAs, K = 8 each), all into the same fp32 accumulator.
-// Call from ONE elected thread.
+// One pipeline stage = one K-block of 32: [A_hi fp32 | A_b bf16][B_hi | B_b], all 128-byte rows (SWIZZLE_128B). Small cross
+// terms first (4 BF16 MMAs, K = 16 each, over the 64 companion columns), then the main product (4 TF32 MMAs, K = 8 each),
+// all into the same fp32 accumulator. Call from ONE elected thread.
 template <bool PAIR>
 __device__ __forceinline__ void t3_mma_stage(uint32_t d_tmem, uint32_t a_base, uint32_t a_bytes, uint32_t b_base, uint32_t b_bytes,
                                              uint32_t idesc32, uint32_t idesc16, bool first) {
-  const uint64_t ahi = umma_desc_sw128(a_base), ahb = umma_desc_sw64(a_base + a_bytes), alb = umma_desc_sw64(a_base + a_bytes + a_bytes / 2);
-  const uint64_t bhi = umma_desc_sw128(b_base), bhb = umma_desc_sw64(b_base + b_bytes), blb = umma_desc_sw64(b_base + b_bytes + b_bytes / 2);
+  const uint64_t ahi = umma_desc_sw128(a_base), ab = umma_desc_sw128(a_base + a_bytes);
+  const uint64_t bhi = umma_desc_sw128(b_base), bb = umma_desc_sw128(b_base + b_bytes);
 #pragma unroll
-  for (int k = 0; k < 2; ++k) t3_mma16<PAIR>(d_tmem, alb + 2 * k, bhb + 2 * k, idesc16, (first && k == 0) ? 0u : 1u);
-#pragma unroll
-  for (int k = 0; k < 2; ++k) t3_mma16<PAIR>(d_tmem, ahb + 2 * k, blb + 2 * k, idesc16, 1u);
+  for (int k = 0; k < 4; ++k) t3_mma16<PAIR>(d_tmem, ab + 2 * k, bb + 2 * k, idesc16, (first && k == 0) ? 0u : 1u);
 #pragma unroll
   for (int k = 0; k < 4; ++k) t3_mma<PAIR>(d_tmem, ahi + 2 * k, bhi + 2 * k, idesc32, 1u);
 }
@@ -258,8 +256,8 @@ __device__ __forceinline__ void t3_split16(const float* x, bool valid, T3Split16
     o.lb[j] = pack_bf16x2(o.lo[2 * j], o.lo[2 * j + 1]);
   }
 }
-// staged tiles of one warp (32 rows): fp32 tile = 128-byte rows, SWIZZLE_128B; bf16 tile = 64-byte rows, SWIZZLE_64B.
-// `j4` = which group of 16 values of the thread's 32 (0 / 1).
+// staged tiles of one warp (32 rows x 32 values), 128-byte rows, SWIZZLE_128B: an fp32 tile, and the companion tile
+// [hb x 32 | lb x 32].  `j4` = which group of 16 values of the thread's 32 (0 / 1).
 __device__ __forceinline__ void t3_stage_f32(uint32_t tile, int lane, int j4, const float* v) {
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
@@ -267,11 +265,21 @@ __device__ __forceinline__ void t3_stage_f32(uint32_t tile, int lane, int j4, co
     st_shared_f4(tile + o, v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
   }
 }
-__device__ __forceinline__ void t3_stage_b16(uint32_t tile, int lane, int j4, const uint32_t* w) {
+__device__ __forceinline__ void t3_stage_b16(uint32_t tile, int lane, int j4, const uint32_t* w, bool is_lo) {
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
-    const uint32_t o = static_cast<uint32_t>(lane) * 64u + (static_cast<uint32_t>((j4 * 2 + c) ^ ((lane >> 1) & 3)) << 4);
+    const uint32_t o = static_cast<uint32_t>(lane) * 128u + (static_cast<uint32_t>(((is_lo ? 4 : 0) + j4 * 2 + c) ^ (lane & 7)) << 4);
     st_shared_u4(tile + o, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+  }
+}
+// companion of 16 channels starting at channel ch (a multiple of 16), row base `rowp` = &b[row * 2C]: direct stores
+__device__ __forceinline__ void t3_store_b16(__nv_bfloat16* rowp, int ch, const uint32_t* hb, const uint32_t* lb) {
+  uint4* dh = reinterpret_cast<uint4*>(rowp + 64 * (ch >> 5) + (ch & 16));
+  uint4* dl = reinterpret_cast<uint4*>(rowp + 64 * (ch >> 5) + 32 + (ch & 16));
+#pragma unroll
+  for (int v = 0; v < 2; ++v) {
+    dh[v] = make_uint4(hb[4 * v], hb[4 * v + 1], hb[4 * v + 2], hb[4 * v + 3]);
+    dl[v] = make_uint4(lb[4 * v], lb[4 * v + 1], lb[4 * v + 2], lb[4 * v + 3]);
   }
 }
 template <bool PAIR>
@@ -368,15 +376,15 @@ tf32_gate_kernel(const __grid_constant__ CUtensorMap map_hh, const __grid_consta
             const int rs = r + (tap - 1) * p.dilation;
             const int carry = (rs >= 0) ? rs / p.R : -((-rs + p.R - 1) / p.R);
             t3_load_4d<PAIR>(a_hi, &map_hh, full_bar(s), cblk * BK, t0 + carry, rs - carry * p.R, 0);
-            t3_load_b_4d<PAIR>(a_b, T3G_A_BYTES / 2, &map_hb, full_bar(s), p.C, cblk * BK, t0 + carry, rs - carry * p.R, 0);
+            t3_load_b_4d<PAIR>(a_b, &map_hb, full_bar(s), cblk * BK, t0 + carry, rs - carry * p.R, 0);
             t3_load_2d<PAIR>(b_hi, &map_w1h, full_bar(s), kb * BK, p.layer * 2 * p.C + bq);
-            t3_load_b_2d<PAIR>(b_b, T3G_B_BYTES / 2, &map_w1b, full_bar(s), 3 * p.C, kb * BK, p.layer * 2 * p.C + bq);
+            t3_load_b_2d<PAIR>(b_b, &map_w1b, full_bar(s), kb * BK, p.layer * 2 * p.C + bq);
           } else {
             const int kc = kb - p.kb_conv;
             t3_load_4d<PAIR>(a_hi, &map_ch, full_bar(s), kc * BK, t0, 0, 0);
-            t3_load_b_4d<PAIR>(a_b, T3G_A_BYTES / 2, &map_cb, full_bar(s), p.kb_cond * BK, kc * BK, t0, 0, 0);
+            t3_load_b_4d<PAIR>(a_b, &map_cb, full_bar(s), kc * BK, t0, 0, 0);
             t3_load_2d<PAIR>(b_hi, &map_vh, full_bar(s), kc * BK, p.wc_row0 + r * p.wc_rstride + bq);
-            t3_load_b_2d<PAIR>(b_b, T3G_B_BYTES / 2, &map_vb, full_bar(s), p.kb_cond * BK, kc * BK, p.wc_row0 + r * p.wc_rstride + bq);
+            t3_load_b_2d<PAIR>(b_b, &map_vb, full_bar(s), kc * BK, p.wc_row0 + r * p.wc_rstride + bq);
           }
         }
         __syncwarp();
@@ -433,7 +441,7 @@ tf32_gate_kernel(const __grid_constant__ CUtensorMap map_hh, const __grid_consta
     // stages its 32 x 32 (hi, lo) output tiles there (128-byte swizzled rows) and writes them with two TMA stores
     // instead of 16 row-strided 16-byte stores per thread (32 half-filled sectors per instruction).
     const bool stage_out = !LAST && EW == 16 && n_items <= item_step;
-    const uint32_t stg_hi = smem_base + static_cast<uint32_t>(we) * 8192u, stg_hb = stg_hi + 4096u, stg_lb = stg_hi + 6144u;
+    const uint32_t stg_hi = smem_base + static_cast<uint32_t>(we) * 8192u, stg_b = stg_hi + 4096u;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     uint32_t n = 0;
@@ -487,19 +495,13 @@ tf32_gate_kernel(const __grid_constant__ CUtensorMap map_hh, const __grid_consta
             t3_split16(a, valid, sp);
             if (stage_out) {
               t3_stage_f32(stg_hi, lane, g2, sp.hi);
-              t3_stage_b16(stg_hb, lane, g2, sp.hb);
-              t3_stage_b16(stg_lb, lane, g2, sp.lb);
+              t3_stage_b16(stg_b, lane, g2, sp.hb, false);
+              t3_stage_b16(stg_b, lane, g2, sp.lb, true);
             } else {
               float4* dh = reinterpret_cast<float4*>(p.acts_hi + m * p.C + q * 128 + ch0);
-              uint4* db = reinterpret_cast<uint4*>(p.acts_b + m * 2 * p.C + q * 128 + ch0);
-              uint4* dl = reinterpret_cast<uint4*>(p.acts_b + m * 2 * p.C + p.C + q * 128 + ch0);
 #pragma unroll
               for (int v = 0; v < 4; ++v) dh[v] = make_float4(sp.hi[4 * v], sp.hi[4 * v + 1], sp.hi[4 * v + 2], sp.hi[4 * v + 3]);
-#pragma unroll
-              for (int v = 0; v < 2; ++v) {
-                db[v] = make_uint4(sp.hb[4 * v], sp.hb[4 * v + 1], sp.hb[4 * v + 2], sp.hb[4 * v + 3]);
-                dl[v] = make_uint4(sp.lb[4 * v], sp.lb[4 * v + 1], sp.lb[4 * v + 2], sp.lb[4 * v + 3]);
-              }
+              t3_store_b16(p.acts_b + m * 2 * p.C, q * 128 + ch0, sp.hb, sp.lb);
             }
           }
         }
@@ -509,8 +511,7 @@ tf32_gate_kernel(const __grid_constant__ CUtensorMap map_hh, const __grid_consta
         __syncwarp();
         if (lane == 0) {
           tma_store_4d(&smap_hi, stg_hi, q * 128 + cg * CH, t0 + quarter * 32, r, 0);
-          tma_store_4d(&smap_b, stg_hb, q * 128 + cg * CH, t0 + quarter * 32, r, 0);
-          tma_store_4d(&smap_b, stg_lb, p.C + q * 128 + cg * CH, t0 + quarter * 32, r, 0);
+          tma_store_4d(&smap_b, stg_b, 2 * (q * 128 + cg * CH), t0 + quarter * 32, r, 0);
           bulk_commit();
         }
       }
@@ -632,9 +633,9 @@ tf32_res_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
           const uint32_t a_hi = smem_base + s * T3R_STAGE_BYTES, a_b = a_hi + T3_A_BYTES;
           const uint32_t b_hi = a_b + T3_A_BYTES, b_b = b_hi + T3R_B_BYTES;
           t3_load_4d<PAIR>(a_hi, &map_ah, full_bar(s), kb * T3_BK, t0, r, 0);
-          t3_load_b_4d<PAIR>(a_b, T3_A_BYTES / 2, &map_ab, full_bar(s), p.C, kb * T3_BK, t0, r, 0);
+          t3_load_b_4d<PAIR>(a_b, &map_ab, full_bar(s), kb * T3_BK, t0, r, 0);
           t3_load_2d<PAIR>(b_hi, &map_w2h, full_bar(s), kb * T3_BK, p.layer * p.C + bq);
-          t3_load_b_2d<PAIR>(b_b, T3R_B_BYTES / 2, &map_w2b, full_bar(s), p.C, kb * T3_BK, p.layer * p.C + bq);
+          t3_load_b_2d<PAIR>(b_b, &map_w2b, full_bar(s), kb * T3_BK, p.layer * p.C + bq);
         }
         __syncwarp();
       }
@@ -689,8 +690,7 @@ tf32_res_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
     constexpr bool PREFETCH = CH <= 32;
     const bool stage_out = EW == 16 && n_items <= item_step;   // see tf32_gate_kernel
     // per warp: h_hi and the exact h_lo (fp32: the next residual add reads h = hi + lo) and the BF16 MMA companions
-    const uint32_t stg_hi = smem_base + static_cast<uint32_t>(we) * 12288u, stg_lo = stg_hi + 4096u, stg_hb = stg_hi + 8192u,
-                   stg_lb = stg_hi + 10240u;
+    const uint32_t stg_hi = smem_base + static_cast<uint32_t>(we) * 12288u, stg_lo = stg_hi + 4096u, stg_b = stg_hi + 8192u;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     uint32_t n = 0;
@@ -736,25 +736,18 @@ tf32_res_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
         if (stage_out) {
           t3_stage_f32(stg_hi, lane, g, sp.hi);
           t3_stage_f32(stg_lo, lane, g, sp.lo);
-          t3_stage_b16(stg_hb, lane, g, sp.hb);
-          t3_stage_b16(stg_lb, lane, g, sp.lb);
+          t3_stage_b16(stg_b, lane, g, sp.hb, false);
+          t3_stage_b16(stg_b, lane, g, sp.lb, true);
           return;
         }
         float4* dh = reinterpret_cast<float4*>(p.ho_hi + off);
         float4* dl = reinterpret_cast<float4*>(p.ho_lo + off);
-        const size_t offb = (m * 2 * p.C) + (off - m * p.C);
-        uint4* db = reinterpret_cast<uint4*>(p.ho_b + offb);
-        uint4* dlb = reinterpret_cast<uint4*>(p.ho_b + offb + p.C);
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
           dh[v] = make_float4(sp.hi[4 * v], sp.hi[4 * v + 1], sp.hi[4 * v + 2], sp.hi[4 * v + 3]);
           dl[v] = make_float4(sp.lo[4 * v], sp.lo[4 * v + 1], sp.lo[4 * v + 2], sp.lo[4 * v + 3]);
         }
-#pragma unroll
-        for (int v = 0; v < 2; ++v) {
-          db[v] = make_uint4(sp.hb[4 * v], sp.hb[4 * v + 1], sp.hb[4 * v + 2], sp.hb[4 * v + 3]);
-          dlb[v] = make_uint4(sp.lb[4 * v], sp.lb[4 * v + 1], sp.lb[4 * v + 2], sp.lb[4 * v + 3]);
-        }
+        t3_store_b16(p.ho_b + m * 2 * p.C, static_cast<int>(off - m * p.C), sp.hb, sp.lb);
       };
       if (PREFETCH) {
 #pragma unroll
@@ -781,8 +774,7 @@ tf32_res_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
         if (lane == 0) {
           tma_store_4d(&smap_hi, stg_hi, q * T3R_BN + cg * CH, t0 + quarter * 32, r, 0);
           tma_store_4d(&smap_lo, stg_lo, q * T3R_BN + cg * CH, t0 + quarter * 32, r, 0);
-          tma_store_4d(&smap_b, stg_hb, q * T3R_BN + cg * CH, t0 + quarter * 32, r, 0);
-          tma_store_4d(&smap_b, stg_lb, p.C + q * T3R_BN + cg * CH, t0 + quarter * 32, r, 0);
+          tma_store_4d(&smap_b, stg_b, 2 * (q * T3R_BN + cg * CH), t0 + quarter * 32, r, 0);
           bulk_commit();
         }
       }
@@ -821,11 +813,12 @@ __global__ void tf32_im2col_kernel(const float* __restrict__ mel, float* __restr
   if (valid && j < 4 && t - j >= 0) v = mel[(static_cast<size_t>(b) * geo.T + t - j) * n_mel + i];
   const float hi = tf32_rna(v);
   a_hi[idx] = hi;
-  a_b[static_cast<size_t>(row) * 2 * Kup + kk] = __float2bfloat16_rn(hi);
-  a_b[static_cast<size_t>(row) * 2 * Kup + Kup + kk] = __float2bfloat16_rn(v - hi);
+  __nv_bfloat16* bp = a_b + static_cast<size_t>(row) * 2 * Kup + 64 * (kk >> 5) + (kk & 31);   // A operand: [hb | lb] per K-block
+  bp[0] = __float2bfloat16_rn(hi);
+  bp[32] = __float2bfloat16_rn(v - hi);
 }
 
-// folded conditioning weights: in [(r, k), n] fp32 -> hi[(r*N + n)*K + k] (fp32) and b[(r*N + n)*2K + {k, K + k}] (bf16 hi | lo)
+// folded conditioning weights: in [(r, k), n] fp32 -> hi[(r*N + n)*K + k] (fp32) and the B-operand companion b[(r*N + n)*2K + ..]
 __global__ void fold_store_tf32_kernel(const float* __restrict__ in, float* __restrict__ o_hi, __nv_bfloat16* __restrict__ o_b,
                                        int R, int K, int N) {
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -836,8 +829,9 @@ __global__ void fold_store_tf32_kernel(const float* __restrict__ in, float* __re
   const float v = in[(static_cast<size_t>(r) * K + k) * N + n];
   const float hi = tf32_rna(v);
   o_hi[idx] = hi;
-  o_b[rn * 2 * K + k] = __float2bfloat16_rn(hi);
-  o_b[rn * 2 * K + K + k] = __float2bfloat16_rn(v - hi);
+  __nv_bfloat16* bp = o_b + rn * 2 * K + 64 * (k >> 5) + (k & 31);   // B operand: [lb | hb] per K-block
+  bp[0] = __float2bfloat16_rn(v - hi);
+  bp[32] = __float2bfloat16_rn(hi);
 }
 
 // ---- host side --------------------------------------------------------------------------------------------------
@@ -857,7 +851,7 @@ inline void make_map_f32(CUtensorMap* m, const void* ptr, int rank, const uint64
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) fail(WG_ERR_CUDA, "cuTensorMapEncodeTiled (fp32) failed with CUresult %d", (int)r);
 }
-// bf16 companion arrays [.., rows, 2K]: boxes of 32 elements (64-byte rows, SWIZZLE_64B)
+// bf16 companion arrays [.., rows, 2K]: boxes of 64 elements = one K-block (128-byte rows, SWIZZLE_128B)
 inline void make_map_b16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint32_t* box) {
   cuuint64_t gdim[4], gstr[3];
   cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
@@ -869,18 +863,18 @@ inline void make_map_b16(CUtensorMap* m, const void* ptr, int rank, const uint64
     if (i < rank - 1) gstr[i] = stride;
   }
   CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) fail(WG_ERR_CUDA, "cuTensorMapEncodeTiled (bf16 companion) failed with CUresult %d", (int)r);
 }
 inline void make_map_b16_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t K, uint32_t box_rows) {
   const uint64_t dims[2] = {2 * K, rows};
-  const uint32_t box[2] = {32, box_rows};
+  const uint32_t box[2] = {64, box_rows};
   make_map_b16(m, ptr, 2, dims, box);
 }
 inline void make_map_b16_4d(CUtensorMap* m, const void* ptr, uint64_t phases, uint64_t rows, uint64_t K, uint32_t box_rows = T3_BM) {
   const uint64_t dims[4] = {2 * K, rows, phases, 1};
-  const uint32_t box[4] = {32, box_rows, 1, 1};
+  const uint32_t box[4] = {64, box_rows, 1, 1};
   make_map_b16(m, ptr, 4, dims, box);
 }
 inline void make_map_f32_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
