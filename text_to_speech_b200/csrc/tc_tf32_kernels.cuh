@@ -4,7 +4,7 @@
 // read at most TF32 (10 explicit mantissa bits), so every fp32 operand x is split as
 //     x_hi = tf32(x)  (cvt.rna, kept in fp32 words)          x_lo = x - x_hi   (exact in fp32)
 // and every multiply is issued as three products, small terms first, into one fp32 TMEM accumulator:
-//     a_lo*b_hi + a_hi*b_lo   kind::f16 MMAs on a BF16 companion [.., 2K] = bf16(x_hi) | bf16(x_lo) of every operand
+//     a_lo*b_hi + a_hi*b_lo   kind::f16 MMAs on a BF16 companion [.., 2K] of every operand (per K-block of 32: hi x 32 | lo x 32)
 //                             (the cross terms are 2^-11 of the product: 8 mantissa bits carry them to ~2e-7)
 //     a_hi*b_hi               kind::tf32 MMAs
 // (the dropped a_lo*b_lo term is <= 2^-22 relative): the "fp32/3xTF32 mode" of BASELINE.json's north_star. The gate is
@@ -15,7 +15,7 @@
 // Two kernels per layer (the fp32 acts tile does not fit beside the operand ring):
 //   tf32_gate_kernel   item = (128-row tile, 256-column chunk q of the gate pre-activation = 128 tanh + 128 sigmoid
 //                      channels).  GEMM1 [128 x (3C + 320)] @ [(3C + 320) x 256] in K-blocks of 32; one pipeline stage =
-//                      [A_hi fp32 | A_hb | A_lb bf16][B_hi | B_hb | B_lb] (t3_mma_stage);
+//                      [A_hi fp32 | A_b bf16][B_hi | B_b], 128-byte rows (t3_mma_stage);
 //                      epilogue: gate, acts -> split -> HBM, skip/end fold into this chunk's OWN partial accumulator
 //                      acc8[q] (no cross-CTA race: the flow boundary sums the partials in a fixed order).
 //   tf32_res_kernel    item = (128-row tile, 128-column chunk of the residual half).  GEMM2 acts[128 x C] @ Wres;
@@ -367,7 +367,7 @@ tf32_gate_kernel(const __grid_constant__ CUtensorMap map_hh, const __grid_consta
         if (elect_one()) {
           if (leader) mbar_expect_tx(full_bar(s), (PAIR ? 2 : 1) * T3G_STAGE_BYTES);   // PAIR: the bytes of both CTAs
           const int bq = q * T3G_BN + (PAIR ? static_cast<int>(rank) * (T3G_BN / 2) : 0);   // first B row this CTA loads
-          // stage = [A_hi | A_hb | A_lb][B_hi | B_hb | B_lb]  (t3_mma_stage)
+          // stage = [A_hi | A_b][B_hi | B_b]  (t3_mma_stage)
           const uint32_t a_hi = smem_base + s * T3G_STAGE_BYTES, a_b = a_hi + T3G_A_BYTES;
           const uint32_t b_hi = a_b + T3G_A_BYTES, b_b = b_hi + T3G_B_BYTES;
           if (kb < p.kb_conv) {
