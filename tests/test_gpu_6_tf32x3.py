@@ -63,7 +63,7 @@ def test_tf32x3_intermediates_against_oracle_taps(lib_built):
     eng.close()
 
 
-@pytest.mark.parametrize("B,T", [(1, 1), (2, 5), (3, 37), (2, 150)])
+@pytest.mark.parametrize("B,T", [(1, 1), (2, 5), (3, 37), (2, 150), (4, 860)])      # 4 x 860: many waves of CTA pairs, 10 s utterances
 def test_tf32x3_shapes_against_fp32_engine_and_oracle(lib_built, B, T):
     hp = WaveGlowHParams()
     w = generate_weights(hp, 31, bias_std=0.05)
