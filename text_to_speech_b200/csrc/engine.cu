@@ -255,7 +255,7 @@ Ws carve(const wg_engine* e, int B, int T, const Ragged* rg = nullptr) {
     w.t3_hb0 = take(M * e->C * 4); w.t3_hb1 = take(M * e->C * 4);
     w.t3_ahi = take(M * e->C * 4); w.t3_ab = take(M * e->C * 4);
     w.t3_chi = take(rows1 * e->Kup * 4); w.t3_cb = take(rows1 * e->Kup * 4);
-    w.t3_sync = take(2 * sizeof(unsigned int));   // grid-barrier words of tf32_flow_kernel: per CALL, a handle may run two at once
+    w.t3_sync = take(T3F_SYNC_WORDS * sizeof(unsigned int));   // barrier words of tf32_flow_kernel: per CALL, a handle may run two at once
     if (rg) {
       w.g_off = take((size_t)B * 4);
       w.g_len = take((size_t)B * 4);
@@ -408,7 +408,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
     flow3 = e->t3_flow;
     flow3.sync = reinterpret_cast<unsigned int*>(base + w.t3_sync);
     if (e->t3_flow_policy != 0 && tf32_flow_fits(plan3, flow3.max_pairs, c.n_layers)) {
-      CK(cudaMemsetAsync(flow3.sync, 0, 2 * sizeof(unsigned int), st));   // arrivals = 0; the barrier re-arms itself afterwards
+      CK(cudaMemsetAsync(flow3.sync, 0, T3F_SYNC_WORDS * sizeof(unsigned int), st));   // arrivals = 0; the barriers re-arm themselves afterwards
       e->launches++;
     }
     e->launches += tf32_upsample(plan3, mel, st);

@@ -18,6 +18,7 @@
 namespace wg {
 
 constexpr int T3F_MAX_LAYERS = 16;
+constexpr int T3F_SYNC_WORDS = 2 + 2 * 128;          // grid barrier + one barrier per tile pair (at most one CTA pair each: <= 74)
 constexpr int T3F_EW = 16, T3F_EPI_THREADS = T3F_EW * 32, T3F_THREADS = 64 + T3F_EPI_THREADS;
 using T3FG = T3G<32, true>;                      // gate ring: 3 stages of 64 KB
 using T3FR = T3RG<true>;                         // residual ring: 4 stages of 48 KB (the same shared memory)
@@ -28,7 +29,7 @@ constexpr int T3F_OFF_B2 = T3F_OFF_B1 + 256 * 4;                 // [128] residu
 constexpr int T3F_OFF_O8 = T3F_OFF_B2 + T3R_BN * 4;              // fold partials of column groups 1..3
 constexpr int T3F_OFF_BARS = T3F_OFF_O8 + 3 * T3_BM * 8 * 4;
 constexpr int T3F_NBARS = 2 * T3FG::STAGES + 2 * T3FR::STAGES + 2;
-constexpr int T3F_SMEM = T3F_OFF_BARS + T3F_NBARS * 8 + 16;
+constexpr int T3F_SMEM = T3F_OFF_BARS + T3F_NBARS * 8 + 16;      // + TMEM slot, 2 generation words
 static_assert(T3F_SMEM <= 232448, "shared memory budget");
 
 struct Tf32FlowMaps {
@@ -51,7 +52,7 @@ struct Tf32FlowParams {
   const float* wse[T3F_MAX_LAYERS];
   const float* h_hi[2];            // residual stream, generic reads of the residual epilogue
   const float* h_lo[2];
-  unsigned int* sync;              // [0] arrivals of the running barrier, [1] generation (completed barriers)
+  unsigned int* sync;              // grid barrier: [0] arrivals, [1] generation; tile-pair barriers: [2 + 2 i], [3 + 2 i]
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
@@ -124,14 +125,21 @@ tf32_flow_kernel(const __grid_constant__ Tf32FlowMaps maps, const __grid_constan
     tmem2_relinquish();
   }
   // the generation the barrier stands at when this launch starts (no CTA arrives before the cluster sync below)
+  // Two barriers: the GRID one (words 0, 1; h of a layer complete everywhere -- the taps of the next layer read other tiles
+  // and other phases) and one per TILE PAIR (words 2 + 2 * tile pair ..; acts complete -- the residual GEMM reads all C
+  // channels of its OWN rows, written by the CTA pairs of that tile pair's chunks only).
   volatile uint32_t* s_gen0 = tmem_slot + 1;
-  if (threadIdx.x == 0) *s_gen0 = ld_acquire_gpu(fp.sync + 1);
+  unsigned int* const tsync = fp.sync + 2 + 2 * ((blockIdx.x >> 1) / (2 * p.C / T3G_BN));
+  if (threadIdx.x == 0) {
+    s_gen0[0] = ld_acquire_gpu(fp.sync + 1);
+    s_gen0[1] = ld_acquire_gpu(tsync + 1);
+  }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const unsigned int gen0 = *s_gen0;
+  const unsigned int gen0 = s_gen0[0], tgen0 = s_gen0[1];
   const unsigned int n_ctas = gridDim.x;
 
   // this CTA's item, the same in every layer: pair item -> (chunk q, phase r, first row t0 of this CTA's tile)
@@ -157,7 +165,7 @@ tf32_flow_kernel(const __grid_constant__ Tf32FlowMaps maps, const __grid_constan
       const int layer = fp.layer0 + l, dil = fp.dilation[l];
       if (l > 0) {
         const long long tq = tm ? clock64() : 0;
-        if (lane == 0) t3f_grid_wait(fp.sync, gen0 + 2u * l);   // every CTA's h of layer l-1 is in memory
+        if (lane == 0) t3f_grid_wait(fp.sync, gen0 + l);   // every CTA's h of layer l-1 is in memory
         __syncwarp();
         if (tm) t_gw += clock64() - tq;
       }
@@ -190,7 +198,7 @@ tf32_flow_kernel(const __grid_constant__ Tf32FlowMaps maps, const __grid_constan
       }
       if (last) break;
       const long long tq1 = tm ? clock64() : 0;
-      if (lane == 0) t3f_grid_wait(fp.sync, gen0 + 2u * l + 1u);   // every CTA's acts of layer l are in memory
+      if (lane == 0) t3f_grid_wait(tsync, tgen0 + l + 1u);   // the acts of this tile pair (all chunks) are in memory
       __syncwarp();
       if (tm) t_gw1 += clock64() - tq1;
       const int b2q = q * T3R_BN + static_cast<int>(rank) * (T3R_BN / 2);
@@ -355,7 +363,7 @@ tf32_flow_kernel(const __grid_constant__ Tf32FlowMaps maps, const __grid_constan
       const long long te2 = tm ? clock64() : 0;
       if (lane == 0) bulk_wait0();
       asm volatile("bar.sync 3, %0;" ::"n"(T3F_EPI_THREADS) : "memory");
-      if (tid == 0) t3f_grid_arrive(fp.sync, n_ctas);
+      if (tid == 0) t3f_grid_arrive(tsync, 2u * static_cast<unsigned int>(n_chunks));
       const long long te3 = tm ? clock64() : 0;
       // ---- residual epilogue (tf32_res_kernel): the old value of h is fetched while the residual GEMM runs
       const size_t off0 = m * p.C + q * T3R_BN + cg * CH;
