@@ -137,6 +137,10 @@ def test_tf32x3_kernel_variants_give_the_same_bits(lib_built, monkeypatch, B, T,
     again = _run(eng, mel, z, 0.6, lengths=lengths)  # the grid barrier re-arms itself
     assert np.array_equal(ref, again)
     eng.close()
+    monkeypatch.setenv("WG_TF32_FLOW", "2")          # the device refuses the cooperative launch -> per-layer kernels, same bits
+    eng = _engine(hp, w)
+    assert np.array_equal(ref, _run(eng, mel, z, 0.6, lengths=lengths)) and eng.last_launch_count > 150
+    eng.close()
     assert np.isfinite(ref).all()
     for k, o in outs.items():
         assert np.array_equal(ref, o), k

@@ -489,6 +489,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
     }
   };
 
+  bool flow_ok = tf32 && e->t3_flow_policy != 0;   // tf32x3: a flow as ONE persistent launch where the call is one wave
   for (int k = F - 1; k >= 0; --k) {
     const FlowW& fw = e->flows[k];
     if (k == stop_flow && stop_layer == -1) { dump(); return; }
@@ -496,7 +497,7 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
       const LayerW& lw = e->layers[k * c.n_layers + i];
       const int d = 1 << i;
       const bool last = i == c.n_layers - 1;
-      if (tf32 && i == 0 && e->t3_flow_policy != 0 && !(k == stop_flow && stop_layer >= 0) &&
+      if (tf32 && i == 0 && flow_ok && !(k == stop_flow && stop_layer >= 0) &&
           tf32_flow_fits(plan3, flow3.max_pairs, c.n_layers)) {
         // single-wave call: the whole flow as ONE persistent launch (grid barriers instead of kernel boundaries)
         const float *b1s[T3F_MAX_LAYERS], *b2s[T3F_MAX_LAYERS], *wses[T3F_MAX_LAYERS];
@@ -505,12 +506,19 @@ void run_infer(wg_engine* e, const float* mel, const float* z, float sigma, int 
           b1s[j] = lj.b1_pm; b2s[j] = lj.b2; wses[j] = lj.wse_d;
         }
         prof_mark();
-        if (e->profiling) e->ev_count.push_back(c.n_layers);
-        e->launches += tf32_wn_flow(plan3, flow3, k * c.n_layers, c.n_layers, hcur, b1s, b2s, wses, st, e->timing);
-        prof_mark();
-        if ((c.n_layers - 1) & 1) hcur ^= 1;
-        e->last_flow_kernel = 1;
-        break;
+        const int nl = tf32_wn_flow(plan3, flow3, k * c.n_layers, c.n_layers, hcur, b1s, b2s, wses, st, e->timing);
+        if (nl > 0) {
+          if (e->profiling) e->ev_count.push_back(c.n_layers);
+          e->launches += nl;
+          prof_mark();
+          if ((c.n_layers - 1) & 1) hcur ^= 1;
+          e->last_flow_kernel = 1;
+          break;
+        }
+        // the device would not take the cooperative launch (SMs held by another context, MPS limits ...): this and the
+        // remaining flows run on the per-layer kernels -- same bits
+        flow_ok = false;
+        if (e->profiling) --e->ev_used;
       }
       if (tf32) {
         // one event pair per flow around its back-to-back layer launches (gate + residual kernel per layer)
@@ -933,6 +941,7 @@ void build_engine(wg_engine* e, const wg_config* cfg, const wg_tensor* tensors, 
     if (const char* pr = std::getenv("WG_PAIR")) e->pair_policy = std::atoi(pr);
     e->t3_flow.max_pairs = std::min(tf32_flow_init(), e->sm_count / 2);
     if (const char* fl = std::getenv("WG_TF32_FLOW")) e->t3_flow_policy = std::atoi(fl);
+    e->t3_flow.refuse = e->t3_flow_policy == 2;
     // Nsight Compute refuses a cooperative launch of a cluster kernel ("LaunchFailed", which ends the profiled process):
     // under its injection the flow kernel is launched plainly -- ncu serialises kernels, so co-residency holds anyway.
     if (std::getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || std::getenv("NV_NSIGHT_INJECTION_PORT_BASE")) e->t3_flow.cooperative = false;

@@ -440,6 +440,7 @@ struct Tf32FlowState {
   unsigned int* sync = nullptr;   // device: [arrivals, generation]
   int max_pairs = 0;              // co-resident CTA pairs of tf32_flow_kernel (0: unavailable)
   bool cooperative = true;        // launch attribute: all CTAs co-resident or the launch fails (WG_TF32_COOP=0: plain launch)
+  bool refuse = false;            // WG_TF32_FLOW=2 (tests): behave as if the device refused the cooperative launch
 };
 
 inline int tf32_flow_init() {
@@ -466,9 +467,11 @@ inline bool tf32_flow_fits(const Tf32Plan& pl, int max_pairs, int n_layers) {
   return items <= max_pairs;
 }
 
-// All `n_layers` layers of one flow (dilation 2^i). Returns the launch count (1).
+// All `n_layers` layers of one flow (dilation 2^i). Returns the launch count (1), or 0 when the device refuses the
+// cooperative launch (not all CTAs can be co-resident right now): the caller falls back to the per-layer kernels.
 inline int tf32_wn_flow(const Tf32Plan& pl, const Tf32FlowState& fs, int layer0, int n_layers, int hcur0, const float* const* b1,
                         const float* const* b2, const float* const* wse, cudaStream_t st, unsigned long long* timing = nullptr) {
+  if (fs.refuse) return 0;
   Tf32FlowMaps m;
   for (int i = 0; i < 2; ++i) {
     m.hh[i] = pl.m_h_hi[i]; m.hb[i] = pl.m_h_b[i];
@@ -503,7 +506,12 @@ inline int tf32_wn_flow(const Tf32Plan& pl, const Tf32FlowState& fs, int layer0,
   attr[1].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = fs.cooperative ? 2 : 1;
-  WG_CK(cudaLaunchKernelEx(&cfg, tf32_flow_kernel, m, fp));
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, tf32_flow_kernel, m, fp);
+  if (le == cudaErrorCooperativeLaunchTooLarge || le == cudaErrorLaunchOutOfResources) {
+    cudaGetLastError();
+    return 0;
+  }
+  WG_CK(le);
   return 1;
 }
 
